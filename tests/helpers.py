@@ -1,0 +1,39 @@
+"""Shared test helpers: golden loading, error metrics, seeded models."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    cfg = eval(str(z["cfg"]))          # repr(dict) of plain ints/floats written by oracle/make_golden.py
+    return z, cfg
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b|  - the 'relative' error of north_star's tolerance, tensor-wise."""
+    a = torch.as_tensor(np.asarray(a)).double() if not torch.is_tensor(a) else a.detach().double().cpu()
+    b = torch.as_tensor(np.asarray(b)).double() if not torch.is_tensor(b) else b.detach().double().cpu()
+    denom = b.abs().max().item()
+    return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
+
+
+def grad_summary(g, nsample=64):
+    g = g.detach().double().reshape(-1).cpu()
+    idx = (torch.arange(nsample, dtype=torch.int64) * (g.numel() - 1)) // (nsample - 1)
+    return np.concatenate([[g.norm().item(), g.abs().max().item(), g.sum().item()], g[idx].numpy()])
+
+
+def params_of(module, requires_grad=True, dtype=None, device=None):
+    out = {}
+    for k, v in module.state_dict().items():
+        t = v.detach().clone()
+        if dtype is not None:
+            t = t.to(dtype)
+        if device is not None:
+            t = t.to(device)
+        out[k] = t.requires_grad_(requires_grad)
+    return out
