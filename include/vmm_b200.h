@@ -1,0 +1,101 @@
+/* vmm_b200.h - C ABI of libvmm_b200.so, the sm_100a implementation of the VMM / Neural-EM
+ * latent-view decomposition hot path of hjjpku/multi_view_sort.
+ *
+ * The reference has no FFI: its boundary is the Python call surface the trainer uses
+ * (SURVEY.md §8b).  Each entry point below names the reference code it replaces
+ * (paths relative to the reference root).  Conventions:
+ *   - plain C types only: device pointers, sizes, a cudaStream_t passed as void*;
+ *   - the CALLER owns every buffer, including workspaces (query the *_bytes functions);
+ *   - return 0 on success or a negative VMM_E_* code; never throws, never aborts;
+ *     vmm_last_error() returns a per-thread message for the last failure;
+ *   - no global mutable state besides a per-device attribute cache: safe to call from
+ *     several host threads, one stream per call;
+ *   - all work is enqueued on `stream`; nothing synchronises the device.
+ *
+ * "Operand planes": matrices consumed by the tensor cores are bf16.  planes == 1 is the
+ * bf16 mode; planes == 2 stores every operand as hi = bf16(v), lo = bf16(v - hi) and every
+ * contraction runs three error-compensated passes (lo*hi + hi*lo + hi*hi) with fp32
+ * accumulation, which reproduces the reference's fp32 arithmetic to ~1e-5.
+ */
+#ifndef VMM_B200_H_
+#define VMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMM_ABI_VERSION 1
+
+#define VMM_E_INVALID (-1)     /* bad argument / unsupported shape */
+#define VMM_E_CUDA (-2)        /* a CUDA runtime/driver call failed */
+#define VMM_E_UNSUPPORTED (-3) /* valid request the library does not implement */
+#define VMM_E_WORKSPACE (-4)   /* caller-provided workspace too small */
+
+#define VMM_MAX_SEGMENTS 8
+
+int vmm_version(void);
+const char* vmm_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Tensor-core contraction (replaces every nn.Linear / GRUCell matmul on the path:
+ * train_nem.py:171-185, 226-241; cuBLAS sgemm in the reference).
+ *
+ *   C[M,N] (+)= sum_s A_s[M,K_s] * B_s[N,K_s]^T  (+ bias[N])
+ *
+ * a_mn_major == 0: A_s is stored [M][K_s] (K contiguous, row pitch lda elements);
+ * a_mn_major == 1: A_s is stored [K_s][M] (M contiguous, row pitch lda) - the layout a
+ * weight-gradient contraction sees.  Same for B with N.  All pointers bf16, 16-byte
+ * aligned, pitches multiples of 8 elements.  accumulate != 0 adds into C with atomics
+ * (required when splits > 1).  splits <= 0 lets the library choose.
+ * ------------------------------------------------------------------------------------- */
+typedef struct vmm_gemm_seg {
+  const void* a; /* bf16 */
+  long long lda;
+  const void* b; /* bf16 */
+  long long ldb;
+  long long k;
+} vmm_gemm_seg;
+
+int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
+                  float* C, long long ldc, const float* bias, int accumulate, int splits, void* stream);
+
+/* Same contract computed by a plain one-thread-per-output CUDA kernel (no tensor cores):
+ * the on-device cross-check used by the GPU tests.  Not used by the product path. */
+int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
+                   float* C, long long ldc, const float* bias, int accumulate, void* stream);
+
+/* fp32 -> bf16 operand planes (lo may be NULL for planes == 1). */
+int vmm_split_planes(const float* src, long long n, void* hi, void* lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * E-step fused into the dec3 contraction (replaces NEM.dec3 + compute_em_probabilities,
+ * train_nem.py:185, 241-263, and the row sums of compute_outer_loss,
+ * tools/NEM_utilities.py:98-128).  pred = z W3^T + b3 is never written to memory.
+ *
+ *   rows = B*K*M (row r = (b*K + k)*M + m), z planes [rows, zk], W3 planes [D, zk].
+ *   x: features [B*M, D] (float, or bf16 when x_is_bf16), row pitch ldx.
+ *   part_e [rows, nblk]: sum over the n-block's columns of exp(-(x-pred)^2 / (2 sigma^2))
+ *   part_sq / part_pp (nullable): same for (x-pred)^2 and pred^2.
+ *   nblk = vmm_estep_num_blocks(D).
+ * ------------------------------------------------------------------------------------- */
+int vmm_estep_num_blocks(int D);
+int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo,
+                      const void* w3_hi, const void* w3_lo, const float* b3, const void* x, int x_is_bf16,
+                      long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
+                      float* part_pp, void* stream);
+
+/* Backward of the fused E-step: recomputes pred tile by tile and writes
+ *   dpred[r,d] = delta*(alpha[r]*exp(-delta^2/(2 sigma^2)) - beta[r]) + kappa[r]*pred,  delta = x - pred
+ * as bf16 operand planes [rows, D] (dpred_lo NULL when planes == 1; kappa may be NULL). */
+int vmm_estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo,
+                       const void* w3_hi, const void* w3_lo, const float* b3, const void* x, int x_is_bf16,
+                       long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
+                       const float* beta, const float* kappa, void* dpred_hi, void* dpred_lo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMM_B200_H_ */

@@ -1,0 +1,329 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map construction, tile/split planning, launch,
+// and the extern "C" entry points vmm_gemm_bf16 / vmm_estep_forward / vmm_estep_backward.
+#include <mutex>
+
+#include "common.h"
+#include "gemm.cuh"
+#include "internal.h"
+
+namespace vmm {
+
+// ---- error text / device attributes -----------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int device_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ---- TMA descriptors ----------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor [outer][inner] with `pitch` elements between outer rows; 128-byte swizzle;
+// out-of-bounds elements read as zero (this is what pads ragged M, N and K edges).
+static int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long pitch,
+                          int box_inner, int box_outer) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return VMM_E_CUDA;
+  }
+  VMM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "operand pointer %p is not 16-byte aligned", ptr);
+  VMM_REQUIRE(pitch % 8 == 0, "operand pitch %lld is not a multiple of 8 bf16 elements", pitch);
+  VMM_REQUIRE(inner > 0 && outer > 0, "empty operand (%lld x %lld)", inner, outer);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner %lld outer %lld pitch %lld)", static_cast<int>(r),
+              inner, outer, pitch);
+    return VMM_E_CUDA;
+  }
+  return 0;
+}
+
+// ---- launch -------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, int EPI, typename XT, int OPL>
+static int launch_one(const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, XT, OPL>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
+    return VMM_E_CUDA;
+  }
+  const int total_work = p.num_m_blk * p.num_n_blk * p.splits;
+  const int grid = total_work < device_sm_count() ? total_work : device_sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI, typename XT, int OPL>
+static int launch_major(const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t s) {
+  if constexpr (EPI == EPI_ESTEP || EPI == EPI_EBWD) {
+    return launch_one<256, false, false, EPI, XT, OPL>(p, s);
+  } else {
+    if (!a_mn && !b_mn) return launch_one<256, false, false, EPI, XT, OPL>(p, s);
+    if (!a_mn && b_mn) return launch_one<256, false, true, EPI, XT, OPL>(p, s);
+    if (a_mn && !b_mn) return launch_one<256, true, false, EPI, XT, OPL>(p, s);
+    return launch_one<256, true, true, EPI, XT, OPL>(p, s);
+  }
+}
+
+static int fill_common(GemmParams& p, int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool b_mn,
+                       int splits_req, bool allow_split) {
+  constexpr int BN = 256;
+  VMM_REQUIRE(M > 0 && N > 0, "empty problem M=%d N=%d", M, N);
+  VMM_REQUIRE(nseg >= 1 && nseg <= VMM_MAX_SEG, "nseg=%d outside [1,%d]", nseg, VMM_MAX_SEG);
+  memset(&p, 0, sizeof(p));
+  p.M = M;
+  p.N = N;
+  p.nseg = nseg;
+  p.num_m_blk = ceil_div(M, BM);
+  p.num_n_blk = ceil_div(N, BN);
+  int total = 0;
+  for (int s = 0; s < nseg; ++s) {
+    const vmm_gemm_seg& g = segs[s];
+    VMM_REQUIRE(g.k > 0 && g.a && g.b, "segment %d is empty", s);
+    if (!a_mn) VMM_TRY(make_tmap_bf16(&p.tma_a[s], g.a, g.k, M, g.lda, BK, BM));
+    else       VMM_TRY(make_tmap_bf16(&p.tma_a[s], g.a, M, g.k, g.lda, 64, BK));
+    if (!b_mn) VMM_TRY(make_tmap_bf16(&p.tma_b[s], g.b, g.k, N, g.ldb, BK, BN));
+    else       VMM_TRY(make_tmap_bf16(&p.tma_b[s], g.b, N, g.k, g.ldb, 64, BK));
+    total += ceil_div(g.k, BK);
+    p.kb_end[s] = total;
+  }
+  for (int s = nseg; s < VMM_MAX_SEG; ++s) p.kb_end[s] = 0x7fffffff;
+  p.total_kb = total;
+  int splits = 1;
+  if (allow_split) {
+    if (splits_req > 0) {
+      splits = splits_req;
+    } else {
+      // fill the machine when there are fewer output tiles than SMs and K is long
+      const int tiles = p.num_m_blk * p.num_n_blk;
+      const int sms = device_sm_count();
+      if (tiles < sms) splits = sms / tiles;
+      const int max_by_k = total / 8 > 0 ? total / 8 : 1;   // keep >= 8 k-blocks per split
+      if (splits > max_by_k) splits = max_by_k;
+    }
+    if (splits > total) splits = total;
+    if (splits < 1) splits = 1;
+  }
+  p.splits = splits;
+  return 0;
+}
+
+int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool b_mn, float* C, long long ldc,
+              const float* bias, bool accumulate, int splits, cudaStream_t stream) {
+  GemmParams p;
+  VMM_TRY(fill_common(p, M, N, nseg, segs, a_mn, b_mn, splits, accumulate));
+  VMM_REQUIRE(C != nullptr && ldc >= N, "bad C / ldc");
+  VMM_REQUIRE(!(accumulate && bias), "bias cannot be combined with accumulate");
+  p.C = C;
+  p.ldc = ldc;
+  p.bias = bias;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0 &&
+              (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) ? 1 : 0;
+  if (accumulate) return launch_major<EPI_RED, float, 1>(p, a_mn, b_mn, stream);
+  return launch_major<EPI_STORE, float, 1>(p, a_mn, b_mn, stream);
+}
+
+static int estep_common(GemmParams& p, vmm_gemm_seg* segs, int rows, int D, int zk, int planes, const void* z_hi,
+                        const void* z_lo, const void* w3_hi, const void* w3_lo, const float* b3, const void* x,
+                        int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma) {
+  VMM_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
+  VMM_REQUIRE(z_hi && w3_hi && b3 && x, "null operand");
+  VMM_REQUIRE(planes == 1 || (z_lo && w3_lo), "planes == 2 needs the lo planes");
+  VMM_REQUIRE(D % 8 == 0 && zk % 8 == 0, "D and zk must be multiples of 8");
+  VMM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(b3) & 15) == 0 &&
+                  ldx % 8 == 0, "x / b3 must be 16-byte aligned, ldx a multiple of 8");
+  VMM_REQUIRE(sigma > 0.f && k_latent > 0 && m_views > 0 && rows % (k_latent * m_views) == 0, "bad E-step geometry");
+  int nseg = 0;
+  if (planes == 2) {
+    segs[nseg++] = {z_lo, zk, w3_hi, zk, zk};
+    segs[nseg++] = {z_hi, zk, w3_lo, zk, zk};
+  }
+  segs[nseg++] = {z_hi, zk, w3_hi, zk, zk};
+  VMM_TRY(fill_common(p, rows, D, nseg, segs, false, false, 1, false));
+  p.bias = b3;
+  p.x = x;
+  p.ldx = ldx;
+  p.km = k_latent * m_views;
+  p.mv = m_views;
+  p.exp_scale = -1.4426950408889634f / (2.f * sigma * sigma);
+  (void)x_is_bf16;
+  return 0;
+}
+
+int estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
+                  const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
+                  int m_views, float sigma, float* part_e, float* part_sq, float* part_pp, cudaStream_t stream) {
+  GemmParams p;
+  vmm_gemm_seg segs[3];
+  VMM_TRY(estep_common(p, segs, rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent,
+                       m_views, sigma));
+  VMM_REQUIRE(part_e != nullptr, "part_e is null");
+  p.part_e = part_e;
+  p.part_sq = part_sq;
+  p.part_pp = part_pp;
+  if (x_is_bf16) return launch_major<EPI_ESTEP, __nv_bfloat16, 1>(p, false, false, stream);
+  return launch_major<EPI_ESTEP, float, 1>(p, false, false, stream);
+}
+
+int estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
+                   const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
+                   int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
+                   void* dpred_hi, void* dpred_lo, cudaStream_t stream) {
+  GemmParams p;
+  vmm_gemm_seg segs[3];
+  VMM_TRY(estep_common(p, segs, rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent,
+                       m_views, sigma));
+  VMM_REQUIRE(alpha && beta && dpred_hi && (planes == 1 || dpred_lo), "null E-step backward argument");
+  VMM_REQUIRE((reinterpret_cast<uintptr_t>(dpred_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(dpred_lo) & 15) == 0,
+              "dpred planes must be 16-byte aligned");
+  p.row_alpha = alpha;
+  p.row_beta = beta;
+  p.row_kappa = kappa;
+  p.out_hi = static_cast<__nv_bfloat16*>(dpred_hi);
+  p.out_lo = static_cast<__nv_bfloat16*>(dpred_lo);
+  p.ldo = D;
+  if (planes == 2) {
+    if (x_is_bf16) return launch_major<EPI_EBWD, __nv_bfloat16, 2>(p, false, false, stream);
+    return launch_major<EPI_EBWD, float, 2>(p, false, false, stream);
+  }
+  if (x_is_bf16) return launch_major<EPI_EBWD, __nv_bfloat16, 1>(p, false, false, stream);
+  return launch_major<EPI_EBWD, float, 1>(p, false, false, stream);
+}
+
+// ---- plain CUDA cross-check (tests only) ---------------------------------------------------
+__global__ void gemm_check_kernel(int M, int N, int nseg, vmm_gemm_seg s0, vmm_gemm_seg s1, vmm_gemm_seg s2,
+                                  vmm_gemm_seg s3, int a_mn, int b_mn, float* C, long long ldc, const float* bias,
+                                  int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  const vmm_gemm_seg segs[4] = {s0, s1, s2, s3};
+  float acc = 0.f;
+  for (int s = 0; s < nseg; ++s) {
+    const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(segs[s].a);
+    const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(segs[s].b);
+    for (long long k = 0; k < segs[s].k; ++k) {
+      const float av = __bfloat162float(a_mn ? a[k * segs[s].lda + m] : a[m * segs[s].lda + k]);
+      const float bv = __bfloat162float(b_mn ? b[k * segs[s].ldb + n] : b[n * segs[s].ldb + k]);
+      acc = fmaf(av, bv, acc);
+    }
+  }
+  float* dst = C + static_cast<long long>(m) * ldc + n;
+  if (accumulate) *dst += acc;
+  else *dst = acc + (bias ? bias[n] : 0.f);
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ src, long long n, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+int split_planes(const float* src, long long n, void* hi, void* lo, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  VMM_REQUIRE(src && hi, "null pointer");
+  long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  split_planes_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, n, static_cast<__nv_bfloat16*>(hi),
+                                                                    static_cast<__nv_bfloat16*>(lo));
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vmm
+
+// ============================== extern "C" ==================================================
+extern "C" {
+
+int vmm_version(void) { return VMM_ABI_VERSION; }
+const char* vmm_last_error(void) { return vmm::g_err; }
+
+int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major, float* C,
+                  long long ldc, const float* bias, int accumulate, int splits, void* stream) {
+  return vmm::gemm_bf16(M, N, nseg, segs, a_mn_major != 0, b_mn_major != 0, C, ldc, bias, accumulate != 0, splits,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major, float* C,
+                   long long ldc, const float* bias, int accumulate, void* stream) {
+  if (nseg < 1 || nseg > 4 || !segs || !C) {
+    vmm::set_error("vmm_gemm_check: nseg must be in [1,4]");
+    return VMM_E_INVALID;
+  }
+  vmm_gemm_seg s[4] = {segs[0], segs[nseg > 1 ? 1 : 0], segs[nseg > 2 ? 2 : 0], segs[nseg > 3 ? 3 : 0]};
+  dim3 grid((N + 127) / 128, M);
+  vmm::gemm_check_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(M, N, nseg, s[0], s[1], s[2], s[3],
+                                                                               a_mn_major, b_mn_major, C, ldc, bias,
+                                                                               accumulate);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vmm_split_planes(const float* src, long long n, void* hi, void* lo, void* stream) {
+  return vmm::split_planes(src, n, hi, lo, static_cast<cudaStream_t>(stream));
+}
+
+int vmm_estep_num_blocks(int D) { return (D + 255) / 256; }
+
+int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
+                      const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
+                      int m_views, float sigma, float* part_e, float* part_sq, float* part_pp, void* stream) {
+  return vmm::estep_forward(rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent, m_views,
+                            sigma, part_e, part_sq, part_pp, static_cast<cudaStream_t>(stream));
+}
+
+int vmm_estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
+                       const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
+                       int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
+                       void* dpred_hi, void* dpred_lo, void* stream) {
+  return vmm::estep_backward(rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent, m_views,
+                             sigma, alpha, beta, kappa, dpred_hi, dpred_lo, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+"""Stage-level Python wrappers over the C ABI (device tensors in, device tensors out).
+
+These are thin: they validate dtypes/contiguity, pass raw pointers and the current CUDA
+stream, and raise on error.  The fused module-level path (functional.py) uses the
+orchestrated entry points instead; the wrappers here exist for the stage-level parity tests
+and for tools.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import GemmSeg, check, lib, ptr, stream_ptr
+
+
+def split_planes(t: torch.Tensor, planes: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """fp32 tensor -> (hi, lo) bf16 operand planes (lo is None when planes == 1)."""
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    hi = torch.empty_like(t, dtype=torch.bfloat16)
+    lo = torch.empty_like(t, dtype=torch.bfloat16) if planes == 2 else None
+    check(lib().vmm_split_planes(ptr(t), C.c_longlong(t.numel()), ptr(hi), ptr(lo), stream_ptr()))
+    return hi, lo
+
+
+def _segs(pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]], a_mn: bool, b_mn: bool):
+    arr = (GemmSeg * len(pairs))()
+    M = N = None
+    for i, (a, b) in enumerate(pairs):
+        assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
+        assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+        ka, m = (a.shape[0], a.shape[1]) if a_mn else (a.shape[1], a.shape[0])
+        kb, n = (b.shape[0], b.shape[1]) if b_mn else (b.shape[1], b.shape[0])
+        assert ka == kb, "K mismatch"
+        assert M in (None, m) and N in (None, n)
+        M, N = m, n
+        arr[i] = GemmSeg(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), ka)
+    return arr, M, N
+
+
+def gemm(pairs, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, splits=0, check_kernel=False):
+    """C[M,N] (+)= sum_i A_i B_i^T.  A_i is (M,K) when a_mn is False, (K,M) when True; same for B."""
+    arr, M, N = _segs(pairs, a_mn, b_mn)
+    if out is None:
+        assert not accumulate
+        out = torch.empty(M, N, device=pairs[0][0].device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (M, N)
+    if check_kernel:
+        check(lib().vmm_gemm_check(M, N, len(pairs), arr, int(a_mn), int(b_mn), ptr(out), C.c_longlong(out.stride(0)),
+                                   ptr(bias), int(accumulate), stream_ptr()))
+    else:
+        check(lib().vmm_gemm_bf16(M, N, len(pairs), arr, int(a_mn), int(b_mn), ptr(out), C.c_longlong(out.stride(0)),
+                                  ptr(bias), int(accumulate), int(splits), stream_ptr()))
+    return out
+
+
+def plane_pairs(a_planes, b_planes):
+    """Error-compensated segment list for operands given as (hi, lo) planes."""
+    (ah, al), (bh, bl) = a_planes, b_planes
+    if al is None or bl is None:
+        return [(ah, bh)]
+    return [(al, bh), (ah, bl), (ah, bh)]
+
+
+def estep_num_blocks(D: int) -> int:
+    return lib().vmm_estep_num_blocks(int(D))
+
+
+def estep_forward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, want_sq=True, want_pp=False):
+    """Fused dec3 + E-step.  z planes (rows, zk), W3 planes (D, zk), x (B*M, D) float or bf16.
+    Returns per-row sums (e, sq, pp) each (rows,) - partial sums over n-blocks are reduced here
+    only for the convenience of tests; the library's gamma kernel consumes the partials."""
+    zh, zl = z_planes
+    wh, wl = w3_planes
+    rows, zk = zh.shape
+    D = wh.shape[0]
+    nb = estep_num_blocks(D)
+    dev = zh.device
+    pe = torch.empty(rows, nb, device=dev)
+    psq = torch.empty(rows, nb, device=dev) if want_sq else None
+    ppp = torch.empty(rows, nb, device=dev) if want_pp else None
+    planes = 1 if zl is None else 2
+    assert x.dtype in (torch.float32, torch.bfloat16) and x.stride(-1) == 1
+    check(lib().vmm_estep_forward(rows, D, zk, planes, ptr(zh), ptr(zl), ptr(wh), ptr(wl), ptr(b3), ptr(x),
+                                  int(x.dtype == torch.bfloat16), C.c_longlong(x.stride(-2)), int(k_latent),
+                                  int(m_views), C.c_float(sigma), ptr(pe), ptr(psq), ptr(ppp), stream_ptr()))
+    return pe, psq, ppp
+
+
+def estep_backward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, alpha, beta, kappa=None):
+    zh, zl = z_planes
+    wh, wl = w3_planes
+    rows, zk = zh.shape
+    D = wh.shape[0]
+    planes = 1 if zl is None else 2
+    dh = torch.empty(rows, D, device=zh.device, dtype=torch.bfloat16)
+    dl = torch.empty(rows, D, device=zh.device, dtype=torch.bfloat16) if planes == 2 else None
+    check(lib().vmm_estep_backward(rows, D, zk, planes, ptr(zh), ptr(zl), ptr(wh), ptr(wl), ptr(b3), ptr(x),
+                                   int(x.dtype == torch.bfloat16), C.c_longlong(x.stride(-2)), int(k_latent),
+                                   int(m_views), C.c_float(sigma), ptr(alpha), ptr(beta), ptr(kappa), ptr(dh), ptr(dl),
+                                   stream_ptr()))
+    return dh, dl

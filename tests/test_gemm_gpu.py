@@ -1,0 +1,123 @@
+"""GPU parity of the tcgen05 contraction and the fused E-step epilogues, through the C ABI.
+
+Checked against (a) fp64 torch matmul of the same bf16-rounded operands and (b) the
+library's plain one-thread-per-output CUDA kernel.  bf16 x bf16 products are exact in
+fp32, so the only difference is fp32 accumulation order: tolerance 2e-5 relative to max|C|.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def _relmax(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+SHAPES = [(128, 256, 64), (128, 256, 256), (256, 512, 1024), (384, 768, 136), (200, 1000, 72), (1024, 40, 4096),
+          (5, 3072, 1024), (3000, 1024, 1024)]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_layouts(M, N, K, a_mn, b_mn):
+    from multi_view_sort_b200 import ops
+    Mp, Np = (M + 7) // 8 * 8, (N + 7) // 8 * 8      # pitches must be multiples of 8 elements
+    A = _rand((K, Mp) if a_mn else (M, K), 1).bfloat16()
+    B = _rand((K, Np) if b_mn else (N, K), 2).bfloat16()
+    Av = A[:, :M] if a_mn else A
+    Bv = B[:, :N] if b_mn else B
+    bias = _rand((N,), 3) if N % 4 == 0 else None
+    ref = (Av.double().t() if a_mn else Av.double()) @ (Bv.double() if b_mn else Bv.double().t())
+    if bias is not None:
+        ref = ref + bias.double()
+    out = ops.gemm([(Av, Bv)], a_mn, b_mn, bias=bias)
+    chk = ops.gemm([(Av, Bv)], a_mn, b_mn, bias=bias, check_kernel=True)
+    torch.cuda.synchronize()
+    assert _relmax(chk, ref) < 2e-5, "cross-check kernel disagrees with torch"
+    err = _relmax(out, ref)
+    assert err < 2e-5, f"tcgen05 GEMM M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn}: rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("splits", [0, 1, 3, 7])
+def test_gemm_accumulate_splitk(splits):
+    from multi_view_sort_b200 import ops
+    M, N, K = 256, 512, 4096 + 64
+    A = _rand((K, M), 4).bfloat16()            # weight-gradient layout: both operands MN-major
+    B = _rand((K, N), 5).bfloat16()
+    C0 = _rand((M, N), 6)
+    ref = C0.double() + A.double().t() @ B.double()
+    out = C0.clone()
+    ops.gemm([(A, B)], True, True, out=out, accumulate=True, splits=splits)
+    torch.cuda.synchronize()
+    assert _relmax(out, ref) < 2e-5
+
+
+def test_gemm_split_precision_matches_fp32():
+    """planes == 2: three bf16 passes reproduce an fp32 contraction to ~1e-5."""
+    from multi_view_sort_b200 import ops
+    M, N, K = 512, 768, 4096
+    A, B = _rand((M, K), 7), _rand((N, K), 8, 0.02)
+    ref = A.double() @ B.double().t()
+    out = ops.gemm(ops.plane_pairs(ops.split_planes(A, 2), ops.split_planes(B, 2)))
+    one = ops.gemm(ops.plane_pairs(ops.split_planes(A, 1), ops.split_planes(B, 1)))
+    torch.cuda.synchronize()
+    e2, e1 = _relmax(out, ref), _relmax(one, ref)
+    fp32 = _relmax(A @ B.t(), ref)
+    print(f"split-bf16 rel err {e2:.3e}; single bf16 {e1:.3e}; torch fp32 {fp32:.3e}")
+    assert e2 < 3e-5 and e1 < 2e-2 and e2 < e1 / 50
+
+
+def test_gemm_two_logical_segments():
+    from multi_view_sort_b200 import ops
+    M, N = 640, 1024
+    A1, B1 = _rand((M, 4096), 9).bfloat16(), _rand((N, 4096), 10).bfloat16()
+    A2, B2 = _rand((M, 1024), 11).bfloat16(), _rand((1024, N), 12).bfloat16().t().contiguous()
+    ref = A1.double() @ B1.double().t() + A2.double() @ B2.double().t()
+    out = ops.gemm([(A1, B1), (A2, B2)])
+    torch.cuda.synchronize()
+    assert _relmax(out, ref) < 2e-5
+
+
+def _estep_ref(z, w3, b3, x, K, Mv, sigma):
+    rows = z.shape[0]
+    B = rows // (K * Mv)
+    pred = (z.double() @ w3.double().t() + b3.double()).view(B, K, Mv, -1)
+    d = x.double().view(B, 1, Mv, -1) - pred
+    e = torch.exp(-d * d / (2 * sigma * sigma))
+    return pred, d, e
+
+
+@pytest.mark.parametrize("planes,xdt", [(1, torch.bfloat16), (2, torch.float32), (1, torch.float32)])
+@pytest.mark.parametrize("B,K,Mv,D,zk", [(3, 3, 12, 512, 256), (16, 4, 12, 4096, 1024), (2, 5, 80, 1000, 1024)])
+def test_estep_fused_forward_backward(B, K, Mv, D, zk, planes, xdt):
+    from multi_view_sort_b200 import ops
+    sigma = 0.25
+    rows = B * K * Mv
+    z = _rand((rows, zk), 20)
+    w3 = _rand((D, zk), 21, 1.0 / 32)
+    b3 = _rand((D,), 22, 0.1)
+    x = torch.relu(_rand((B * Mv, D), 23)).to(xdt)
+    zp, wp = ops.split_planes(z, planes), ops.split_planes(w3, planes)
+    # what the kernel multiplies: the sum of its planes
+    zq = zp[0].float() + (zp[1].float() if planes == 2 else 0)
+    wq = wp[0].float() + (wp[1].float() if planes == 2 else 0)
+    pred, d, e = _estep_ref(zq, wq, b3, x.float(), K, Mv, sigma)
+    pe, psq, ppp = ops.estep_forward(zp, wp, b3, x, K, Mv, sigma, want_sq=True, want_pp=True)
+    torch.cuda.synchronize()
+    tol = 2e-5 if planes == 2 else 1e-4
+    assert _relmax(pe.sum(1), e.sum(-1).view(-1)) < tol
+    assert _relmax(psq.sum(1), (d * d).sum(-1).view(-1)) < tol
+    assert _relmax(ppp.sum(1), (pred * pred).sum(-1).view(-1)) < tol
+    alpha, beta, kappa = _rand((rows,), 24), _rand((rows,), 25, 0.1), _rand((rows,), 26, 0.05)
+    dref = d * (alpha.double().view(B, K, Mv, 1) * e - beta.double().view(B, K, Mv, 1)) + kappa.double().view(B, K, Mv, 1) * pred
+    dh, dl = ops.estep_backward(zp, wp, b3, x, K, Mv, sigma, alpha, beta, kappa)
+    torch.cuda.synchronize()
+    got = dh.float() + (dl.float() if planes == 2 else 0)
+    err = _relmax(got.view(-1), dref.reshape(-1))
+    assert err < (3e-5 if planes == 2 else 6e-3), f"dpred rel err {err:.3e}"
