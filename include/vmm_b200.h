@@ -29,6 +29,12 @@ extern "C" {
 
 #define VMM_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define VMM_API __attribute__((visibility("default")))
+#else
+#define VMM_API
+#endif
+
 #define VMM_E_INVALID (-1)     /* bad argument / unsupported shape */
 #define VMM_E_CUDA (-2)        /* a CUDA runtime/driver call failed */
 #define VMM_E_UNSUPPORTED (-3) /* valid request the library does not implement */
@@ -36,8 +42,8 @@ extern "C" {
 
 #define VMM_MAX_SEGMENTS 8
 
-int vmm_version(void);
-const char* vmm_last_error(void);
+VMM_API int vmm_version(void);
+VMM_API const char* vmm_last_error(void);
 
 /* ---------------------------------------------------------------------------------------
  * Tensor-core contraction (replaces every nn.Linear / GRUCell matmul on the path:
@@ -59,16 +65,16 @@ typedef struct vmm_gemm_seg {
   long long k;
 } vmm_gemm_seg;
 
-int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
+VMM_API int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
                   float* C, long long ldc, const float* bias, int accumulate, int splits, void* stream);
 
 /* Same contract computed by a plain one-thread-per-output CUDA kernel (no tensor cores):
  * the on-device cross-check used by the GPU tests.  Not used by the product path. */
-int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
+VMM_API int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
                    float* C, long long ldc, const float* bias, int accumulate, void* stream);
 
 /* fp32 -> bf16 operand planes (lo may be NULL for planes == 1). */
-int vmm_split_planes(const float* src, long long n, void* hi, void* lo, void* stream);
+VMM_API int vmm_split_planes(const float* src, long long n, void* hi, void* lo, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * E-step fused into the dec3 contraction (replaces NEM.dec3 + compute_em_probabilities,
@@ -81,8 +87,8 @@ int vmm_split_planes(const float* src, long long n, void* hi, void* lo, void* st
  *   part_sq / part_pp (nullable): same for (x-pred)^2 and pred^2.
  *   nblk = vmm_estep_num_blocks(D).
  * ------------------------------------------------------------------------------------- */
-int vmm_estep_num_blocks(int D);
-int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo,
+VMM_API int vmm_estep_num_blocks(int D);
+VMM_API int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo,
                       const void* w3_hi, const void* w3_lo, const float* b3, const void* x, int x_is_bf16,
                       long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
                       float* part_pp, void* stream);
@@ -90,7 +96,7 @@ int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z_hi, con
 /* Backward of the fused E-step: recomputes pred tile by tile and writes
  *   dpred[r,d] = delta*(alpha[r]*exp(-delta^2/(2 sigma^2)) - beta[r]) + kappa[r]*pred,  delta = x - pred
  * as bf16 operand planes [rows, D] (dpred_lo NULL when planes == 1; kappa may be NULL). */
-int vmm_estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo,
+VMM_API int vmm_estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo,
                        const void* w3_hi, const void* w3_lo, const float* b3, const void* x, int x_is_bf16,
                        long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
                        const float* beta, const float* kappa, void* dpred_hi, void* dpred_lo, void* stream);
