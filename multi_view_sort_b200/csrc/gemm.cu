@@ -309,7 +309,7 @@ int vmm_split_planes(const float* src, long long n, void* hi, void* lo, void* st
   return vmm::split_planes(src, n, hi, lo, static_cast<cudaStream_t>(stream));
 }
 
-int vmm_estep_num_blocks(int D) { return (D + 255) / 256; }
+int vmm_estep_num_blocks(int D) { return 2 * ((D + 255) / 256); }
 
 int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
                       const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,

@@ -8,8 +8,9 @@
 // (A_hi,B_lo), (A_hi,B_hi)) and how two contractions that land in the same output are
 // fused into one launch.
 //
-// One CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
-// (one elected lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes it may read).
+// One CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
+// (one elected lane), warps 2..9 = epilogue (two warps per 32-lane TMEM group, each taking half
+// of the tile's columns).
 // Tiles are 128 x BN with BLOCK_K = 64 (one 128-byte swizzle row of bf16), a STAGES-deep
 // smem ring fed by TMA, and two TMEM accumulators so the epilogue of tile i overlaps the
 // MMAs of tile i+1.
@@ -32,9 +33,10 @@ namespace vmm {
 constexpr int VMM_MAX_SEG = 8;
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int GROUP_M = 16;
-constexpr int EPI_STAGE_BYTES = 32 * 36 * 4;   // per epilogue warp
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;   // per epilogue warp (XOR-swizzled 32x32 fp32 tile)
 
 enum { EPI_STORE = 0, EPI_RED = 1, EPI_ESTEP = 2, EPI_EBWD = 3 };
 
@@ -57,9 +59,9 @@ struct alignas(64) GemmParams {
   int km;                    // K_latent * Mv
   int mv;                    // views per object
   float exp_scale;           // -log2(e) / (2 sigma^2)
-  float* part_e;             // [M, num_n_blk]  sum_d exp(...)
-  float* part_sq;            // [M, num_n_blk]  sum_d (x-pred)^2   (nullable)
-  float* part_pp;            // [M, num_n_blk]  sum_d pred^2       (nullable)
+  float* part_e;             // [M, 2*num_n_blk]  sum_d exp(...) per 128-column half tile
+  float* part_sq;            // [M, 2*num_n_blk]  sum_d (x-pred)^2   (nullable)
+  float* part_pp;            // [M, 2*num_n_blk]  sum_d pred^2       (nullable)
   const float* row_alpha;    // EBWD per-row scalars
   const float* row_beta;
   const float* row_kappa;    // nullable
@@ -76,7 +78,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256: power of two
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 4 * EPI_STAGE_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + BAR_BYTES;
 };
 
 struct WorkItem {
@@ -101,56 +103,114 @@ __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work) {
 
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t hi16) { return __uint_as_float(hi16 << 16); }
 
-// Features of one 32x32 chunk -> warp-private smem tile (pitch 36 floats), coalesced.
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// Warp-private staging tile: 32 rows x 8 float4, XOR-swizzled so that both the row-per-lane
+// accesses and the 4-rows-per-instruction coalesced accesses are bank-conflict free.
+__device__ __forceinline__ int st_slot(int r, int c4) { return r * 8 + (c4 ^ (r & 7)); }
+
+// Features of one 32x32 chunk, fetched coalesced into registers (8 x 16 bytes per lane for
+// fp32, 4 x 16 for bf16).  Row r of the tile reads feature row (r / (K*Mv)) * Mv + r % Mv.
 template <typename XT>
-__device__ __forceinline__ void stage_x_chunk(const GemmParams& p, float* st, int row0, int col0, int lane) {
+struct XRegs {
+  uint4 v[sizeof(XT) == 4 ? 8 : 4];
+};
+
+template <typename XT>
+__device__ __forceinline__ void x_fetch(const GemmParams& p, XRegs<XT>& xr, int row0, int col0, int lane) {
+  constexpr int NI = sizeof(XT) == 4 ? 8 : 4;
+  constexpr int RPI = 32 / NI;             // rows covered per instruction: 4 (fp32) or 8 (bf16)
+  constexpr int LPR = 32 / RPI;            // lanes per row: 8 or 4
+  constexpr int EPL = 16 / sizeof(XT);     // elements per lane: 4 or 8
+  const XT* x = static_cast<const XT*>(p.x);
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
+    const int r = j * RPI + lane / LPR, cc = (lane % LPR) * EPL;
+    const int grow = row0 + r, gcol = col0 + cc;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (grow < p.M && gcol < p.N) {
+      const long long xrow = static_cast<long long>(grow / p.km) * p.mv + grow % p.mv;
+      v = __ldg(reinterpret_cast<const uint4*>(x + xrow * p.ldx + gcol));
+    }
+    xr.v[j] = v;
+  }
+}
+
+template <typename XT>
+__device__ __forceinline__ void x_stage(const XRegs<XT>& xr, float4* st, int lane) {
   if constexpr (sizeof(XT) == 4) {
-    const float* x = static_cast<const float*>(p.x);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int r = j * 4 + (lane >> 3), cc = (lane & 7) * 4;
-      const int grow = row0 + r, gcol = col0 + cc;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (grow < p.M && gcol < p.N) {
-        const long long xr = static_cast<long long>(grow / p.km) * p.mv + grow % p.mv;
-        v = __ldg(reinterpret_cast<const float4*>(x + xr * p.ldx + gcol));
-      }
-      *reinterpret_cast<float4*>(st + r * 36 + cc) = v;
+      const int r = j * 4 + (lane >> 3), c4 = lane & 7;
+      st[st_slot(r, c4)] = make_float4(__uint_as_float(xr.v[j].x), __uint_as_float(xr.v[j].y),
+                                       __uint_as_float(xr.v[j].z), __uint_as_float(xr.v[j].w));
     }
   } else {
-    const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(p.x);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int r = j * 8 + (lane >> 2), cc = (lane & 3) * 8;
-      const int grow = row0 + r, gcol = col0 + cc;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (grow < p.M && gcol < p.N) {
-        const long long xr = static_cast<long long>(grow / p.km) * p.mv + grow % p.mv;
-        v = __ldg(reinterpret_cast<const uint4*>(x + xr * p.ldx + gcol));
-      }
-      float4 lo4 = make_float4(bf16_bits_to_float(v.x & 0xffffu), bf16_bits_to_float(v.x >> 16),
-                               bf16_bits_to_float(v.y & 0xffffu), bf16_bits_to_float(v.y >> 16));
-      float4 hi4 = make_float4(bf16_bits_to_float(v.z & 0xffffu), bf16_bits_to_float(v.z >> 16),
-                               bf16_bits_to_float(v.w & 0xffffu), bf16_bits_to_float(v.w >> 16));
-      *reinterpret_cast<float4*>(st + r * 36 + cc) = lo4;
-      *reinterpret_cast<float4*>(st + r * 36 + cc + 4) = hi4;
+      const int r = j * 8 + (lane >> 2), c4 = (lane & 3) * 2;
+      const uint4 v = xr.v[j];
+      st[st_slot(r, c4)] = make_float4(bf16_bits_to_float(v.x & 0xffffu), bf16_bits_to_float(v.x >> 16),
+                                       bf16_bits_to_float(v.y & 0xffffu), bf16_bits_to_float(v.y >> 16));
+      st[st_slot(r, c4 + 1)] = make_float4(bf16_bits_to_float(v.z & 0xffffu), bf16_bits_to_float(v.z >> 16),
+                                           bf16_bits_to_float(v.w & 0xffffu), bf16_bits_to_float(v.w >> 16));
     }
   }
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
+// ---- per-chunk epilogue bodies ---------------------------------------------------------------
+// STORE / RED: accumulator chunk -> staging (row per lane) -> coalesced 4-rows-per-instruction.
+template <int EPI>
+__device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint32_t (&v)[32], float4* st, int row0,
+                                                int col0, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st[st_slot(lane, j)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r = j * 4 + (lane >> 3), c4 = lane & 7;
+    const int grow = row0 + r, gcol = col0 + c4 * 4;
+    if (grow < p.M && gcol < p.N) {
+      float4 val = st[st_slot(r, c4)];
+      float* dst = p.C + static_cast<long long>(grow) * p.ldc + gcol;
+      if (p.vec_ok && gcol + 3 < p.N) {
+        if constexpr (EPI == EPI_STORE) {
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+            val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
+          }
+          *reinterpret_cast<float4*>(dst) = val;
+        } else {
+          atomicAdd(reinterpret_cast<float4*>(dst), val);
+        }
+      } else {
+        const float e[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (gcol + q < p.N) {
+            if constexpr (EPI == EPI_STORE) dst[q] = e[q] + (p.bias ? __ldg(p.bias + gcol + q) : 0.f);
+            else atomicAdd(dst + q, e[q]);
+          }
+      }
+    }
+  }
+  __syncwarp();
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, typename XT, int OPL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr bool kFused = (EPI == EPI_ESTEP || EPI == EPI_EBWD);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + 4 * EPI_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -171,7 +231,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -257,17 +317,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
   } else {
     // ===================== epilogue warps =====================
-    const int lane_grp = warp & 3;                                   // TMEM lanes [32*lane_grp, +32)
-    float* st = reinterpret_cast<float*>(epi_smem + (warp - 2) * EPI_STAGE_BYTES);
+    // Warp w may read TMEM lanes [32*(w%4), +32).  Two warps share each lane group and split
+    // the tile's columns in halves; each walks its half in 32-column chunks with the TMEM
+    // load of chunk c+1 and the feature fetch of chunk c+1 in flight while chunk c is processed.
+    constexpr int NCH = BN / 2 / 32;
+    const int ew = warp - 2;
+    const int lane_grp = warp & 3;
+    const int col_half = ew >> 2;
+    float4* st = reinterpret_cast<float4*>(epi_smem + ew * EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       const WorkItem w = decode_work(p, work);
       const int row0 = w.m_blk * BM + lane_grp * 32;                 // first row of this warp
-      const int n0 = w.n_blk * BN;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const int nbase = w.n_blk * BN + col_half * (BN / 2);
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
+                              static_cast<uint32_t>(acc * BN + col_half * (BN / 2));
 
       float sum_e = 0.f, sum_sq = 0.f, sum_pp = 0.f;
       float alpha = 0.f, beta = 0.f, kappa = 0.f;
@@ -279,115 +344,87 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           if (p.row_kappa) kappa = p.row_kappa[grow];
         }
       }
+      XRegs<XT> xr;
+      if constexpr (kFused) x_fetch<XT>(p, xr, row0, nbase, lane);   // overlaps the wait for the MMAs
 
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;                                      // warp-uniform
-        uint32_t v[32];
-        if constexpr (EPI == EPI_ESTEP || EPI == EPI_EBWD) stage_x_chunk<XT>(p, st, row0, col0, lane);
-        tmem_ld_32x32b_x32(taddr0 + static_cast<uint32_t>(c * 32), v);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(taddr0, va);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col0 = nbase + c * 32;
+        uint32_t (&v)[32] = (c & 1) ? vb : va;
+        uint32_t (&vn)[32] = (c & 1) ? va : vb;
         tmem_wait_ld();
-
-        if constexpr (EPI == EPI_STORE || EPI == EPI_RED) {
+        if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr0 + static_cast<uint32_t>((c + 1) * 32), vn);
+        if (col0 < p.N) {                                            // warp-uniform
+          if constexpr (!kFused) {
+            epi_store_chunk<EPI>(p, v, st, row0, col0, lane);
+          } else {
+            x_stage<XT>(xr, st, lane);
+            if (c + 1 < NCH) x_fetch<XT>(p, xr, row0, col0 + 32, lane);
+            __syncwarp();
+            float out[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(st + lane * 36 + j * 4) =
-                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                            __uint_as_float(v[4 * j + 3]));
-          __syncwarp();
+            for (int j = 0; j < 8; ++j) {
+              const float4 xv = st[st_slot(lane, j)];
+              const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col0 + j * 4 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
+              const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int r = j * 4 + (lane >> 3), cc = (lane & 7) * 4;
-            const int grow = row0 + r, gcol = col0 + cc;
-            if (grow < p.M && gcol < p.N) {
-              float4 val = *reinterpret_cast<const float4*>(st + r * 36 + cc);
-              float* dst = p.C + static_cast<long long>(grow) * p.ldc + gcol;
-              if (p.vec_ok && gcol + 3 < p.N) {
-                if constexpr (EPI == EPI_STORE) {
-                  if (p.bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
-                    val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
-                  }
-                  *reinterpret_cast<float4*>(dst) = val;
+              for (int q = 0; q < 4; ++q) {
+                const bool ok = (col0 + j * 4 + q) < p.N;
+                const float pred = __uint_as_float(v[4 * j + q]) + bs[q];
+                const float d = xs[q] - pred;
+                const float e = exp2f(d * d * p.exp_scale);
+                if constexpr (EPI == EPI_ESTEP) {
+                  if (ok) { sum_e += e; sum_sq = fmaf(d, d, sum_sq); sum_pp = fmaf(pred, pred, sum_pp); }
                 } else {
-                  atomicAdd(reinterpret_cast<float4*>(dst), val);
+                  out[4 * j + q] = ok ? fmaf(d, fmaf(alpha, e, -beta), kappa * pred) : 0.f;
                 }
-              } else {
-                const float e[4] = {val.x, val.y, val.z, val.w};
+              }
+            }
+            __syncwarp();                                            // all lanes have consumed their x row
+            if constexpr (EPI == EPI_EBWD) {
+              // bf16 planes: 64 B per row -> [32 rows][4 x 16 B], swizzled by (row>>1)&3
+              uint4* stw = reinterpret_cast<uint4*>(st);
+#pragma unroll
+              for (int pl = 0; pl < OPL; ++pl) {
+                uint32_t w16[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  float a = out[2 * q], b = out[2 * q + 1];
+                  if (pl == 1) {
+                    a -= __bfloat162float(__float2bfloat16_rn(a));
+                    b -= __bfloat162float(__float2bfloat16_rn(b));
+                  }
+                  w16[q] = pack_bf16x2(a, b);
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                  if (gcol + q < p.N) {
-                    if constexpr (EPI == EPI_STORE) dst[q] = e[q] + (p.bias ? __ldg(p.bias + gcol + q) : 0.f);
-                    else atomicAdd(dst + q, e[q]);
-                  }
-              }
-            }
-          }
-          __syncwarp();
-        } else {
-          // x chunk was staged by this warp; make it visible, then each lane reads its own row.
-          __syncwarp();
-          float out[32];
+                  stw[lane * 4 + (q ^ ((lane >> 1) & 3))] = make_uint4(w16[4 * q], w16[4 * q + 1], w16[4 * q + 2], w16[4 * q + 3]);
+                __syncwarp();
+                __nv_bfloat16* outp = pl == 0 ? p.out_hi : p.out_lo;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 xv = *reinterpret_cast<const float4*>(st + lane * 36 + j * 4);
-            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col0 + j * 4 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
-            const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const bool ok = (col0 + j * 4 + q) < p.N;
-              const float pred = __uint_as_float(v[4 * j + q]) + bs[q];
-              const float d = xs[q] - pred;
-              const float e = exp2f(d * d * p.exp_scale);
-              if constexpr (EPI == EPI_ESTEP) {
-                if (ok) { sum_e += e; sum_sq += d * d; sum_pp += pred * pred; }
-              } else {
-                out[4 * j + q] = ok ? (d * (alpha * e - beta) + kappa * pred) : 0.f;
-              }
-            }
-          }
-          if constexpr (EPI == EPI_EBWD) {
-            __syncwarp();                                            // everyone has consumed its x row
-            uint32_t* stw = reinterpret_cast<uint32_t*>(st);
-#pragma unroll
-            for (int pl = 0; pl < OPL; ++pl) {
-              uint32_t w16[16];
-#pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                float a = out[2 * q], b = out[2 * q + 1];
-                if (pl == 1) {
-                  a -= __bfloat162float(__float2bfloat16_rn(a));
-                  b -= __bfloat162float(__float2bfloat16_rn(b));
+                for (int j = 0; j < 4; ++j) {
+                  const int r = j * 8 + (lane >> 2), q = lane & 3;
+                  const int grow = row0 + r, gcol = col0 + q * 8;
+                  if (grow < p.M && gcol < p.N)
+                    *reinterpret_cast<uint4*>(outp + static_cast<long long>(grow) * p.ldo + gcol) = stw[r * 4 + (q ^ ((r >> 1) & 3))];
                 }
-                w16[q] = pack_bf16x2(a, b);
+                __syncwarp();
               }
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(stw + lane * 20 + q * 4) = make_uint4(w16[4 * q], w16[4 * q + 1], w16[4 * q + 2], w16[4 * q + 3]);
-              __syncwarp();
-              __nv_bfloat16* outp = pl == 0 ? p.out_hi : p.out_lo;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int r = j * 8 + (lane >> 2), q = lane & 3;
-                const int grow = row0 + r, gcol = col0 + q * 8;
-                if (grow < p.M && gcol < p.N)
-                  *reinterpret_cast<uint4*>(outp + static_cast<long long>(grow) * p.ldo + gcol) =
-                      *reinterpret_cast<const uint4*>(stw + r * 20 + q * 4);
-              }
-              __syncwarp();
             }
-          } else {
-            __syncwarp();                                            // before the next chunk overwrites st
           }
         }
       }
       if constexpr (EPI == EPI_ESTEP) {
         const int grow = row0 + lane;
         if (grow < p.M) {
-          const long long o = static_cast<long long>(grow) * p.num_n_blk + w.n_blk;
+          const long long o = static_cast<long long>(grow) * (2 * p.num_n_blk) + 2 * w.n_blk + col_half;
           p.part_e[o] = sum_e;
           if (p.part_sq) p.part_sq[o] = sum_sq;
           if (p.part_pp) p.part_pp[o] = sum_pp;
