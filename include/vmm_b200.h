@@ -95,11 +95,87 @@ VMM_API int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z
 
 /* Backward of the fused E-step: recomputes pred tile by tile and writes
  *   dpred[r,d] = delta*(alpha[r]*exp(-delta^2/(2 sigma^2)) - beta[r]) + kappa[r]*pred,  delta = x - pred
- * as bf16 operand planes [rows, D] (dpred_lo NULL when planes == 1; kappa may be NULL). */
+ * as bf16 operand planes [rows, D] (dpred_lo NULL when planes == 1; kappa may be NULL).
+ * d_b3 (nullable): [D] += exact fp32 column sums of dpred - the dec3 bias gradient. */
 VMM_API int vmm_estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo,
                        const void* w3_hi, const void* w3_lo, const float* b3, const void* x, int x_is_bf16,
                        long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
-                       const float* beta, const float* kappa, void* dpred_hi, void* dpred_lo, void* stream);
+                       const float* beta, const float* kappa, void* dpred_hi, void* dpred_lo, float* d_b3,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The whole EM loop of one batch (replaces the per-batch loop of tools/Trainer.py:160-203:
+ * NEM.init_state, T x NEM.forward (train_nem.py:272-294) and compute_outer_loss of the last
+ * iteration), and its hand-written backward (replaces autograd's BPTT through the T
+ * iterations, Trainer.py:219).
+ *
+ * Geometry: B objects, K latent views (-cluster_n), M views, D feature dim, H GRU hidden,
+ * T iterations (-iter_num).  Row orders are the reference's: h is [B*K, H], gamma is
+ * [B, K, M], x is [B, M, D].
+ * ------------------------------------------------------------------------------------- */
+typedef struct vmm_em_config {
+  int B, K, M, D, H, T;
+  int planes;          /* 1: bf16 contractions; 2: split-bf16 (fp32-class) contractions        */
+  int x_is_bf16;       /* features are bf16 ("bf16 features" mode) instead of float             */
+  int if_gamma_prior;  /* 0,1,2 as in tools/NEM_utilities.py:98-106                             */
+  int stop_gamma_grad; /* detach gamma inside the intra loss (NEM_utilities.py:118-123)         */
+  int training;        /* 1: keep every iteration's activations for vmm_em_backward             */
+  float sigma;         /* e_sigma (train_nem.py:150)                                            */
+  float ln_eps;        /* nn.LayerNorm eps, 1e-5                                                */
+} vmm_em_config;
+
+/* fp32 parameters in the reference's own state_dict layout (torch Linear [out, in]; GRU gate
+ * order r, z, n) - train_nem.py:171-185.  after_rnn.* is never used by the reference's
+ * forward (train_nem.py:179 vs 232-235) and is not part of this struct. */
+typedef struct vmm_em_params {
+  const float *enc1_w, *enc1_b, *enc1_ln_g, *enc1_ln_b; /* [1024,D] [1024] [1024] [1024]        */
+  const float *enc2_w, *enc2_b, *enc2_ln_g, *enc2_ln_b; /* [4096,1024*M] [4096] ...             */
+  const float *gru_w_ih, *gru_w_hh, *gru_b_ih, *gru_b_hh; /* [3H,4096] [3H,H] [3H] [3H]         */
+  const float *dec1_w, *dec1_b, *dec1_ln_g, *dec1_ln_b; /* [4096,H] [4096] ...                  */
+  const float *dec2_w, *dec2_b, *dec2_ln_g, *dec2_ln_b; /* [1024*M,4096] [1024*M] ...           */
+  const float *dec3_w, *dec3_b;                         /* [D,1024] [D]                         */
+} vmm_em_params;
+
+/* Same fields, non-const: gradients are ACCUMULATED (+=) into these buffers. */
+typedef struct vmm_em_grads {
+  float *enc1_w, *enc1_b, *enc1_ln_g, *enc1_ln_b;
+  float *enc2_w, *enc2_b, *enc2_ln_g, *enc2_ln_b;
+  float *gru_w_ih, *gru_w_hh, *gru_b_ih, *gru_b_hh;
+  float *dec1_w, *dec1_b, *dec1_ln_g, *dec1_ln_b;
+  float *dec2_w, *dec2_b, *dec2_ln_g, *dec2_ln_b;
+  float *dec3_w, *dec3_b;
+} vmm_em_grads;
+
+/* Buffer sizes (bytes) the caller must provide. */
+VMM_API long long vmm_em_weights_bytes(const vmm_em_config* cfg);   /* prepared bf16 weight planes   */
+VMM_API long long vmm_em_workspace_bytes(const vmm_em_config* cfg); /* activations kept for backward */
+VMM_API long long vmm_em_scratch_bytes(const vmm_em_config* cfg);   /* transient, forward or backward */
+
+/* Once per set of parameter values (per optimizer step): bf16 operand planes of every weight,
+ * W13 = enc1.W * dec3.W and w1b3 = enc1.W * dec3.b (the dec3 -> residual -> enc1 fold, see
+ * DESIGN.md) into `weights`. */
+VMM_API int vmm_em_prepare(const vmm_em_config* cfg, const vmm_em_params* params, void* weights, void* scratch,
+                           void* stream);
+
+/* Forward.  x: [B,M,D]; gamma0, prior: [B,K,M] float (NEM.init_state's gamma / gamma_prior).
+ * Outputs: h_out [B*K,H], gamma_out [B,K,M], loss_out[3] = (nem_loss, intra, inter) of the
+ * last iteration, all float on the device. */
+VMM_API int vmm_em_forward(const vmm_em_config* cfg, const vmm_em_params* params, const void* weights, const void* x,
+                           const float* gamma0, const float* prior, void* workspace, void* scratch, float* h_out,
+                           float* gamma_out, float* loss_out, void* stream);
+
+/* Backward of vmm_em_forward (cfg->training must have been 1).  d_h [B*K,H] and d_gamma
+ * [B,K,M] (either may be NULL = zero) are the gradients w.r.t. h_out / gamma_out; d_loss[3]
+ * (device) the gradients w.r.t. loss_out.  Parameter gradients are accumulated into `grads`. */
+VMM_API int vmm_em_backward(const vmm_em_config* cfg, const vmm_em_params* params, const void* weights, const void* x,
+                            const float* gamma0, const float* prior, const void* workspace, void* scratch,
+                            const float* d_h, const float* d_gamma, const float* d_loss, const vmm_em_grads* grads,
+                            void* stream);
+
+/* Address of a named intermediate of iteration `iter` inside `workspace` (for stage-level
+ * parity tests and debugging); returns NULL for an unknown name.  Names: "xw1", "g1", "a_hi",
+ * "g2", "e_hi", "gi", "gh", "h", "h_hi", "g4", "u_hi", "g5", "z_hi", "z_lo", "gamma", "row_sq". */
+VMM_API const void* vmm_em_workspace_ptr(const vmm_em_config* cfg, const void* workspace, const char* name, int iter);
 
 #ifdef __cplusplus
 }

@@ -208,7 +208,7 @@ int estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const v
 int estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
                    const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
                    int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
-                   void* dpred_hi, void* dpred_lo, cudaStream_t stream) {
+                   void* dpred_hi, void* dpred_lo, float* colsum, cudaStream_t stream) {
   GemmParams p;
   vmm_gemm_seg segs[3];
   VMM_TRY(estep_common(p, segs, rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent,
@@ -222,6 +222,7 @@ int estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const 
   p.out_hi = static_cast<__nv_bfloat16*>(dpred_hi);
   p.out_lo = static_cast<__nv_bfloat16*>(dpred_lo);
   p.ldo = D;
+  p.colsum = colsum;
   if (planes == 2) {
     if (x_is_bf16) return launch_major<EPI_EBWD, __nv_bfloat16, 2>(p, false, false, stream);
     return launch_major<EPI_EBWD, float, 2>(p, false, false, stream);
@@ -321,9 +322,9 @@ int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z_hi, con
 int vmm_estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
                        const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
                        int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
-                       void* dpred_hi, void* dpred_lo, void* stream) {
+                       void* dpred_hi, void* dpred_lo, float* d_b3, void* stream) {
   return vmm::estep_backward(rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent, m_views,
-                             sigma, alpha, beta, kappa, dpred_hi, dpred_lo, static_cast<cudaStream_t>(stream));
+                             sigma, alpha, beta, kappa, dpred_hi, dpred_lo, d_b3, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

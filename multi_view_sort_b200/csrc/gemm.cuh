@@ -68,6 +68,7 @@ struct alignas(64) GemmParams {
   __nv_bfloat16* out_hi;     // EBWD output planes [M, ldo]
   __nv_bfloat16* out_lo;     // nullable
   long long ldo;
+  float* colsum;             // EBWD: [N] += column sums of dL/dpred (dec3 bias gradient), nullable
 };
 
 template <int BN>
@@ -389,6 +390,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
             __syncwarp();                                            // all lanes have consumed their x row
             if constexpr (EPI == EPI_EBWD) {
+              if (p.colsum) {
+                // exact fp32 column sums of this warp's 32x32 block (bias gradient of dec3)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  st[st_slot(lane, j)] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+                __syncwarp();
+                const float* stf = reinterpret_cast<const float*>(st);
+                float cs = 0.f;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) cs += stf[st_slot(r, lane >> 2) * 4 + (lane & 3)];
+                if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, cs);
+                __syncwarp();
+              }
               // bf16 planes: 64 B per row -> [32 rows][4 x 16 B], swizzled by (row>>1)&3
               uint4* stw = reinterpret_cast<uint4*>(st);
 #pragma unroll

@@ -1,0 +1,790 @@
+// Memory-bound stages of the VMM EM iteration (see stages.cuh).  All kernels are plain
+// coalesced fp32 streaming kernels: one block per row for the LayerNorm family (row
+// reductions by warp shuffle + smem), one thread per column for the column reductions.
+#include "stages.cuh"
+
+#include <math.h>
+
+namespace vmm {
+namespace {
+
+constexpr int LN_THREADS = 256;
+constexpr int LN_CACHE = 4;   // float4 per thread kept in registers -> rows up to 4096 wide
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block (LN_THREADS threads); every thread gets the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum_f(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();                      // protect `red` from the previous use
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < (blockDim.x >> 5)) ? red[l] : 0.f;
+  return warp_sum_f(t);
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float act_fwd(int act, float y) {
+  if (act == ACT_ELU) return y > 0.f ? y : expm1f(y);
+  if (act == ACT_RELU) return y > 0.f ? y : 0.f;
+  return y;
+}
+__device__ __forceinline__ float act_grad(int act, float y) {
+  if (act == ACT_ELU) return y > 0.f ? 1.f : expf(y);
+  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, float4 v) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&h0);
+  u.y = *reinterpret_cast<const uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(hi + idx) = u;
+  if (lo) {
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+    const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    u.x = *reinterpret_cast<const uint32_t*>(&l0);
+    u.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(lo + idx) = u;
+  }
+}
+__device__ __forceinline__ void store_planes1(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[idx] = h;
+  if (lo) lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// Pre-normalisation value of 4 consecutive columns, and (LN_ENC1) the residual factor s with
+// value = gamma * s + bias.
+template <int MODE>
+__device__ __forceinline__ float4 ln_value4(const LnDesc& d, int row, long long xrow, float gam, int c, float4* s_out) {
+  const float4 b = ld4(d.bias + c);
+  if (MODE == LN_BIAS) {
+    const float4 v = ld4(d.C + static_cast<long long>(row) * d.ldc + c);
+    return make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
+  }
+  float4 s = ld4(d.xw1 + xrow * d.width + c);
+  if (d.C) {
+    const float4 g1 = ld4(d.C + static_cast<long long>(row) * d.ldc + c);
+    const float4 w = ld4(d.w1b3 + c);
+    s = make_float4(s.x - g1.x - w.x, s.y - g1.y - w.y, s.z - g1.z - w.z, s.w - g1.w - w.w);
+  }
+  if (s_out) *s_out = s;
+  return make_float4(fmaf(gam, s.x, b.x), fmaf(gam, s.y, b.y), fmaf(gam, s.z, b.z), fmaf(gam, s.w, b.w));
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (+activation) forward: one block per row.
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool CACHED>
+__global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int act, __nv_bfloat16* out_hi,
+                                                                __nv_bfloat16* out_lo, float* mean_out, float* rstd_out) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+  float gam = 0.f;
+  long long xrow = 0;
+  if (MODE == LN_ENC1) {
+    gam = d.gamma[row];
+    xrow = static_cast<long long>(row / d.km) * d.mv + row % d.mv;
+  }
+  float4 cache[CACHED ? LN_CACHE : 1];
+  float sum = 0.f;
+  if (CACHED) {
+#pragma unroll
+    for (int i = 0; i < LN_CACHE; ++i) {
+      const int c = (tid + i * LN_THREADS) * 4;
+      if (c < d.width) {
+        cache[i] = ln_value4<MODE>(d, row, xrow, gam, c, nullptr);
+        sum += (cache[i].x + cache[i].y) + (cache[i].z + cache[i].w);
+      }
+    }
+  } else {
+    for (int c = tid * 4; c < d.width; c += LN_THREADS * 4) {
+      const float4 v = ln_value4<MODE>(d, row, xrow, gam, c, nullptr);
+      sum += (v.x + v.y) + (v.z + v.w);
+    }
+  }
+  const float mean = block_sum(sum, red) / static_cast<float>(d.width);
+  float sq = 0.f;
+  if (CACHED) {
+#pragma unroll
+    for (int i = 0; i < LN_CACHE; ++i) {
+      const int c = (tid + i * LN_THREADS) * 4;
+      if (c < d.width) {
+        const float4 v = cache[i];
+        const float a = v.x - mean, b = v.y - mean, e = v.z - mean, f = v.w - mean;
+        sq += (a * a + b * b) + (e * e + f * f);
+      }
+    }
+  } else {
+    for (int c = tid * 4; c < d.width; c += LN_THREADS * 4) {
+      const float4 v = ln_value4<MODE>(d, row, xrow, gam, c, nullptr);
+      const float a = v.x - mean, b = v.y - mean, e = v.z - mean, f = v.w - mean;
+      sq += (a * a + b * b) + (e * e + f * f);
+    }
+  }
+  const float var = block_sum(sq, red) / static_cast<float>(d.width);
+  const float rstd = 1.0f / sqrtf(var + d.eps);
+  if (tid == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  const long long obase = static_cast<long long>(row) * d.width;
+  auto emit = [&](int c, float4 v) {
+    const float4 g = ld4(d.ln_g + c), b = ld4(d.ln_b + c);
+    float4 o;
+    o.x = act_fwd(act, fmaf((v.x - mean) * rstd, g.x, b.x));
+    o.y = act_fwd(act, fmaf((v.y - mean) * rstd, g.y, b.y));
+    o.z = act_fwd(act, fmaf((v.z - mean) * rstd, g.z, b.z));
+    o.w = act_fwd(act, fmaf((v.w - mean) * rstd, g.w, b.w));
+    store_planes4(out_hi, out_lo, obase + c, o);
+  };
+  if (CACHED) {
+#pragma unroll
+    for (int i = 0; i < LN_CACHE; ++i) {
+      const int c = (tid + i * LN_THREADS) * 4;
+      if (c < d.width) emit(c, cache[i]);
+    }
+  } else {
+    for (int c = tid * 4; c < d.width; c += LN_THREADS * 4) emit(c, ln_value4<MODE>(d, row, xrow, gam, c, nullptr));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (+activation) backward, row part.  LN_BIAS: one block per row.  LN_ENC1: one block
+// per feature row (b, m) looping over the K latent rows that share it, so that
+// dxw1[b*Mv+m, :] += sum_k gamma*dv needs no atomics.
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(LN_THREADS) ln_backward_rows_kernel(
+    LnDesc d, int act, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+    const float* __restrict__ d_out, long long ldd, __nv_bfloat16* dv_hi, __nv_bfloat16* dv_lo, float* c1_out,
+    float* c2_out, float* dgamma, float* dxw1, __nv_bfloat16* dg1_hi, __nv_bfloat16* dg1_lo) {
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  const int klat = (MODE == LN_ENC1) ? d.km / d.mv : 1;
+  for (int kk = 0; kk < klat; ++kk) {
+    int row;
+    long long xrow = 0;
+    float gam = 0.f;
+    if (MODE == LN_ENC1) {
+      const int b = blockIdx.x / d.mv, m = blockIdx.x % d.mv;
+      row = (b * klat + kk) * d.mv + m;
+      xrow = blockIdx.x;
+      gam = d.gamma[row];
+    } else {
+      row = blockIdx.x;
+    }
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = tid * 4; c < d.width; c += LN_THREADS * 4) {
+      const float4 v = ln_value4<MODE>(d, row, xrow, gam, c, nullptr);
+      const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c);
+      const float4 go = ld4(d_out + static_cast<long long>(row) * ldd + c);
+      const float vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w}, be[4] = {bb.x, bb.y, bb.z, bb.w},
+                  oo[4] = {go.x, go.y, go.z, go.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float xh = (vv[q] - mean) * rstd;
+        const float y = fmaf(xh, gg[q], be[q]);
+        const float dxh = oo[q] * act_grad(act, y) * gg[q];
+        s1 += dxh;
+        s2 = fmaf(dxh, xh, s2);
+      }
+    }
+    const float c1 = block_sum(s1, red) / static_cast<float>(d.width);
+    const float c2 = block_sum(s2, red) / static_cast<float>(d.width);
+    if (tid == 0) {
+      c1_out[row] = c1;
+      c2_out[row] = c2;
+    }
+    float dgam = 0.f;
+    for (int c = tid * 4; c < d.width; c += LN_THREADS * 4) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v = ln_value4<MODE>(d, row, xrow, gam, c, &s);
+      const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c);
+      const float4 go = ld4(d_out + static_cast<long long>(row) * ldd + c);
+      const float vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w}, be[4] = {bb.x, bb.y, bb.z, bb.w},
+                  oo[4] = {go.x, go.y, go.z, go.w}, ss[4] = {s.x, s.y, s.z, s.w};
+      float dv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float xh = (vv[q] - mean) * rstd;
+        const float y = fmaf(xh, gg[q], be[q]);
+        const float dxh = oo[q] * act_grad(act, y) * gg[q];
+        dv[q] = rstd * (dxh - c1 - xh * c2);
+        if (MODE == LN_ENC1) dgam = fmaf(dv[q], ss[q], dgam);
+      }
+      const long long o = static_cast<long long>(row) * d.width + c;
+      if (dv_hi) store_planes4(dv_hi, dv_lo, o, make_float4(dv[0], dv[1], dv[2], dv[3]));
+      if (MODE == LN_ENC1) {
+        if (dg1_hi) store_planes4(dg1_hi, dg1_lo, o, make_float4(-gam * dv[0], -gam * dv[1], -gam * dv[2], -gam * dv[3]));
+        if (dxw1) {
+          float4* px = reinterpret_cast<float4*>(dxw1 + xrow * d.width + c);   // this block owns the row
+          float4 a = *px;
+          a.x = fmaf(gam, dv[0], a.x); a.y = fmaf(gam, dv[1], a.y); a.z = fmaf(gam, dv[2], a.z); a.w = fmaf(gam, dv[3], a.w);
+          *px = a;
+        }
+      }
+    }
+    if (MODE == LN_ENC1 && dgamma) {
+      const float t = block_sum(dgam, red);
+      if (tid == 0) dgamma[row] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm backward, column part: thread per column, blockIdx.y strides over row chunks.
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) ln_backward_cols_kernel(LnDesc d, int act, const float* __restrict__ mean_in,
+                                                               const float* __restrict__ rstd_in,
+                                                               const float* __restrict__ c1_in,
+                                                               const float* __restrict__ c2_in,
+                                                               const float* __restrict__ d_out, long long ldd,
+                                                               int rows_per_block, float* d_ln_g, float* d_ln_b,
+                                                               float* d_bias, float* d_w1b3) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.width) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(d.rows, r0 + rows_per_block);
+  const float g = d.ln_g[c], be = d.ln_b[c], bias = d.bias[c];
+  const float w1b3 = (MODE == LN_ENC1 && d.C) ? d.w1b3[c] : 0.f;
+  float a_g = 0.f, a_b = 0.f, a_bias = 0.f, a_w = 0.f;
+  for (int row = r0; row < r1; ++row) {
+    float v, gam = 0.f;
+    if (MODE == LN_BIAS) {
+      v = d.C[static_cast<long long>(row) * d.ldc + c] + bias;
+    } else {
+      gam = d.gamma[row];
+      const long long xrow = static_cast<long long>(row / d.km) * d.mv + row % d.mv;
+      float s = d.xw1[xrow * d.width + c];
+      if (d.C) s = s - d.C[static_cast<long long>(row) * d.ldc + c] - w1b3;
+      v = fmaf(gam, s, bias);
+    }
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float xh = (v - mean) * rstd;
+    const float y = fmaf(xh, g, be);
+    const float dy = d_out[static_cast<long long>(row) * ldd + c] * act_grad(act, y);
+    const float dv = rstd * (dy * g - c1_in[row] - xh * c2_in[row]);
+    a_g = fmaf(dy, xh, a_g);
+    a_b += dy;
+    a_bias += dv;
+    if (MODE == LN_ENC1) a_w = fmaf(-gam, dv, a_w);
+  }
+  atomicAdd(d_ln_g + c, a_g);
+  atomicAdd(d_ln_b + c, a_b);
+  atomicAdd(d_bias + c, a_bias);
+  if (MODE == LN_ENC1 && d_w1b3) atomicAdd(d_w1b3 + c, a_w);
+}
+
+// ------------------------------------------------------------------------------------------
+// GRU gates
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(256) gru_forward_kernel(int rows, int H, const float* __restrict__ gi,
+                                                          const float* __restrict__ gh, const float* __restrict__ b_ih,
+                                                          const float* __restrict__ b_hh,
+                                                          const float* __restrict__ h_prev, float* __restrict__ h_new,
+                                                          __nv_bfloat16* h_hi, __nv_bfloat16* h_lo) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * H) return;
+  const int row = static_cast<int>(idx / H), j = static_cast<int>(idx % H);
+  const long long g0 = static_cast<long long>(row) * 3 * H + j;
+  const float r = sigmoidf_((gi[g0] + b_ih[j]) + (gh[g0] + b_hh[j]));
+  const float z = sigmoidf_((gi[g0 + H] + b_ih[H + j]) + (gh[g0 + H] + b_hh[H + j]));
+  const float n = tanhf((gi[g0 + 2 * H] + b_ih[2 * H + j]) + r * (gh[g0 + 2 * H] + b_hh[2 * H + j]));
+  const float hp = h_prev[idx];
+  const float h = (hp - n) * z + n;
+  h_new[idx] = h;
+  store_planes1(h_hi, h_lo, idx, h);
+}
+
+// thread per hidden column j, blockIdx.y strides over row chunks (bias gradients need column sums)
+__global__ void __launch_bounds__(256) gru_backward_kernel(int rows, int H, int rows_per_block,
+                                                           const float* __restrict__ gi, const float* __restrict__ gh,
+                                                           const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                                           const float* __restrict__ h_prev, const float* __restrict__ dh,
+                                                           __nv_bfloat16* dgi_hi, __nv_bfloat16* dgi_lo,
+                                                           __nv_bfloat16* dgh_hi, __nv_bfloat16* dgh_lo,
+                                                           float* __restrict__ dh_prev, float* d_b_ih, float* d_b_hh) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  const float bir = b_ih[j], biz = b_ih[H + j], bin = b_ih[2 * H + j];
+  const float bhr = b_hh[j], bhz = b_hh[H + j], bhn = b_hh[2 * H + j];
+  float s_r = 0.f, s_z = 0.f, s_in = 0.f, s_hn = 0.f;
+  for (int row = r0; row < r1; ++row) {
+    const long long g0 = static_cast<long long>(row) * 3 * H + j;
+    const long long hidx = static_cast<long long>(row) * H + j;
+    const float r = sigmoidf_((gi[g0] + bir) + (gh[g0] + bhr));
+    const float z = sigmoidf_((gi[g0 + H] + biz) + (gh[g0 + H] + bhz));
+    const float ghn = gh[g0 + 2 * H] + bhn;
+    const float n = tanhf((gi[g0 + 2 * H] + bin) + r * ghn);
+    const float hp = h_prev[hidx];
+    const float g = dh[hidx];
+    // h = (hp - n) z + n
+    const float dn = g * (1.f - z);
+    const float dz = g * (hp - n);
+    const float dn_pre = dn * (1.f - n * n);
+    const float dr_pre = dn_pre * ghn * r * (1.f - r);
+    const float dz_pre = dz * z * (1.f - z);
+    const float dhn = dn_pre * r;
+    store_planes1(dgi_hi, dgi_lo, g0, dr_pre);
+    store_planes1(dgi_hi, dgi_lo, g0 + H, dz_pre);
+    store_planes1(dgi_hi, dgi_lo, g0 + 2 * H, dn_pre);
+    store_planes1(dgh_hi, dgh_lo, g0, dr_pre);
+    store_planes1(dgh_hi, dgh_lo, g0 + H, dz_pre);
+    store_planes1(dgh_hi, dgh_lo, g0 + 2 * H, dhn);
+    dh_prev[hidx] = g * z;
+    s_r += dr_pre;
+    s_z += dz_pre;
+    s_in += dn_pre;
+    s_hn += dhn;
+  }
+  atomicAdd(d_b_ih + j, s_r);
+  atomicAdd(d_b_ih + H + j, s_z);
+  atomicAdd(d_b_ih + 2 * H + j, s_in);
+  atomicAdd(d_b_hh + j, s_r);
+  atomicAdd(d_b_hh + H + j, s_z);
+  atomicAdd(d_b_hh + 2 * H + j, s_hn);
+}
+
+// ------------------------------------------------------------------------------------------
+// Responsibilities
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gamma_forward_kernel(int B, int K, int Mv, int nblk, float coef,
+                                                            const float* __restrict__ part_e,
+                                                            const float* __restrict__ part_sq,
+                                                            const float* __restrict__ part_pp, float* __restrict__ gamma,
+                                                            float* __restrict__ inv_s, float* __restrict__ row_sq,
+                                                            float* __restrict__ row_pp) {
+  const int bm = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bm >= B * Mv) return;
+  const int b = bm / Mv, m = bm % Mv;
+  float S = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const long long row = static_cast<long long>(b * K + k) * Mv + m;
+    float e = 0.f, sq = 0.f, pp = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      e += part_e[row * nblk + j];
+      if (part_sq) sq += part_sq[row * nblk + j];
+      if (part_pp) pp += part_pp[row * nblk + j];
+    }
+    const float p = fmaf(coef, e, 1e-10f);
+    gamma[row] = p;                       // normalised below
+    S += p;
+    if (row_sq && part_sq) row_sq[row] = sq;
+    if (row_pp && part_pp) row_pp[row] = pp;
+  }
+  for (int k = 0; k < K; ++k) {
+    const long long row = static_cast<long long>(b * K + k) * Mv + m;
+    gamma[row] = gamma[row] / S;
+  }
+  inv_s[bm] = 1.0f / S;
+}
+
+__global__ void __launch_bounds__(128) gamma_backward_kernel(int B, int K, int Mv, float coef_over_s2,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ inv_s,
+                                                             const float* __restrict__ dgamma, float* __restrict__ alpha) {
+  const int bm = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bm >= B * Mv) return;
+  const int b = bm / Mv, m = bm % Mv;
+  float dot = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const long long row = static_cast<long long>(b * K + k) * Mv + m;
+    dot = fmaf(dgamma[row], gamma[row], dot);
+  }
+  const float is = inv_s[bm];
+  for (int k = 0; k < K; ++k) {
+    const long long row = static_cast<long long>(b * K + k) * Mv + m;
+    alpha[row] = (dgamma[row] - dot) * is * coef_over_s2;      // dL/dp * coef / sigma^2
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Outer loss (single block: B*K*Mv is at most a few hundred thousand values)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_1024(float v, float* red) {
+  v = warp_sum_f(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < (blockDim.x >> 5)) ? red[l] : 0.f;
+  return warp_sum_f(t);
+}
+
+__global__ void __launch_bounds__(1024) loss_forward_kernel(int B, int K, int Mv, int D, int mode,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ prior,
+                                                            const float* __restrict__ row_sq,
+                                                            const float* __restrict__ row_pp, float* __restrict__ out3) {
+  __shared__ float red[32];
+  const int rows = B * K * Mv;
+  const float inv_bmd = 1.0f / (static_cast<float>(B) * Mv * D);
+  float intra = 0.f, inter0 = 0.f, ent = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float g = gamma[r];
+    intra = fmaf(g, row_sq[r], intra);
+    if (mode == 0) inter0 = fmaf(1.f - g, 0.5f * row_pp[r], inter0);
+    if (mode == 2) ent = fmaf(g, logf(g + 1e-6f), ent);
+  }
+  float kl = 0.f, sig = 0.f;
+  if (mode != 0) {
+    for (int bk = threadIdx.x; bk < B * K; bk += blockDim.x) {
+      const float* g = gamma + static_cast<long long>(bk) * Mv;
+      const float* pr = prior + static_cast<long long>(bk) * Mv;
+      float mx = -INFINITY, mean = 0.f;
+      for (int m = 0; m < Mv; ++m) { mx = fmaxf(mx, g[m]); mean += g[m]; }
+      mean /= Mv;
+      float se = 0.f;
+      for (int m = 0; m < Mv; ++m) se += expf(g[m] - mx);
+      const float lse = mx + logf(se);
+      float ss = 0.f;
+      for (int m = 0; m < Mv; ++m) {
+        const float t = pr[m];
+        if (t > 0.f) kl += t * (logf(t) - (g[m] - lse));
+        const float dd = g[m] - mean;
+        ss = fmaf(dd, dd, ss);
+      }
+      if (mode == 2) sig += sqrtf(ss);
+    }
+  }
+  intra = block_sum_1024(intra, red) * inv_bmd;
+  inter0 = block_sum_1024(inter0, red) * inv_bmd;
+  kl = block_sum_1024(kl, red) / static_cast<float>(B * K);
+  ent = block_sum_1024(ent, red);
+  sig = block_sum_1024(sig, red);
+  if (threadIdx.x == 0) {
+    float inter;
+    if (mode == 0) inter = inter0;
+    else if (mode == 1) inter = kl;
+    else inter = (-ent / B / Mv - sig / B / K) + kl;
+    const float w_inter = (mode == 0) ? 0.5f : 1.0f;
+    out3[0] = intra * 2.0f + w_inter * inter;
+    out3[1] = intra;
+    out3[2] = inter;
+  }
+}
+
+// thread per (b,k)
+__global__ void __launch_bounds__(128) loss_backward_kernel(int B, int K, int Mv, int D, int mode, int stop_gamma_grad,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ prior,
+                                                            const float* __restrict__ row_sq,
+                                                            const float* __restrict__ row_pp,
+                                                            const float* __restrict__ g3, float* __restrict__ dgamma,
+                                                            float* __restrict__ beta, float* __restrict__ kappa) {
+  const int bk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bk >= B * K) return;
+  const float w_inter = (mode == 0) ? 0.5f : 1.0f;
+  const float G_intra = g3[0] * 2.0f + g3[1];
+  const float G_inter = g3[0] * w_inter + g3[2];
+  const float inv_bmd = 1.0f / (static_cast<float>(B) * Mv * D);
+  const float* g = gamma + static_cast<long long>(bk) * Mv;
+  const float* pr = prior + static_cast<long long>(bk) * Mv;
+  float mx = -INFINITY, mean = 0.f, psum = 0.f;
+  for (int m = 0; m < Mv; ++m) { mx = fmaxf(mx, g[m]); mean += g[m]; psum += pr[m]; }
+  mean /= Mv;
+  float se = 0.f, ss = 0.f;
+  for (int m = 0; m < Mv; ++m) {
+    se += expf(g[m] - mx);
+    const float dd = g[m] - mean;
+    ss = fmaf(dd, dd, ss);
+  }
+  const float sigma_bk = sqrtf(ss);
+  for (int m = 0; m < Mv; ++m) {
+    const long long r = static_cast<long long>(bk) * Mv + m;
+    const float gm = g[m];
+    float dg = 0.f;
+    if (!stop_gamma_grad) dg += G_intra * row_sq[r] * inv_bmd;
+    beta[r] = G_intra * 2.0f * gm * inv_bmd;
+    float kap = 0.f;
+    if (mode == 0) {
+      if (!stop_gamma_grad) dg -= G_inter * 0.5f * row_pp[r] * inv_bmd;
+      kap = G_inter * (1.f - gm) * inv_bmd;
+    } else {
+      const float sm = expf(gm - mx) / se;
+      dg += G_inter * (sm * psum - pr[m]) / static_cast<float>(B * K);
+      if (mode == 2) {
+        dg -= G_inter * (logf(gm + 1e-6f) + gm / (gm + 1e-6f)) / static_cast<float>(B) / Mv;
+        if (sigma_bk > 0.f) dg -= G_inter * (gm - mean) / sigma_bk / static_cast<float>(B) / K;
+      }
+    }
+    if (kappa) kappa[r] = kap;
+    dgamma[r] += dg;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// small dense helpers
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemv_rows_kernel(int n, int k, const float* __restrict__ W,
+                                                        const float* __restrict__ v, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) s = fmaf(W[static_cast<long long>(i) * k + j], v[j], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[i] = s;
+}
+__global__ void __launch_bounds__(256) rank1_update_kernel(int n, int k, const float* __restrict__ u,
+                                                           const float* __restrict__ v, float* __restrict__ W) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * k) return;
+  W[idx] = fmaf(u[idx / k], v[idx % k], W[idx]);
+}
+__global__ void __launch_bounds__(256) gemv_cols_acc_kernel(int n, int k, int rows_per_block,
+                                                            const float* __restrict__ W, const float* __restrict__ u,
+                                                            float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(n, r0 + rows_per_block);
+  float s = 0.f;
+  for (int i = r0; i < r1; ++i) s = fmaf(u[i], W[static_cast<long long>(i) * k + j], s);
+  atomicAdd(out + j, s);
+}
+__global__ void __launch_bounds__(256) colsum_acc_kernel(int rows, int width, int rows_per_block,
+                                                         const float* __restrict__ src, long long ld,
+                                                         float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= width) return;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  for (int i = r0; i < r1; ++i) s += src[static_cast<long long>(i) * ld + j];
+  atomicAdd(out + j, s);
+}
+__global__ void __launch_bounds__(256) act_planes_kernel(int act, long long rows, int width,
+                                                         const float* __restrict__ src, long long ld,
+                                                         __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  const long long n4 = rows * (width / 4);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const long long r = i / (width / 4);
+    const int c = static_cast<int>(i % (width / 4)) * 4;
+    float4 v = ld4(src + r * ld + c);
+    v.x = act_fwd(act, v.x); v.y = act_fwd(act, v.y); v.z = act_fwd(act, v.z); v.w = act_fwd(act, v.w);
+    store_planes4(hi, lo, r * width + c, v);
+  }
+}
+__global__ void __launch_bounds__(256) act_backward_kernel(int act, long long n, const float* __restrict__ pre,
+                                                           float* __restrict__ grad) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    grad[i] *= act_grad(act, pre[i]);
+}
+
+int pick_rows_per_block(int rows, int col_blocks) {
+  // aim for ~8 blocks per SM in total
+  const int target = device_sm_count() * 8;
+  int chunks = target / (col_blocks > 0 ? col_blocks : 1);
+  if (chunks < 1) chunks = 1;
+  int rpb = (rows + chunks - 1) / chunks;
+  if (rpb < 8) rpb = 8;
+  return rpb;
+}
+
+}  // namespace
+
+// ---- host wrappers ------------------------------------------------------------------------
+static int check_ln(const LnDesc& d, int mode) {
+  VMM_REQUIRE(d.rows > 0 && d.width > 0 && d.width % 4 == 0, "LayerNorm stage: bad shape %d x %d", d.rows, d.width);
+  VMM_REQUIRE(d.bias && d.ln_g && d.ln_b, "LayerNorm stage: null parameter");
+  if (mode == LN_BIAS) {
+    VMM_REQUIRE(d.C && d.ldc % 4 == 0, "LayerNorm stage: bad input");
+  } else {
+    VMM_REQUIRE(d.xw1 && d.gamma && d.km > 0 && d.mv > 0 && d.km % d.mv == 0 && d.rows % d.km == 0,
+                "enc1 stage: bad geometry");
+    VMM_REQUIRE(!d.C || (d.w1b3 && d.ldc % 4 == 0), "enc1 stage: G1 given without w1b3");
+  }
+  return 0;
+}
+
+int ln_forward(int mode, int act, const LnDesc& d, void* out_hi, void* out_lo, float* mean, float* rstd,
+               cudaStream_t stream) {
+  VMM_TRY(check_ln(d, mode));
+  VMM_REQUIRE(out_hi && mean && rstd, "ln_forward: null output");
+  auto* hi = static_cast<__nv_bfloat16*>(out_hi);
+  auto* lo = static_cast<__nv_bfloat16*>(out_lo);
+  const bool cached = d.width <= LN_THREADS * 4 * LN_CACHE;
+  if (mode == LN_BIAS) {
+    if (cached) ln_forward_kernel<LN_BIAS, true><<<d.rows, LN_THREADS, 0, stream>>>(d, act, hi, lo, mean, rstd);
+    else ln_forward_kernel<LN_BIAS, false><<<d.rows, LN_THREADS, 0, stream>>>(d, act, hi, lo, mean, rstd);
+  } else {
+    if (cached) ln_forward_kernel<LN_ENC1, true><<<d.rows, LN_THREADS, 0, stream>>>(d, act, hi, lo, mean, rstd);
+    else ln_forward_kernel<LN_ENC1, false><<<d.rows, LN_THREADS, 0, stream>>>(d, act, hi, lo, mean, rstd);
+  }
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out,
+                     long long ldd, void* dv_hi, void* dv_lo, float* c1, float* c2, float* dgamma, float* dxw1,
+                     void* dg1_hi, void* dg1_lo, cudaStream_t stream) {
+  VMM_TRY(check_ln(d, mode));
+  VMM_REQUIRE(mean && rstd && d_out && c1 && c2 && ldd % 4 == 0 && (dv_hi || mode == LN_ENC1), "ln_backward_rows: null argument");
+  auto* hi = static_cast<__nv_bfloat16*>(dv_hi);
+  auto* lo = static_cast<__nv_bfloat16*>(dv_lo);
+  if (mode == LN_BIAS) {
+    ln_backward_rows_kernel<LN_BIAS><<<d.rows, LN_THREADS, 0, stream>>>(d, act, mean, rstd, d_out, ldd, hi, lo, c1, c2,
+                                                                          nullptr, nullptr, nullptr, nullptr);
+  } else {
+    const int groups = d.rows / d.km * d.mv;      // feature rows (b, m)
+    ln_backward_rows_kernel<LN_ENC1><<<groups, LN_THREADS, 0, stream>>>(
+        d, act, mean, rstd, d_out, ldd, hi, lo, c1, c2, dgamma, dxw1, static_cast<__nv_bfloat16*>(dg1_hi),
+        static_cast<__nv_bfloat16*>(dg1_lo));
+  }
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, const float* rstd, const float* c1,
+                     const float* c2, const float* d_out, long long ldd, float* d_ln_g, float* d_ln_b, float* d_bias,
+                     float* d_w1b3, cudaStream_t stream) {
+  VMM_TRY(check_ln(d, mode));
+  VMM_REQUIRE(mean && rstd && c1 && c2 && d_out && d_ln_g && d_ln_b && d_bias, "ln_backward_cols: null argument");
+  const int col_blocks = ceil_div(d.width, 256);
+  const int rpb = pick_rows_per_block(d.rows, col_blocks);
+  dim3 grid(col_blocks, ceil_div(d.rows, rpb));
+  if (mode == LN_BIAS)
+    ln_backward_cols_kernel<LN_BIAS><<<grid, 256, 0, stream>>>(d, act, mean, rstd, c1, c2, d_out, ldd, rpb, d_ln_g, d_ln_b,
+                                                                d_bias, nullptr);
+  else
+    ln_backward_cols_kernel<LN_ENC1><<<grid, 256, 0, stream>>>(d, act, mean, rstd, c1, c2, d_out, ldd, rpb, d_ln_g, d_ln_b,
+                                                                d_bias, d_w1b3);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gru_forward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
+                const float* h_prev, float* h_new, void* h_hi, void* h_lo, cudaStream_t stream) {
+  VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && h_new && h_hi, "gru_forward: bad argument");
+  const long long n = static_cast<long long>(rows) * H;
+  gru_forward_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      rows, H, gi, gh, b_ih, b_hh, h_prev, h_new, static_cast<__nv_bfloat16*>(h_hi), static_cast<__nv_bfloat16*>(h_lo));
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gru_backward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
+                 const float* h_prev, const float* dh, void* dgi_hi, void* dgi_lo, void* dgh_hi, void* dgh_lo,
+                 float* dh_prev, float* d_b_ih, float* d_b_hh, cudaStream_t stream) {
+  VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && dh && dgi_hi && dgh_hi && dh_prev && d_b_ih &&
+                  d_b_hh, "gru_backward: bad argument");
+  const int col_blocks = ceil_div(H, 256);
+  const int rpb = pick_rows_per_block(rows, col_blocks);
+  dim3 grid(col_blocks, ceil_div(rows, rpb));
+  gru_backward_kernel<<<grid, 256, 0, stream>>>(rows, H, rpb, gi, gh, b_ih, b_hh, h_prev, dh,
+                                                static_cast<__nv_bfloat16*>(dgi_hi), static_cast<__nv_bfloat16*>(dgi_lo),
+                                                static_cast<__nv_bfloat16*>(dgh_hi), static_cast<__nv_bfloat16*>(dgh_lo),
+                                                dh_prev, d_b_ih, d_b_hh);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static float gauss_coef(float sigma) { return static_cast<float>(1.0 / sqrt(2.0 * M_PI * static_cast<double>(sigma) * sigma)); }
+
+int gamma_forward(int B, int K, int Mv, int nblk, float sigma, const float* part_e, const float* part_sq,
+                  const float* part_pp, float* gamma, float* inv_s, float* row_sq, float* row_pp, cudaStream_t stream) {
+  VMM_REQUIRE(B > 0 && K > 0 && Mv > 0 && nblk > 0 && part_e && gamma && inv_s, "gamma_forward: bad argument");
+  gamma_forward_kernel<<<ceil_div(B * Mv, 128), 128, 0, stream>>>(B, K, Mv, nblk, gauss_coef(sigma), part_e, part_sq, part_pp,
+                                                                  gamma, inv_s, row_sq, row_pp);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gamma_backward(int B, int K, int Mv, float sigma, const float* gamma, const float* inv_s, const float* dgamma,
+                   float* alpha, cudaStream_t stream) {
+  VMM_REQUIRE(B > 0 && K > 0 && Mv > 0 && gamma && inv_s && dgamma && alpha, "gamma_backward: bad argument");
+  gamma_backward_kernel<<<ceil_div(B * Mv, 128), 128, 0, stream>>>(B, K, Mv, gauss_coef(sigma) / (sigma * sigma), gamma, inv_s,
+                                                                   dgamma, alpha);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int loss_forward(int B, int K, int Mv, int D, int if_gamma_prior, const float* gamma, const float* prior,
+                 const float* row_sq, const float* row_pp, float* out3, cudaStream_t stream) {
+  VMM_REQUIRE(if_gamma_prior >= 0 && if_gamma_prior <= 2, "if_gamma_prior must be 0, 1 or 2");
+  VMM_REQUIRE(gamma && row_sq && out3 && (if_gamma_prior == 0 ? row_pp != nullptr : prior != nullptr), "loss_forward: null argument");
+  loss_forward_kernel<<<1, 1024, 0, stream>>>(B, K, Mv, D, if_gamma_prior, gamma, prior, row_sq, row_pp, out3);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int loss_backward(int B, int K, int Mv, int D, int if_gamma_prior, int stop_gamma_grad, const float* gamma,
+                  const float* prior, const float* row_sq, const float* row_pp, const float* g3, float* dgamma,
+                  float* beta, float* kappa, cudaStream_t stream) {
+  VMM_REQUIRE(if_gamma_prior >= 0 && if_gamma_prior <= 2, "if_gamma_prior must be 0, 1 or 2");
+  VMM_REQUIRE(gamma && row_sq && g3 && dgamma && beta && (if_gamma_prior == 0 ? (row_pp && kappa) : prior != nullptr),
+              "loss_backward: null argument");
+  loss_backward_kernel<<<ceil_div(B * K, 128), 128, 0, stream>>>(B, K, Mv, D, if_gamma_prior, stop_gamma_grad, gamma,
+                                                                 prior ? prior : gamma, row_sq, row_pp, g3, dgamma, beta, kappa);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gemv_rows(int n, int k, const float* W, const float* v, float* out, cudaStream_t stream) {
+  gemv_rows_kernel<<<n, 256, 0, stream>>>(n, k, W, v, out);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int rank1_update(int n, int k, const float* u, const float* v, float* W, cudaStream_t stream) {
+  const long long t = static_cast<long long>(n) * k;
+  rank1_update_kernel<<<static_cast<unsigned>((t + 255) / 256), 256, 0, stream>>>(n, k, u, v, W);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int gemv_cols_acc(int n, int k, const float* W, const float* u, float* out, cudaStream_t stream) {
+  const int col_blocks = ceil_div(k, 256);
+  const int rpb = pick_rows_per_block(n, col_blocks);
+  dim3 grid(col_blocks, ceil_div(n, rpb));
+  gemv_cols_acc_kernel<<<grid, 256, 0, stream>>>(n, k, rpb, W, u, out);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int colsum_acc(int rows, int width, const float* src, long long ld, float* out, cudaStream_t stream) {
+  const int col_blocks = ceil_div(width, 256);
+  const int rpb = pick_rows_per_block(rows, col_blocks);
+  dim3 grid(col_blocks, ceil_div(rows, rpb));
+  colsum_acc_kernel<<<grid, 256, 0, stream>>>(rows, width, rpb, src, ld, out);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int act_planes(int act, long long rows, int width, const float* src, long long ld, void* hi, void* lo,
+               cudaStream_t stream) {
+  VMM_REQUIRE(width % 4 == 0 && ld % 4 == 0 && src && hi, "act_planes: bad argument");
+  if (rows <= 0) return 0;
+  long long blocks = (rows * (width / 4) + 255) / 256;
+  const long long cap = static_cast<long long>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  act_planes_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, rows, width, src, ld,
+                                                                       static_cast<__nv_bfloat16*>(hi),
+                                                                       static_cast<__nv_bfloat16*>(lo));
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int act_backward(int act, long long n, const float* pre, float* grad, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  act_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, n, pre, grad);
+  VMM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vmm

@@ -1,0 +1,91 @@
+// Memory-bound stages of the EM iteration that sit between the tensor-core contractions:
+// LayerNorm + activation (and the enc1 "residual x responsibility" prologue), the GRU gate
+// math, the responsibility normalisation, the outer loss, and all of their backward passes.
+// Every kernel reads the fp32 output of a contraction and writes the bf16 operand planes the
+// next contraction consumes.
+#pragma once
+#include "common.h"
+
+namespace vmm {
+
+enum { ACT_NONE = 0, ACT_ELU = 1, ACT_RELU = 2 };
+enum { LN_BIAS = 0, LN_ENC1 = 1 };
+
+// One LayerNorm(+activation) stage.  The pre-normalisation value of element (row, j) is
+//   LN_BIAS : C[row, j] + bias[j]                                  (enc2, dec1, dec2)
+//   LN_ENC1 : gamma[row] * (xw1[xrow, j] - C[row, j] - w1b3[j]) + bias[j]
+//             with xrow = (row / km) * mv + row % mv; C == nullptr on the first EM iteration
+//             (pred_0 = 0, train_nem.py:156,197) where the value is gamma * xw1 + bias.
+//             This is enc1.Linear applied to (x - pred) * gamma (train_nem.py:280-284, 171)
+//             with pred = dec3(z) folded in:  W1 pred = (W1 W3) z + W1 b3.
+struct LnDesc {
+  int rows, width;
+  const float* C;
+  long long ldc;
+  const float* bias;
+  const float* ln_g;
+  const float* ln_b;
+  const float* xw1;
+  const float* w1b3;
+  const float* gamma;
+  int km, mv;
+  float eps;
+};
+
+int ln_forward(int mode, int act, const LnDesc& d, void* out_hi, void* out_lo, float* mean, float* rstd,
+               cudaStream_t stream);
+
+// Backward through activation + LayerNorm (+ the enc1 prologue).  d_out is the gradient w.r.t.
+// the stage output [rows, width] (fp32).  Produces dv = dL/d(pre-normalisation value) as operand
+// planes, the per-row LayerNorm reductions c1/c2 (consumed by ln_backward_cols), and for LN_ENC1
+// also dgamma[row] (nullable), dxw1 += gamma*dv summed over the K latent rows that share a feature
+// row, and dG1 = -gamma*dv as operand planes (nullable).
+int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out,
+                     long long ldd, void* dv_hi, void* dv_lo, float* c1, float* c2, float* dgamma, float* dxw1,
+                     void* dg1_hi, void* dg1_lo, cudaStream_t stream);
+
+// Column reductions of the same stage, accumulated (+=) into fp32 parameter gradients:
+// d_ln_g += sum_rows dy*xhat, d_ln_b += sum_rows dy, d_bias += sum_rows dv, and for LN_ENC1
+// d_w1b3 += sum_rows (-gamma*dv) (nullable).
+int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, const float* rstd, const float* c1,
+                     const float* c2, const float* d_out, long long ldd, float* d_ln_g, float* d_ln_b, float* d_bias,
+                     float* d_w1b3, cudaStream_t stream);
+
+// GRUCell gate math (train_nem.py:177,232; torch.nn.GRUCell, gate order r,z,n).
+// gi = e Wih^T, gh = h Whh^T are the raw contraction outputs [rows, 3H] (biases added here).
+int gru_forward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
+                const float* h_prev, float* h_new, void* h_hi, void* h_lo, cudaStream_t stream);
+// dh is the total gradient w.r.t. h_new.  Writes dgi/dgh operand planes [rows,3H], the direct
+// path dh_prev = dh * z (the Whh contraction adds the rest), and accumulates the bias gradients.
+int gru_backward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
+                 const float* h_prev, const float* dh, void* dgi_hi, void* dgi_lo, void* dgh_hi, void* dgh_lo,
+                 float* dh_prev, float* d_b_ih, float* d_b_hh, cudaStream_t stream);
+
+// Responsibilities from the fused E-step partial sums (train_nem.py:253-270):
+//   p = coef * sum_d exp(..) + 1e-10,  gamma = p / sum_k p.   Also folds the partial sums of
+//   (x-pred)^2 and pred^2 into per-row totals when given.
+int gamma_forward(int B, int K, int Mv, int nblk, float sigma, const float* part_e, const float* part_sq,
+                  const float* part_pp, float* gamma, float* inv_s, float* row_sq, float* row_pp, cudaStream_t stream);
+// dgamma -> alpha[row] = dL/dp[row] * coef / sigma^2 (the per-row scalar of the E-step backward).
+int gamma_backward(int B, int K, int Mv, float sigma, const float* gamma, const float* inv_s, const float* dgamma,
+                   float* alpha, cudaStream_t stream);
+
+// Outer loss of the last iteration (tools/NEM_utilities.py:98-128).  out[0..2] = total, intra, inter.
+int loss_forward(int B, int K, int Mv, int D, int if_gamma_prior, const float* gamma, const float* prior,
+                 const float* row_sq, const float* row_pp, float* out3, cudaStream_t stream);
+// Gradients of the loss: dgamma += ..., beta/kappa = per-row scalars of dL/dpred (see EPI_EBWD).
+// g3 = upstream gradients of (total, intra, inter) on the device.
+int loss_backward(int B, int K, int Mv, int D, int if_gamma_prior, int stop_gamma_grad, const float* gamma,
+                  const float* prior, const float* row_sq, const float* row_pp, const float* g3, float* dgamma,
+                  float* beta, float* kappa, cudaStream_t stream);
+
+// Small dense helpers on fp32 parameters.
+int gemv_rows(int n, int k, const float* W, const float* v, float* out, cudaStream_t stream);            // out[i] = W[i,:].v
+int rank1_update(int n, int k, const float* u, const float* v, float* W, cudaStream_t stream);            // W[i,j] += u[i] v[j]
+int gemv_cols_acc(int n, int k, const float* W, const float* u, float* out, cudaStream_t stream);         // out[j] += sum_i u[i] W[i,j]
+int colsum_acc(int rows, int width, const float* src, long long ld, float* out, cudaStream_t stream);     // out[j] += sum_r src[r,j]
+int act_planes(int act, long long rows, int width, const float* src, long long ld, void* hi, void* lo,
+               cudaStream_t stream);                                                                     // planes(act(src))
+int act_backward(int act, long long n, const float* pre, float* grad, cudaStream_t stream);              // grad *= act'(pre)
+
+}  // namespace vmm

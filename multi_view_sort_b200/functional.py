@@ -1,0 +1,169 @@
+"""torch.autograd bindings of the orchestrated C-ABI entry points.
+
+`run_em` is the fused path: every EM iteration, the E-step and the last iteration's outer
+loss in ONE autograd node whose forward is `vmm_em_forward` and whose backward is
+`vmm_em_backward` (hand-written BPTT).  torch only provides device memory, the stream and the
+autograd plumbing; no torch op touches the data.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+
+
+# ---- ctypes mirrors of include/vmm_b200.h ----------------------------------------------------
+class EMConfig(C.Structure):
+    _fields_ = [("B", C.c_int), ("K", C.c_int), ("M", C.c_int), ("D", C.c_int), ("H", C.c_int), ("T", C.c_int),
+                ("planes", C.c_int), ("x_is_bf16", C.c_int), ("if_gamma_prior", C.c_int), ("stop_gamma_grad", C.c_int),
+                ("training", C.c_int), ("sigma", C.c_float), ("ln_eps", C.c_float)]
+
+
+EM_PARAM_FIELDS = [
+    ("enc1_w", "enc1.0.weight"), ("enc1_b", "enc1.0.bias"), ("enc1_ln_g", "enc1.1.weight"), ("enc1_ln_b", "enc1.1.bias"),
+    ("enc2_w", "enc2.0.weight"), ("enc2_b", "enc2.0.bias"), ("enc2_ln_g", "enc2.1.weight"), ("enc2_ln_b", "enc2.1.bias"),
+    ("gru_w_ih", "rnn_nem.weight_ih"), ("gru_w_hh", "rnn_nem.weight_hh"), ("gru_b_ih", "rnn_nem.bias_ih"),
+    ("gru_b_hh", "rnn_nem.bias_hh"),
+    ("dec1_w", "dec1.0.weight"), ("dec1_b", "dec1.0.bias"), ("dec1_ln_g", "dec1.1.weight"), ("dec1_ln_b", "dec1.1.bias"),
+    ("dec2_w", "dec2.0.weight"), ("dec2_b", "dec2.0.bias"), ("dec2_ln_g", "dec2.1.weight"), ("dec2_ln_b", "dec2.1.bias"),
+    ("dec3_w", "dec3.weight"), ("dec3_b", "dec3.bias"),
+]
+
+
+class EMPointers(C.Structure):      # vmm_em_params and vmm_em_grads share this layout
+    _fields_ = [(f, C.c_void_p) for f, _ in EM_PARAM_FIELDS]
+
+
+def _pointers(tensors) -> EMPointers:
+    s = EMPointers()
+    for (f, _), t in zip(EM_PARAM_FIELDS, tensors):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), f
+        setattr(s, f, t.data_ptr())
+    return s
+
+
+def em_param_tensors(module):
+    """The 22 live parameters of a NEM module in the C struct's order (after_rnn.* excluded:
+    the reference never applies it, train_nem.py:179 vs 232-235, so it must keep grad=None)."""
+    named = dict(module.named_parameters())
+    return [named[k] for _, k in EM_PARAM_FIELDS]
+
+
+def _bytes(fn, cfg) -> int:
+    fn.restype = C.c_longlong
+    n = fn(C.byref(cfg))
+    if n < 0:
+        check(int(n))
+    return int(n)
+
+
+def make_config(module, B, T, x_is_bf16, training) -> EMConfig:
+    planes = {"fp32": 2, "bf16": 1}[module.precision]
+    return EMConfig(B=B, K=module.k, M=module.m, D=module.input_dim, H=module.rnn_hidden_size, T=T, planes=planes,
+                    x_is_bf16=int(x_is_bf16), if_gamma_prior=int(module.if_gamma_prior),
+                    stop_gamma_grad=int(module.stop_gamma_grad), training=int(training), sigma=float(module.e_sigma),
+                    ln_eps=float(module.enc1[1].eps))
+
+
+class _WeightCache:
+    """bf16 operand planes of the weights (+ the W1*W3 fold), rebuilt only when a parameter changed."""
+
+    def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def get(self, cfg: EMConfig, params):
+        key = (cfg.planes, cfg.M, cfg.D, cfg.H) + tuple((p.data_ptr(), p._version) for p in params)
+        if key != self.key:
+            nbytes = _bytes(lib().vmm_em_weights_bytes, cfg)
+            if self.buf is None or self.buf.numel() < nbytes or self.buf.device != params[0].device:
+                self.buf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
+            pp = _pointers(params)
+            check(lib().vmm_em_prepare(C.byref(cfg), C.byref(pp), ptr(self.buf), None, stream_ptr()))
+            self.key = key
+        return self.buf
+
+
+def _weight_cache(module) -> _WeightCache:
+    wc = module.__dict__.get("_vmm_weight_cache")
+    if wc is None:
+        wc = _WeightCache()
+        module.__dict__["_vmm_weight_cache"] = wc
+    return wc
+
+
+class _EMFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, T, x, gamma0, prior, *params):
+        B = x.shape[0]
+        dev = x.device
+        training = any(ctx.needs_input_grad[5:])     # False under no_grad or with frozen parameters
+        cfg = make_config(module, B, T, x.dtype == torch.bfloat16, training)
+        with torch.cuda.device(dev):
+            weights = _weight_cache(module).get(cfg, params)
+            ws = torch.empty(_bytes(lib().vmm_em_workspace_bytes, cfg), dtype=torch.uint8, device=dev)
+            scratch = torch.empty(_bytes(lib().vmm_em_scratch_bytes, cfg), dtype=torch.uint8, device=dev)
+            h = torch.empty(B * cfg.K, cfg.H, device=dev)
+            gamma = torch.empty(B, cfg.K, cfg.M, 1, device=dev)
+            loss = torch.empty(3, device=dev)
+            pp = _pointers(params)
+            check(lib().vmm_em_forward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(x), ptr(gamma0), ptr(prior), ptr(ws),
+                                       ptr(scratch), ptr(h), ptr(gamma), ptr(loss), stream_ptr()))
+        ctx.cfg = cfg
+        ctx.module = module
+        ctx.nparams = len(params)
+        if training:
+            ctx.save_for_backward(x, gamma0, prior, ws, weights, *params)
+        return h, gamma, loss
+
+    @staticmethod
+    def backward(ctx, d_h, d_gamma, d_loss):
+        x, gamma0, prior, ws, weights = ctx.saved_tensors[:5]
+        params = ctx.saved_tensors[5:]
+        cfg = ctx.cfg
+        dev = x.device
+        with torch.cuda.device(dev):
+            scratch = torch.empty(_bytes(lib().vmm_em_scratch_bytes, cfg), dtype=torch.uint8, device=dev)
+            grads = [torch.zeros_like(p) for p in params]
+            gp, pp = _pointers(grads), _pointers(params)
+            d_h = d_h.contiguous().float() if d_h is not None else None
+            d_gamma = d_gamma.contiguous().float() if d_gamma is not None else None
+            d_loss = d_loss.contiguous().float() if d_loss is not None else torch.zeros(3, device=dev)
+            check(lib().vmm_em_backward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(x), ptr(gamma0), ptr(prior), ptr(ws),
+                                        ptr(scratch), ptr(d_h), ptr(d_gamma), ptr(d_loss), C.byref(gp), stream_ptr()))
+        return (None, None, None, None, None, *grads)
+
+
+def run_em(module, x: torch.Tensor, iters: int, gamma0: Optional[torch.Tensor] = None,
+           gamma_prior: Optional[torch.Tensor] = None):
+    """All EM iterations + last-iteration outer loss.  Returns (h_T, gamma_T, nem_loss, intra, inter)."""
+    if not x.is_cuda:
+        raise RuntimeError("multi_view_sort_b200 has no CPU path: x must be a CUDA tensor")
+    assert x.dim() == 3 and x.shape[1] == module.m and x.shape[2] == module.input_dim, "x must be (B, M, D)"
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    B = x.shape[0]
+    dev = x.device
+    if gamma0 is None or (gamma_prior is None and module.if_gamma_prior != 0):
+        _, _, g0, gp = module.init_state(x.shape, x)
+        gamma0 = g0 if gamma0 is None else gamma0
+        gamma_prior = gp if gamma_prior is None else gamma_prior
+    gamma0 = gamma0.to(dev, torch.float32).reshape(B, module.k, module.m).contiguous()
+    if gamma_prior is None:
+        gamma_prior = gamma0
+    gamma_prior = gamma_prior.to(dev, torch.float32).reshape(B, module.k, module.m).contiguous()
+    params = em_param_tensors(module)
+    h, gamma, loss = _EMFunction.apply(module, int(iters), x, gamma0, gamma_prior, *params)
+    return h, gamma, loss[0], loss[1], loss[2]
+
+
+def em_step(module, x, state):
+    raise NotImplementedError("step-level NEM.forward: use NEM.run_em (fused path)")
+
+
+def head_forward(module, h, gamma):
+    raise NotImplementedError("head kernels are built in head.cu")

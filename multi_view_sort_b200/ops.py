@@ -88,7 +88,7 @@ def estep_forward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, want_sq=
     return pe, psq, ppp
 
 
-def estep_backward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, alpha, beta, kappa=None):
+def estep_backward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, alpha, beta, kappa=None, d_b3=None):
     zh, zl = z_planes
     wh, wl = w3_planes
     rows, zk = zh.shape
@@ -99,5 +99,5 @@ def estep_backward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, alpha, 
     check(lib().vmm_estep_backward(rows, D, zk, planes, ptr(zh), ptr(zl), ptr(wh), ptr(wl), ptr(b3), ptr(x),
                                    int(x.dtype == torch.bfloat16), C.c_longlong(x.stride(-2)), int(k_latent),
                                    int(m_views), C.c_float(sigma), ptr(alpha), ptr(beta), ptr(kappa), ptr(dh), ptr(dl),
-                                   stream_ptr()))
+                                   ptr(d_b3), stream_ptr()))
     return dh, dl

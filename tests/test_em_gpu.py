@@ -1,0 +1,133 @@
+"""GPU parity of the fused EM loop (vmm_em_forward / vmm_em_backward through the autograd
+Function) against the CPU oracle on the same seeded inputs and weights.
+
+Tolerances are north_star's: fp32 mode 1e-4 relative on outputs and gradients, bf16 mode
+1e-2, with "relative" = max|a-b| / max|b| per tensor (helpers.rel_err).  A probe loss
+  L = nem_loss + <h_T, Wh> + <gamma_T, Wg>
+drives every backward path (through h, through gamma, through the loss) without the head.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import nem_oracle as O
+from oracle.make_golden import seeded_models
+from helpers import load_golden, rel_err, params_of
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _probe(cfg):
+    g = torch.Generator().manual_seed(77)
+    wh = torch.randn(cfg["B"] * cfg["K"], cfg["H"], generator=g) * 0.01
+    wg = torch.randn(cfg["B"], cfg["K"], cfg["M"], 1, generator=g)
+    return wh, wg
+
+
+def _oracle(cfg, nem, x, dtype):
+    pn = params_of(nem, dtype=dtype)
+    r = O.run_em(pn, x.to(dtype), cfg["K"], cfg["T"], cfg["sigma"], "bin_uniform", cfg["if_gamma_prior"], cfg["stop_gamma_grad"])
+    wh, wg = _probe(cfg)
+    loss = r["nem_loss"] + (r["h"] * wh.to(dtype)).sum() + (r["gamma"] * wg.to(dtype)).sum()
+    loss.backward()
+    return r, pn
+
+
+def _cuda(cfg, nem, x, precision, xdtype):
+    nem = nem.cuda()
+    nem.precision = precision
+    h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda().to(xdtype), cfg["T"])
+    wh, wg = _probe(cfg)
+    loss = nem_loss + (h * wh.cuda()).sum() + (gamma * wg.cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    return dict(h=h, gamma=gamma, nem_loss=nem_loss, intra=intra, inter=inter), nem
+
+
+def _report(name, tag, cfg, res, nem_cuda, ref, ref_params, truth=None, truth_params=None):
+    rows = {}
+    for k in ("h", "gamma", "nem_loss", "intra", "inter"):
+        rows[k] = rel_err(res[k].reshape(-1), ref[k].reshape(-1))
+    named = dict(nem_cuda.named_parameters())
+    for n, p in ref_params.items():
+        if p.grad is None:
+            assert named[n].grad is None, f"{n} must keep grad=None like the reference"
+            continue
+        rows["grad/" + n] = rel_err(named[n].grad, p.grad)
+    ref_vs_truth = {}
+    if truth is not None:
+        for k in ("h", "gamma", "nem_loss"):
+            ref_vs_truth[k] = rel_err(ref[k].reshape(-1), truth[k].reshape(-1))
+        for n, p in truth_params.items():
+            if p.grad is not None:
+                ref_vs_truth["grad/" + n] = rel_err(ref_params[n].grad, p.grad)
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f"em_parity_{name}_{tag}.json"), "w") as f:
+        json.dump(dict(cuda_vs_oracle=rows, oracle_fp32_vs_fp64=ref_vs_truth), f, indent=1)
+    return rows
+
+
+CASES = ["peaky_b6_k4_m12_t4", "prior0_b5_k2_m12_t3", "cfg1_b8_k3_m12_t10"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_run_em_fp32_mode(name):
+    _, cfg = load_golden(name)
+    nem, _ = seeded_models(cfg)
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    ref, pn = _oracle(cfg, nem, x, torch.float32)
+    truth, pt = _oracle(cfg, nem, x, torch.float64)
+    res, nem_c = _cuda(cfg, nem, x, "fp32", torch.float32)
+    rows = _report(name, "fp32", cfg, res, nem_c, ref, pn, truth, pt)
+    worst = max(rows.items(), key=lambda kv: kv[1])
+    print(name, "fp32 worst", worst)
+    bad = {k: v for k, v in rows.items() if not v < 1e-4}
+    assert not bad, f"fp32-mode parity > 1e-4: {bad}"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_run_em_bf16_mode(name):
+    """bf16 features: the oracle consumes the bf16-rounded features up-cast to fp32."""
+    _, cfg = load_golden(name)
+    nem, _ = seeded_models(cfg)
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    xb = x.bfloat16()
+    ref, pn = _oracle(cfg, nem, xb.float(), torch.float32)
+    res, nem_c = _cuda(cfg, nem, xb, "bf16", torch.bfloat16)
+    rows = _report(name, "bf16", cfg, res, nem_c, ref, pn)
+    worst = max(rows.items(), key=lambda kv: kv[1])
+    print(name, "bf16 worst", worst)
+    bad = {k: v for k, v in rows.items() if not v < 1e-2}
+    assert not bad, f"bf16-mode parity > 1e-2: {bad}"
+
+
+def test_run_em_matches_reference_golden():
+    """CUDA fp32-mode forward against the frozen outputs of the UNMODIFIED reference."""
+    name = "cfg1_b8_k3_m12_t10"
+    z, cfg = load_golden(name)
+    nem, _ = seeded_models(cfg)
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    nem = nem.cuda()
+    with torch.no_grad():
+        h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda(), cfg["T"])
+    assert rel_err(h, z["h"]) < 1e-4
+    assert rel_err(gamma.reshape(z["gamma"].shape), z["gamma"]) < 1e-4
+    assert abs(nem_loss.item() - float(z["nem_loss"])) < 1e-4 * abs(float(z["nem_loss"]))
+    assert abs(intra.item() - float(z["intra"])) < 1e-4 * abs(float(z["intra"]))
+    assert abs(inter.item() - float(z["inter"])) < 1e-4 * abs(float(z["inter"]))
+
+
+def test_inference_mode_equals_training_forward():
+    """no_grad (2-slot ring workspace) and training forward produce identical outputs."""
+    _, cfg = load_golden("peaky_b6_k4_m12_t4")
+    nem, _ = seeded_models(cfg)
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    nem = nem.cuda()
+    a = nem.run_em(x.cuda(), cfg["T"])
+    with torch.no_grad():
+        b = nem.run_em(x.cuda(), cfg["T"])
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)

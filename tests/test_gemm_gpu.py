@@ -116,8 +116,11 @@ def test_estep_fused_forward_backward(B, K, Mv, D, zk, planes, xdt):
     assert _relmax(ppp.sum(1), (pred * pred).sum(-1).view(-1)) < tol
     alpha, beta, kappa = _rand((rows,), 24), _rand((rows,), 25, 0.1), _rand((rows,), 26, 0.05)
     dref = d * (alpha.double().view(B, K, Mv, 1) * e - beta.double().view(B, K, Mv, 1)) + kappa.double().view(B, K, Mv, 1) * pred
-    dh, dl = ops.estep_backward(zp, wp, b3, x, K, Mv, sigma, alpha, beta, kappa)
+    d_b3 = torch.full((D,), 0.5, device="cuda")
+    dh, dl = ops.estep_backward(zp, wp, b3, x, K, Mv, sigma, alpha, beta, kappa, d_b3=d_b3)
     torch.cuda.synchronize()
     got = dh.float() + (dl.float() if planes == 2 else 0)
     err = _relmax(got.view(-1), dref.reshape(-1))
     assert err < (3e-5 if planes == 2 else 6e-3), f"dpred rel err {err:.3e}"
+    # fused dec3-bias gradient: exact fp32 column sums, accumulated into the caller's buffer
+    assert _relmax(d_b3 - 0.5, dref.reshape(rows, D).sum(0)) < tol
