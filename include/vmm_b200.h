@@ -12,10 +12,10 @@
  *     several host threads, one stream per call;
  *   - all work is enqueued on `stream`; nothing synchronises the device.
  *
- * "Operand planes": matrices consumed by the tensor cores are bf16.  planes == 1 is the
- * bf16 mode; planes == 2 stores every operand as hi = bf16(v), lo = bf16(v - hi) and every
- * contraction runs three error-compensated passes (lo*hi + hi*lo + hi*hi) with fp32
- * accumulation, which reproduces the reference's fp32 arithmetic to ~1e-5.
+ * "Operand planes": matrices consumed by the tensor cores are bf16.  One plane is plain bf16;
+ * with n planes every operand is stored as n successive bf16 residuals and every contraction
+ * sums the cross terms A_i * B_j with i + j < n (3 passes for n = 2, 6 for n = 3) with fp32
+ * accumulation in TMEM.  n = 3 reproduces the reference's fp32 arithmetic.
  */
 #ifndef VMM_B200_H_
 #define VMM_B200_H_
@@ -40,7 +40,16 @@ extern "C" {
 #define VMM_E_UNSUPPORTED (-3) /* valid request the library does not implement */
 #define VMM_E_WORKSPACE (-4)   /* caller-provided workspace too small */
 
-#define VMM_MAX_SEGMENTS 8
+#define VMM_MAX_SEGMENTS 12
+#define VMM_MAX_PLANES 3
+
+/* bf16 operand planes of one matrix: p[0] = bf16(v), p[1] = bf16(v - p[0]), p[2] = bf16(v - p[0] - p[1]).
+ * n = 1 (plain bf16), 2 (~16 mantissa bits, 3 tensor-core passes per contraction) or
+ * 3 (~24 bits, 6 passes: fp32-class). */
+typedef struct vmm_planes {
+  void* p[VMM_MAX_PLANES];
+  int n;
+} vmm_planes;
 
 VMM_API int vmm_version(void);
 VMM_API const char* vmm_last_error(void);
@@ -56,6 +65,11 @@ VMM_API const char* vmm_last_error(void);
  * weight-gradient contraction sees.  Same for B with N.  All pointers bf16, 16-byte
  * aligned, pitches multiples of 8 elements.  accumulate != 0 adds into C with atomics
  * (required when splits > 1).  splits <= 0 lets the library choose.
+ * chain_kblocks > 0 bounds how many 64-wide K blocks (per segment) the tensor core may
+ * accumulate in TMEM before the epilogue folds the partial sum into C in round-to-nearest
+ * fp32: the MMA datapath truncates at every accumulate step (measured: -4.4e-9 relative per
+ * K element), so fp32-class results need short chains (4 = 256 K elements matches cuBLAS
+ * sgemm accuracy).  0 = unlimited.
  * ------------------------------------------------------------------------------------- */
 typedef struct vmm_gemm_seg {
   const void* a; /* bf16 */
@@ -66,15 +80,16 @@ typedef struct vmm_gemm_seg {
 } vmm_gemm_seg;
 
 VMM_API int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
-                  float* C, long long ldc, const float* bias, int accumulate, int splits, void* stream);
+                  float* C, long long ldc, const float* bias, int accumulate, int splits, int chain_kblocks,
+                  void* stream);
 
 /* Same contract computed by a plain one-thread-per-output CUDA kernel (no tensor cores):
  * the on-device cross-check used by the GPU tests.  Not used by the product path. */
 VMM_API int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
                    float* C, long long ldc, const float* bias, int accumulate, void* stream);
 
-/* fp32 -> bf16 operand planes (lo may be NULL for planes == 1). */
-VMM_API int vmm_split_planes(const float* src, long long n, void* hi, void* lo, void* stream);
+/* fp32 -> bf16 operand planes. */
+VMM_API int vmm_split_planes(const float* src, long long n, const vmm_planes* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * E-step fused into the dec3 contraction (replaces NEM.dec3 + compute_em_probabilities,
@@ -88,20 +103,18 @@ VMM_API int vmm_split_planes(const float* src, long long n, void* hi, void* lo, 
  *   nblk = vmm_estep_num_blocks(D).
  * ------------------------------------------------------------------------------------- */
 VMM_API int vmm_estep_num_blocks(int D);
-VMM_API int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo,
-                      const void* w3_hi, const void* w3_lo, const float* b3, const void* x, int x_is_bf16,
-                      long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
-                      float* part_pp, void* stream);
+VMM_API int vmm_estep_forward(int rows, int D, int zk, const vmm_planes* z, const vmm_planes* w3, const float* b3,
+                              const void* x, int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma,
+                              float* part_e, float* part_sq, float* part_pp, void* stream);
 
 /* Backward of the fused E-step: recomputes pred tile by tile and writes
  *   dpred[r,d] = delta*(alpha[r]*exp(-delta^2/(2 sigma^2)) - beta[r]) + kappa[r]*pred,  delta = x - pred
- * as bf16 operand planes [rows, D] (dpred_lo NULL when planes == 1; kappa may be NULL).
+ * as bf16 operand planes [rows, D] (dpred->n planes; kappa may be NULL).
  * d_b3 (nullable): [D] += exact fp32 column sums of dpred - the dec3 bias gradient. */
-VMM_API int vmm_estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo,
-                       const void* w3_hi, const void* w3_lo, const float* b3, const void* x, int x_is_bf16,
-                       long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
-                       const float* beta, const float* kappa, void* dpred_hi, void* dpred_lo, float* d_b3,
-                       void* stream);
+VMM_API int vmm_estep_backward(int rows, int D, int zk, const vmm_planes* z, const vmm_planes* w3, const float* b3,
+                               const void* x, int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma,
+                               const float* alpha, const float* beta, const float* kappa, const vmm_planes* dpred,
+                               float* d_b3, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * The whole EM loop of one batch (replaces the per-batch loop of tools/Trainer.py:160-203:
@@ -115,11 +128,13 @@ VMM_API int vmm_estep_backward(int rows, int D, int zk, int planes, const void* 
  * ------------------------------------------------------------------------------------- */
 typedef struct vmm_em_config {
   int B, K, M, D, H, T;
-  int planes;          /* 1: bf16 contractions; 2: split-bf16 (fp32-class) contractions        */
+  int planes;          /* operand planes of the forward contractions (1, 2 or 3)               */
+  int planes_bwd;      /* operand planes of the gradient contractions (1 .. planes)            */
   int x_is_bf16;       /* features are bf16 ("bf16 features" mode) instead of float             */
   int if_gamma_prior;  /* 0,1,2 as in tools/NEM_utilities.py:98-106                             */
   int stop_gamma_grad; /* detach gamma inside the intra loss (NEM_utilities.py:118-123)         */
   int training;        /* 1: keep every iteration's activations for vmm_em_backward             */
+  int accum_chain;     /* chain_kblocks of every contraction (see vmm_gemm_bf16); 0 = unlimited */
   float sigma;         /* e_sigma (train_nem.py:150)                                            */
   float ln_eps;        /* nn.LayerNorm eps, 1e-5                                                */
 } vmm_em_config;

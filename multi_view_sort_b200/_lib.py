@@ -21,6 +21,21 @@ class GemmSeg(C.Structure):
     _fields_ = [("a", C.c_void_p), ("lda", C.c_longlong), ("b", C.c_void_p), ("ldb", C.c_longlong), ("k", C.c_longlong)]
 
 
+class PlanesC(C.Structure):
+    """vmm_planes: up to 3 bf16 residual planes of one matrix."""
+    _fields_ = [("p", C.c_void_p * 3), ("n", C.c_int)]
+
+
+def planes_c(planes):
+    """Sequence of bf16 tensors (most significant first) -> vmm_planes."""
+    planes = [t for t in planes if t is not None]
+    s = PlanesC()
+    s.n = len(planes)
+    for i, t in enumerate(planes):
+        s.p[i] = t.data_ptr()
+    return s
+
+
 def lib():
     global _lib
     if _lib is None:

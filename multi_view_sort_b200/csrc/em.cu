@@ -20,11 +20,6 @@ namespace {
 constexpr int E1 = 1024;   // enc1 width, dec3 input width (train_nem.py:171,185)
 constexpr int E2 = 4096;   // enc2 / dec1 width (train_nem.py:175,181)
 
-struct Planes {
-  __nv_bfloat16* hi = nullptr;
-  __nv_bfloat16* lo = nullptr;
-};
-
 struct Bump {
   char* base;
   long long off = 0;
@@ -38,18 +33,19 @@ struct Bump {
   }
   Planes planes(long long count, int n) {
     Planes p;
-    p.hi = take<__nv_bfloat16>(count);
-    if (n == 2) p.lo = take<__nv_bfloat16>(count);
+    p.n = n;
+    for (int i = 0; i < n; ++i) p.p[i] = take<__nv_bfloat16>(count);
     return p;
   }
 };
 
 struct Dims {
-  int B, K, M, D, H, T, planes;
+  int B, K, M, D, H, T, planes, pb;   // pb: operand planes of the gradient contractions
+  int chain;                          // accumulation chain length in k-blocks (0 = unlimited)
   long long R, RM, BM, ZW;   // B*K, B*K*M, B*M, 1024*M
   int nblk;
   explicit Dims(const vmm_em_config& c)
-      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), R(1ll * c.B * c.K),
+      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), R(1ll * c.B * c.K),
         RM(1ll * c.B * c.K * c.M), BM(1ll * c.B * c.M), ZW(1ll * E1 * c.M), nblk(2 * ((c.D + 255) / 256)) {}
 };
 
@@ -171,21 +167,21 @@ struct Scratch {
       kappa = b.take<float>(d.RM);
       c1 = b.take<float>(d.RM);
       c2 = b.take<float>(d.RM);
-      dpred = b.planes(d.RM * d.D, d.planes);
+      dpred = b.planes(d.RM * d.D, d.pb);
       dz = b.take<float>(d.RM * E1);
-      dv5 = b.planes(d.R * d.ZW, d.planes);
+      dv5 = b.planes(d.R * d.ZW, d.pb);
       du = b.take<float>(d.R * E2);
-      dv4 = b.planes(d.R * E2, d.planes);
-      dgi = b.planes(d.R * 3 * d.H, d.planes);
-      dgh = b.planes(d.R * 3 * d.H, d.planes);
+      dv4 = b.planes(d.R * E2, d.pb);
+      dgi = b.planes(d.R * 3 * d.H, d.pb);
+      dgh = b.planes(d.R * 3 * d.H, d.pb);
       de = b.take<float>(d.R * E2);
-      dv2 = b.planes(d.R * E2, d.planes);
+      dv2 = b.planes(d.R * E2, d.pb);
       da = b.take<float>(d.R * d.ZW);
-      dg1 = b.planes(d.RM * E1, d.planes);
+      dg1 = b.planes(d.RM * E1, d.pb);
       dxw1 = b.take<float>(d.BM * E1);
-      dxw1p = b.planes(d.BM * E1, d.planes);
+      dxw1p = b.planes(d.BM * E1, d.pb);
       dw13 = b.take<float>(1ll * E1 * E1);
-      dw13p = b.planes(1ll * E1 * E1, d.planes);
+      dw13p = b.planes(1ll * E1 * E1, d.pb);
       dw1b3 = b.take<float>(E1);
     }
     bytes = b.off + 256;
@@ -196,40 +192,35 @@ int check_cfg(const vmm_em_config* c) {
   VMM_REQUIRE(c != nullptr, "null config");
   VMM_REQUIRE(c->B > 0 && c->K > 0 && c->M > 0 && c->D > 0 && c->H > 0 && c->T > 0, "non-positive dimension");
   VMM_REQUIRE(c->D % 8 == 0 && c->H % 8 == 0, "D and H must be multiples of 8");
-  VMM_REQUIRE(c->planes == 1 || c->planes == 2, "planes must be 1 or 2");
+  VMM_REQUIRE(c->planes >= 1 && c->planes <= 3, "planes must be 1, 2 or 3");
+  VMM_REQUIRE(c->planes_bwd >= 1 && c->planes_bwd <= c->planes, "planes_bwd must be in [1, planes]");
   VMM_REQUIRE(c->if_gamma_prior >= 0 && c->if_gamma_prior <= 2, "if_gamma_prior must be 0, 1 or 2");
   VMM_REQUIRE(c->sigma > 0.f && c->ln_eps > 0.f, "sigma and ln_eps must be positive");
+  VMM_REQUIRE(c->accum_chain >= 0, "accum_chain must be >= 0");
   VMM_REQUIRE(1ll * c->B * c->K * c->M < (1ll << 31) / 2, "too many rows for 32-bit indexing; split the batch");
   return 0;
 }
 
-// segment list of A (planes) x B (planes): low-order terms first
-int make_segs(vmm_gemm_seg* s, const Planes& a, long long lda, const Planes& b, long long ldb, long long k) {
-  int n = 0;
-  if (a.lo) s[n++] = {a.lo, lda, b.hi, ldb, k};
-  if (b.lo) s[n++] = {a.hi, lda, b.lo, ldb, k};
-  s[n++] = {a.hi, lda, b.hi, ldb, k};
-  return n;
-}
-
 // y[rows, n] = a[rows, k] * w[n, k]^T        (nn.Linear forward; bias is added by the consumer stage)
-int linear_fwd(const Planes& a, const Planes& w, long long rows, int n, long long k, float* y, cudaStream_t st) {
-  vmm_gemm_seg s[3];
+int linear_fwd(const Planes& a, const Planes& w, long long rows, int n, long long k, float* y, int chain,
+               cudaStream_t st) {
+  vmm_gemm_seg s[9];
   const int ns = make_segs(s, a, k, w, k, k);
-  return gemm_bf16(static_cast<int>(rows), n, ns, s, false, false, y, n, nullptr, false, 1, st);
+  return gemm_bf16(static_cast<int>(rows), n, ns, s, false, false, y, n, nullptr, false, 1, chain, st);
 }
 // dx[rows, k] (+)= dy[rows, n] * w[n, k]     (data gradient; w is read N-major, no transposed copy)
 int linear_dgrad(const Planes& dy, const Planes& w, long long rows, int n, long long k, float* dx, bool accumulate,
-                 cudaStream_t st) {
-  vmm_gemm_seg s[3];
-  const int ns = make_segs(s, dy, n, w, k, n);
-  return gemm_bf16(static_cast<int>(rows), static_cast<int>(k), ns, s, false, true, dx, k, nullptr, accumulate, 1, st);
+                 int chain, cudaStream_t st) {
+  vmm_gemm_seg s[9];
+  const int ns = make_segs(s, dy, n, w.first(dy.n), k, n);
+  return gemm_bf16(static_cast<int>(rows), static_cast<int>(k), ns, s, false, true, dx, k, nullptr, accumulate, 1, chain, st);
 }
 // dw[n, k] += dy[rows, n]^T * x[rows, k]     (weight gradient; both operands read MN-major, split-K)
-int linear_wgrad(const Planes& dy, const Planes& x, long long rows, int n, long long k, float* dw, cudaStream_t st) {
-  vmm_gemm_seg s[3];
-  const int ns = make_segs(s, dy, n, x, k, rows);
-  return gemm_bf16(n, static_cast<int>(k), ns, s, true, true, dw, k, nullptr, true, 0, st);
+int linear_wgrad(const Planes& dy, const Planes& x, long long rows, int n, long long k, float* dw, int chain,
+                 cudaStream_t st) {
+  vmm_gemm_seg s[9];
+  const int ns = make_segs(s, dy, n, x.first(dy.n), k, rows);
+  return gemm_bf16(n, static_cast<int>(k), ns, s, true, true, dw, k, nullptr, true, 0, chain, st);
 }
 
 LnDesc ln_desc(long long rows, long long width, const float* C, const float* bias, const float* g, const float* b,
@@ -256,19 +247,19 @@ int em_prepare(const vmm_em_config* c, const vmm_em_params* p, void* weights, vo
   (void)scratch;
   Dims d(*c);
   Weights w(*c, weights);
-  VMM_TRY(split_planes(p->enc1_w, 1ll * E1 * d.D, w.w1.hi, w.w1.lo, st));
-  VMM_TRY(split_planes(p->enc2_w, 1ll * E2 * d.ZW, w.w2.hi, w.w2.lo, st));
-  VMM_TRY(split_planes(p->gru_w_ih, 3ll * d.H * E2, w.wih.hi, w.wih.lo, st));
-  VMM_TRY(split_planes(p->gru_w_hh, 3ll * d.H * d.H, w.whh.hi, w.whh.lo, st));
-  VMM_TRY(split_planes(p->dec1_w, 1ll * E2 * d.H, w.w4.hi, w.w4.lo, st));
-  VMM_TRY(split_planes(p->dec2_w, d.ZW * E2, w.w5.hi, w.w5.lo, st));
-  VMM_TRY(split_planes(p->dec3_w, 1ll * d.D * E1, w.w3.hi, w.w3.lo, st));
+  VMM_TRY(split_planes(p->enc1_w, 1ll * E1 * d.D, w.w1, st));
+  VMM_TRY(split_planes(p->enc2_w, 1ll * E2 * d.ZW, w.w2, st));
+  VMM_TRY(split_planes(p->gru_w_ih, 3ll * d.H * E2, w.wih, st));
+  VMM_TRY(split_planes(p->gru_w_hh, 3ll * d.H * d.H, w.whh, st));
+  VMM_TRY(split_planes(p->dec1_w, 1ll * E2 * d.H, w.w4, st));
+  VMM_TRY(split_planes(p->dec2_w, d.ZW * E2, w.w5, st));
+  VMM_TRY(split_planes(p->dec3_w, 1ll * d.D * E1, w.w3, st));
   // W13[i, j] = sum_d W1[i, d] W3[d, j]:  A = W1 (K-major over d), B[n=j][k=d] = W3[d][j] (N-major)
   {
-    vmm_gemm_seg s[3];
+    vmm_gemm_seg s[9];
     const int ns = make_segs(s, w.w1, d.D, w.w3, E1, d.D);
-    VMM_TRY(gemm_bf16(E1, E1, ns, s, false, true, w.w13f, E1, nullptr, false, 1, st));
-    VMM_TRY(split_planes(w.w13f, 1ll * E1 * E1, w.w13.hi, w.w13.lo, st));
+    VMM_TRY(gemm_bf16(E1, E1, ns, s, false, true, w.w13f, E1, nullptr, false, 1, d.chain, st));
+    VMM_TRY(split_planes(w.w13f, 1ll * E1 * E1, w.w13, st));
   }
   VMM_TRY(gemv_rows(E1, d.D, p->enc1_w, p->dec3_b, w.w1b3, st));
   return 0;
@@ -289,12 +280,13 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
   // operand planes of the features and W1 x (once per batch)
   Planes xp = ws.x;
   if (c->x_is_bf16) {
-    xp.hi = static_cast<__nv_bfloat16*>(const_cast<void*>(x));
-    xp.lo = nullptr;
+    xp = Planes();
+    xp.n = 1;
+    xp.p[0] = static_cast<__nv_bfloat16*>(const_cast<void*>(x));     // bf16 features are their own (exact) plane
   } else {
-    VMM_TRY(split_planes(static_cast<const float*>(x), d.BM * d.D, xp.hi, xp.lo, st));
+    VMM_TRY(split_planes(static_cast<const float*>(x), d.BM * d.D, xp, st));
   }
-  VMM_TRY(linear_fwd(xp, w.w1, d.BM, E1, d.D, ws.xw1, st));
+  VMM_TRY(linear_fwd(xp, w.w1, d.BM, E1, d.D, ws.xw1, d.chain, st));
   VMM_CHECK_CUDA(cudaMemsetAsync(ws.h0, 0, sizeof(float) * d.R * d.H, st));
 
   for (int t = 0; t < d.T; ++t) {
@@ -303,7 +295,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
     const bool last = (t == d.T - 1);
     const float* gam_prev = t > 0 ? prev.gamma : gamma0;
     // --- enc1 on the responsibility-weighted residual (train_nem.py:280-284, 226)
-    if (t > 0) VMM_TRY(linear_fwd(prev.z, w.w13, d.RM, E1, E1, cur.g1, st));
+    if (t > 0) VMM_TRY(linear_fwd(prev.z, w.w13, d.RM, E1, E1, cur.g1, d.chain, st));
     {
       LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps);
       ln.xw1 = ws.xw1;
@@ -311,28 +303,28 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
       ln.gamma = gam_prev;
       ln.km = d.K * d.M;
       ln.mv = d.M;
-      VMM_TRY(ln_forward(LN_ENC1, ACT_ELU, ln, cur.a.hi, cur.a.lo, cur.mean1, cur.rstd1, st));
+      VMM_TRY(ln_forward(LN_ENC1, ACT_ELU, ln, cur.a, cur.mean1, cur.rstd1, st));
     }
     // --- enc2 (train_nem.py:228-229)
-    VMM_TRY(linear_fwd(cur.a, w.w2, d.R, E2, d.ZW, cur.g2, st));
-    VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps), cur.e.hi,
-                       cur.e.lo, cur.mean2, cur.rstd2, st));
+    VMM_TRY(linear_fwd(cur.a, w.w2, d.R, E2, d.ZW, cur.g2, d.chain, st));
+    VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps), cur.e,
+                       cur.mean2, cur.rstd2, st));
     // --- GRU (train_nem.py:232)
-    VMM_TRY(linear_fwd(cur.e, w.wih, d.R, 3 * d.H, E2, cur.gi, st));
-    if (t > 0) VMM_TRY(linear_fwd(prev.hp, w.whh, d.R, 3 * d.H, d.H, cur.gh, st));
+    VMM_TRY(linear_fwd(cur.e, w.wih, d.R, 3 * d.H, E2, cur.gi, d.chain, st));
+    if (t > 0) VMM_TRY(linear_fwd(prev.hp, w.whh, d.R, 3 * d.H, d.H, cur.gh, d.chain, st));
     else VMM_CHECK_CUDA(cudaMemsetAsync(cur.gh, 0, sizeof(float) * d.R * 3 * d.H, st));
     VMM_TRY(gru_forward(static_cast<int>(d.R), d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, t > 0 ? prev.h : ws.h0, cur.h,
-                        cur.hp.hi, cur.hp.lo, st));
+                        cur.hp, st));
     // --- dec1, dec2 (train_nem.py:238-240)
-    VMM_TRY(linear_fwd(cur.hp, w.w4, d.R, E2, d.H, cur.g4, st));
-    VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps), cur.u.hi,
-                       cur.u.lo, cur.mean4, cur.rstd4, st));
-    VMM_TRY(linear_fwd(cur.u, w.w5, d.R, static_cast<int>(d.ZW), E2, cur.g5, st));
-    VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps), cur.z.hi,
-                       cur.z.lo, cur.mean5, cur.rstd5, st));
+    VMM_TRY(linear_fwd(cur.hp, w.w4, d.R, E2, d.H, cur.g4, d.chain, st));
+    VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps), cur.u,
+                       cur.mean4, cur.rstd4, st));
+    VMM_TRY(linear_fwd(cur.u, w.w5, d.R, static_cast<int>(d.ZW), E2, cur.g5, d.chain, st));
+    VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps), cur.z,
+                       cur.mean5, cur.rstd5, st));
     // --- dec3 fused with the E-step (train_nem.py:241-270)
     const bool want_pp = last && c->if_gamma_prior == 0;
-    VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, d.planes, cur.z.hi, cur.z.lo, w.w3.hi, w.w3.lo, p->dec3_b, x,
+    VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, cur.z, w.w3, p->dec3_b, x,
                           c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
                           want_pp ? sc.part_pp : nullptr, st));
     VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
@@ -363,8 +355,9 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
 
   Planes xp = ws.x;
   if (c->x_is_bf16) {
-    xp.hi = static_cast<__nv_bfloat16*>(const_cast<void*>(x));
-    xp.lo = nullptr;
+    xp = Planes();
+    xp.n = 1;
+    xp.p[0] = static_cast<__nv_bfloat16*>(const_cast<void*>(x));
   }
   if (d_h) VMM_CHECK_CUDA(cudaMemcpyAsync(sc.dh, d_h, sizeof(float) * d.R * d.H, cudaMemcpyDeviceToDevice, st));
   else VMM_CHECK_CUDA(cudaMemsetAsync(sc.dh, 0, sizeof(float) * d.R * d.H, st));
@@ -391,45 +384,44 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_CHECK_CUDA(cudaMemsetAsync(sc.beta, 0, sizeof(float) * d.RM, st));
     }
     VMM_TRY(gamma_backward(d.B, d.K, d.M, c->sigma, cur.gamma, cur.inv_s, sc.dgamma, sc.alpha, st));
-    VMM_TRY(estep_backward(static_cast<int>(d.RM), d.D, E1, d.planes, cur.z.hi, cur.z.lo, w.w3.hi, w.w3.lo, p->dec3_b, x,
-                           c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.alpha, sc.beta, kappa, sc.dpred.hi, sc.dpred.lo,
-                           g->dec3_b, st));
+    VMM_TRY(estep_backward(static_cast<int>(d.RM), d.D, E1, cur.z, w.w3, p->dec3_b, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
+                           sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st));
     // --- dec3: weight gradient; dz = dpred W3 (+ dG1_{t+1} W13, the path through the next residual)
-    VMM_TRY(linear_wgrad(sc.dpred, cur.z, d.RM, d.D, E1, g->dec3_w, st));
+    VMM_TRY(linear_wgrad(sc.dpred, cur.z, d.RM, d.D, E1, g->dec3_w, d.chain, st));
     {
-      vmm_gemm_seg s[6];
-      int ns = make_segs(s, sc.dpred, d.D, w.w3, E1, d.D);
-      if (!last) ns += make_segs(s + ns, sc.dg1, E1, w.w13, E1, E1);
-      VMM_TRY(gemm_bf16(static_cast<int>(d.RM), E1, ns, s, false, true, sc.dz, E1, nullptr, false, 1, st));
+      vmm_gemm_seg s[18];
+      int ns = make_segs(s, sc.dpred, d.D, w.w3.first(d.pb), E1, d.D);
+      if (!last) ns += make_segs(s + ns, sc.dg1, E1, w.w13.first(d.pb), E1, E1);
+      VMM_TRY(gemm_bf16(static_cast<int>(d.RM), E1, ns, s, false, true, sc.dz, E1, nullptr, false, 1, d.chain, st));
     }
     // --- dec2: LayerNorm(1024*M) backward, dgrad, wgrad
     {
       LnDesc ln = ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps);
-      VMM_TRY(ln_backward_rows(LN_BIAS, ACT_NONE, ln, cur.mean5, cur.rstd5, sc.dz, d.ZW, sc.dv5.hi, sc.dv5.lo, sc.c1, sc.c2,
-                               nullptr, nullptr, nullptr, nullptr, st));
+      VMM_TRY(ln_backward_rows(LN_BIAS, ACT_NONE, ln, cur.mean5, cur.rstd5, sc.dz, d.ZW, sc.dv5, sc.c1, sc.c2, nullptr, nullptr,
+                               Planes(), st));
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_NONE, ln, cur.mean5, cur.rstd5, sc.c1, sc.c2, sc.dz, d.ZW, g->dec2_ln_g,
                                g->dec2_ln_b, g->dec2_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv5, w.w5, d.R, static_cast<int>(d.ZW), E2, sc.du, false, st));
-    VMM_TRY(linear_wgrad(sc.dv5, cur.u, d.R, static_cast<int>(d.ZW), E2, g->dec2_w, st));
+    VMM_TRY(linear_dgrad(sc.dv5, w.w5, d.R, static_cast<int>(d.ZW), E2, sc.du, false, d.chain, st));
+    VMM_TRY(linear_wgrad(sc.dv5, cur.u, d.R, static_cast<int>(d.ZW), E2, g->dec2_w, d.chain, st));
     // --- dec1
     {
       LnDesc ln = ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps);
-      VMM_TRY(ln_backward_rows(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.du, E2, sc.dv4.hi, sc.dv4.lo, sc.c1, sc.c2,
-                               nullptr, nullptr, nullptr, nullptr, st));
+      VMM_TRY(ln_backward_rows(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.du, E2, sc.dv4, sc.c1, sc.c2, nullptr, nullptr,
+                               Planes(), st));
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.c1, sc.c2, sc.du, E2, g->dec1_ln_g,
                                g->dec1_ln_b, g->dec1_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv4, w.w4, d.R, E2, d.H, dh, true, st));          // dh += dG4 W4
-    VMM_TRY(linear_wgrad(sc.dv4, cur.hp, d.R, E2, d.H, g->dec1_w, st));
+    VMM_TRY(linear_dgrad(sc.dv4, w.w4, d.R, E2, d.H, dh, true, d.chain, st));          // dh += dG4 W4
+    VMM_TRY(linear_wgrad(sc.dv4, cur.hp, d.R, E2, d.H, g->dec1_w, d.chain, st));
     // --- GRU
-    VMM_TRY(gru_backward(R, d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, t > 0 ? prev.h : ws.h0, dh, sc.dgi.hi, sc.dgi.lo,
-                         sc.dgh.hi, sc.dgh.lo, dh_prev, g->gru_b_ih, g->gru_b_hh, st));
-    VMM_TRY(linear_dgrad(sc.dgi, w.wih, d.R, 3 * d.H, E2, sc.de, false, st));
-    VMM_TRY(linear_wgrad(sc.dgi, cur.e, d.R, 3 * d.H, E2, g->gru_w_ih, st));
+    VMM_TRY(gru_backward(R, d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, t > 0 ? prev.h : ws.h0, dh, sc.dgi, sc.dgh,
+                         dh_prev, g->gru_b_ih, g->gru_b_hh, st));
+    VMM_TRY(linear_dgrad(sc.dgi, w.wih, d.R, 3 * d.H, E2, sc.de, false, d.chain, st));
+    VMM_TRY(linear_wgrad(sc.dgi, cur.e, d.R, 3 * d.H, E2, g->gru_w_ih, d.chain, st));
     if (t > 0) {
-      VMM_TRY(linear_dgrad(sc.dgh, w.whh, d.R, 3 * d.H, d.H, dh_prev, true, st));   // dh_{t-1} += dgh Whh
-      VMM_TRY(linear_wgrad(sc.dgh, prev.hp, d.R, 3 * d.H, d.H, g->gru_w_hh, st));
+      VMM_TRY(linear_dgrad(sc.dgh, w.whh, d.R, 3 * d.H, d.H, dh_prev, true, d.chain, st));   // dh_{t-1} += dgh Whh
+      VMM_TRY(linear_wgrad(sc.dgh, prev.hp, d.R, 3 * d.H, d.H, g->gru_w_hh, d.chain, st));
     }
     {
       float* tmp = dh;
@@ -439,13 +431,13 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     // --- enc2
     {
       LnDesc ln = ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps);
-      VMM_TRY(ln_backward_rows(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.de, E2, sc.dv2.hi, sc.dv2.lo, sc.c1, sc.c2,
-                               nullptr, nullptr, nullptr, nullptr, st));
+      VMM_TRY(ln_backward_rows(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.de, E2, sc.dv2, sc.c1, sc.c2, nullptr, nullptr,
+                               Planes(), st));
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.c1, sc.c2, sc.de, E2, g->enc2_ln_g,
                                g->enc2_ln_b, g->enc2_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv2, w.w2, d.R, E2, d.ZW, sc.da, false, st));
-    VMM_TRY(linear_wgrad(sc.dv2, cur.a, d.R, E2, d.ZW, g->enc2_w, st));
+    VMM_TRY(linear_dgrad(sc.dv2, w.w2, d.R, E2, d.ZW, sc.da, false, d.chain, st));
+    VMM_TRY(linear_wgrad(sc.dv2, cur.a, d.R, E2, d.ZW, g->enc2_w, d.chain, st));
     // --- enc1 + residual: dgamma_{t-1}, dXW1, dG1 (-> dz_{t-1} and dW13)
     {
       LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps);
@@ -454,26 +446,25 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       ln.gamma = gam_prev;
       ln.km = d.K * d.M;
       ln.mv = d.M;
-      VMM_TRY(ln_backward_rows(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, nullptr, nullptr, sc.c1, sc.c2,
-                               t > 0 ? sc.dgamma : nullptr, sc.dxw1, t > 0 ? sc.dg1.hi : nullptr,
-                               t > 0 ? sc.dg1.lo : nullptr, st));
+      VMM_TRY(ln_backward_rows(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, Planes(), sc.c1, sc.c2,
+                               t > 0 ? sc.dgamma : nullptr, sc.dxw1, t > 0 ? sc.dg1 : Planes(), st));
       VMM_TRY(ln_backward_cols(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.c1, sc.c2, sc.da, E1, g->enc1_ln_g,
                                g->enc1_ln_b, g->enc1_b, t > 0 ? sc.dw1b3 : nullptr, st));
     }
-    if (t > 0) VMM_TRY(linear_wgrad(sc.dg1, prev.z, d.RM, E1, E1, sc.dw13, st));
+    if (t > 0) VMM_TRY(linear_wgrad(sc.dg1, prev.z, d.RM, E1, E1, sc.dw13, d.chain, st));
   }
   // --- parameters behind the fold: XW1 = x W1^T, W13 = W1 W3, w1b3 = W1 b3
-  VMM_TRY(split_planes(sc.dxw1, d.BM * E1, sc.dxw1p.hi, sc.dxw1p.lo, st));
-  VMM_TRY(linear_wgrad(sc.dxw1p, xp, d.BM, E1, d.D, g->enc1_w, st));                       // dW1 += dXW1^T x
-  VMM_TRY(split_planes(sc.dw13, 1ll * E1 * E1, sc.dw13p.hi, sc.dw13p.lo, st));
+  VMM_TRY(split_planes(sc.dxw1, d.BM * E1, sc.dxw1p, st));
+  VMM_TRY(linear_wgrad(sc.dxw1p, xp, d.BM, E1, d.D, g->enc1_w, d.chain, st));                       // dW1 += dXW1^T x
+  VMM_TRY(split_planes(sc.dw13, 1ll * E1 * E1, sc.dw13p, st));
   {
-    vmm_gemm_seg s[3];
+    vmm_gemm_seg s[9];
     // dW1[i, d] += sum_j dW13[i, j] W3[d, j]
-    int ns = make_segs(s, sc.dw13p, E1, w.w3, E1, E1);
-    VMM_TRY(gemm_bf16(E1, d.D, ns, s, false, false, g->enc1_w, d.D, nullptr, true, 0, st));
+    int ns = make_segs(s, sc.dw13p, E1, w.w3.first(d.pb), E1, E1);
+    VMM_TRY(gemm_bf16(E1, d.D, ns, s, false, false, g->enc1_w, d.D, nullptr, true, 0, d.chain, st));
     // dW3[d, j] += sum_i W1[i, d] dW13[i, j]
-    ns = make_segs(s, w.w1, d.D, sc.dw13p, E1, E1);
-    VMM_TRY(gemm_bf16(d.D, E1, ns, s, true, true, g->dec3_w, E1, nullptr, true, 0, st));
+    ns = make_segs(s, w.w1.first(d.pb), d.D, sc.dw13p, E1, E1);
+    VMM_TRY(gemm_bf16(d.D, E1, ns, s, true, true, g->dec3_w, E1, nullptr, true, 0, d.chain, st));
   }
   VMM_TRY(rank1_update(E1, d.D, sc.dw1b3, p->dec3_b, g->enc1_w, st));                       // dW1 += dw1b3 b3^T
   VMM_TRY(gemv_cols_acc(E1, d.D, p->enc1_w, sc.dw1b3, g->dec3_b, st));                      // db3 += W1^T dw1b3
@@ -517,8 +508,8 @@ const void* vmm_em_workspace_ptr(const vmm_em_config* cfg, const void* workspace
   vmm::Workspace ws(*cfg, const_cast<void*>(workspace));
   const vmm::IterBufs b = ws.slot(iter);
   struct { const char* n; const void* p; } tab[] = {
-      {"xw1", ws.xw1}, {"g1", b.g1}, {"a_hi", b.a.hi}, {"g2", b.g2}, {"e_hi", b.e.hi}, {"gi", b.gi}, {"gh", b.gh},
-      {"h", b.h}, {"h_hi", b.hp.hi}, {"g4", b.g4}, {"u_hi", b.u.hi}, {"g5", b.g5}, {"z_hi", b.z.hi}, {"z_lo", b.z.lo},
+      {"xw1", ws.xw1}, {"g1", b.g1}, {"a_hi", b.a.p[0]}, {"g2", b.g2}, {"e_hi", b.e.p[0]}, {"gi", b.gi}, {"gh", b.gh},
+      {"h", b.h}, {"h_hi", b.hp.p[0]}, {"g4", b.g4}, {"u_hi", b.u.p[0]}, {"g5", b.g5}, {"z_hi", b.z.p[0]}, {"z_lo", b.z.p[1]},
       {"gamma", b.gamma}, {"row_sq", ws.row_sq}};
   for (auto& e : tab)
     if (strcmp(e.n, name) == 0) return e.p;

@@ -106,7 +106,7 @@ static int launch_major(const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t 
 }
 
 static int fill_common(GemmParams& p, int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool b_mn,
-                       int splits_req, bool allow_split) {
+                       int splits_req, bool allow_split, int chain_req) {
   constexpr int BN = 256;
   VMM_REQUIRE(M > 0 && N > 0, "empty problem M=%d N=%d", M, N);
   VMM_REQUIRE(nseg >= 1 && nseg <= VMM_MAX_SEG, "nseg=%d outside [1,%d]", nseg, VMM_MAX_SEG);
@@ -116,7 +116,7 @@ static int fill_common(GemmParams& p, int M, int N, int nseg, const vmm_gemm_seg
   p.nseg = nseg;
   p.num_m_blk = ceil_div(M, BM);
   p.num_n_blk = ceil_div(N, BN);
-  int total = 0;
+  int nkb_max = 0;
   for (int s = 0; s < nseg; ++s) {
     const vmm_gemm_seg& g = segs[s];
     VMM_REQUIRE(g.k > 0 && g.a && g.b, "segment %d is empty", s);
@@ -124,34 +124,38 @@ static int fill_common(GemmParams& p, int M, int N, int nseg, const vmm_gemm_seg
     else       VMM_TRY(make_tmap_bf16(&p.tma_a[s], g.a, M, g.k, g.lda, 64, BK));
     if (!b_mn) VMM_TRY(make_tmap_bf16(&p.tma_b[s], g.b, g.k, N, g.ldb, BK, BN));
     else       VMM_TRY(make_tmap_bf16(&p.tma_b[s], g.b, N, g.k, g.ldb, 64, BK));
-    total += ceil_div(g.k, BK);
-    p.kb_end[s] = total;
+    p.seg_kb[s] = ceil_div(g.k, BK);
+    if (p.seg_kb[s] > nkb_max) nkb_max = p.seg_kb[s];
   }
-  for (int s = nseg; s < VMM_MAX_SEG; ++s) p.kb_end[s] = 0x7fffffff;
-  p.total_kb = total;
-  int splits = 1;
+  // Accumulation chains and split-K.  chain_req > 0 bounds the k-blocks one TMEM accumulation may
+  // span (fp32-class modes); otherwise a chain is as long as the parallel split allows.
+  int chain = (chain_req > 0 && chain_req < nkb_max) ? chain_req : nkb_max;
+  int want = 1;
   if (allow_split) {
     if (splits_req > 0) {
-      splits = splits_req;
+      want = splits_req;
     } else {
-      // fill the machine when there are fewer output tiles than SMs and K is long
       const int tiles = p.num_m_blk * p.num_n_blk;
       const int sms = device_sm_count();
-      if (tiles < sms) splits = sms / tiles;
-      const int max_by_k = total / 8 > 0 ? total / 8 : 1;   // keep >= 8 k-blocks per split
-      if (splits > max_by_k) splits = max_by_k;
+      if (tiles < sms) want = sms / tiles;               // fill the machine when output tiles are few
+      const int max_by_k = nkb_max / 8 > 0 ? nkb_max / 8 : 1;   // keep >= 8 k-blocks per split
+      if (want > max_by_k) want = max_by_k;
     }
-    if (splits > total) splits = total;
-    if (splits < 1) splits = 1;
+    if (want > nkb_max) want = nkb_max;
+    if (want < 1) want = 1;
+    const int by_split = ceil_div(nkb_max, want);
+    if (by_split < chain) chain = by_split;
   }
-  p.splits = splits;
+  p.chain_kb = chain;
+  p.total_chains = ceil_div(nkb_max, chain);
+  p.splits = want < p.total_chains ? want : p.total_chains;
   return 0;
 }
 
 int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool b_mn, float* C, long long ldc,
-              const float* bias, bool accumulate, int splits, cudaStream_t stream) {
+              const float* bias, bool accumulate, int splits, int chain_kb, cudaStream_t stream) {
   GemmParams p;
-  VMM_TRY(fill_common(p, M, N, nseg, segs, a_mn, b_mn, splits, accumulate));
+  VMM_TRY(fill_common(p, M, N, nseg, segs, a_mn, b_mn, splits, accumulate, chain_kb));
   VMM_REQUIRE(C != nullptr && ldc >= N, "bad C / ldc");
   VMM_REQUIRE(!(accumulate && bias), "bias cannot be combined with accumulate");
   p.C = C;
@@ -163,40 +167,45 @@ int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool 
   return launch_major<EPI_STORE, float, 1>(p, a_mn, b_mn, stream);
 }
 
-static int estep_common(GemmParams& p, vmm_gemm_seg* segs, int rows, int D, int zk, int planes, const void* z_hi,
-                        const void* z_lo, const void* w3_hi, const void* w3_lo, const float* b3, const void* x,
-                        int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma) {
-  VMM_REQUIRE(planes == 1 || planes == 2, "planes must be 1 or 2");
-  VMM_REQUIRE(z_hi && w3_hi && b3 && x, "null operand");
-  VMM_REQUIRE(planes == 1 || (z_lo && w3_lo), "planes == 2 needs the lo planes");
+int make_segs(vmm_gemm_seg* s, const Planes& a, long long lda, const Planes& b, long long ldb, long long k) {
+  const int order = a.n > b.n ? a.n : b.n;
+  int n = 0;
+  for (int sum = order - 1; sum >= 0; --sum)
+    for (int i = 0; i < a.n; ++i) {
+      const int j = sum - i;
+      if (j < 0 || j >= b.n) continue;
+      s[n++] = {a.p[i], lda, b.p[j], ldb, k};
+    }
+  return n;
+}
+
+static int estep_common(GemmParams& p, int rows, int D, int zk, const Planes& z, const Planes& w3, const float* b3,
+                        const void* x, long long ldx, int k_latent, int m_views, float sigma) {
+  VMM_REQUIRE(z.n >= 1 && z.n <= 3 && w3.n >= 1 && w3.n <= 3, "planes must be 1, 2 or 3");
+  for (int i = 0; i < z.n; ++i) VMM_REQUIRE(z.p[i] != nullptr, "null z plane");
+  for (int i = 0; i < w3.n; ++i) VMM_REQUIRE(w3.p[i] != nullptr, "null W3 plane");
+  VMM_REQUIRE(b3 && x, "null operand");
   VMM_REQUIRE(D % 8 == 0 && zk % 8 == 0, "D and zk must be multiples of 8");
   VMM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(b3) & 15) == 0 &&
                   ldx % 8 == 0, "x / b3 must be 16-byte aligned, ldx a multiple of 8");
   VMM_REQUIRE(sigma > 0.f && k_latent > 0 && m_views > 0 && rows % (k_latent * m_views) == 0, "bad E-step geometry");
-  int nseg = 0;
-  if (planes == 2) {
-    segs[nseg++] = {z_lo, zk, w3_hi, zk, zk};
-    segs[nseg++] = {z_hi, zk, w3_lo, zk, zk};
-  }
-  segs[nseg++] = {z_hi, zk, w3_hi, zk, zk};
-  VMM_TRY(fill_common(p, rows, D, nseg, segs, false, false, 1, false));
+  vmm_gemm_seg segs[9];
+  const int nseg = make_segs(segs, z, zk, w3, zk, zk);
+  VMM_TRY(fill_common(p, rows, D, nseg, segs, false, false, 1, false, 0));
   p.bias = b3;
   p.x = x;
   p.ldx = ldx;
   p.km = k_latent * m_views;
   p.mv = m_views;
   p.exp_scale = -1.4426950408889634f / (2.f * sigma * sigma);
-  (void)x_is_bf16;
   return 0;
 }
 
-int estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
-                  const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
-                  int m_views, float sigma, float* part_e, float* part_sq, float* part_pp, cudaStream_t stream) {
+int estep_forward(int rows, int D, int zk, const Planes& z, const Planes& w3, const float* b3, const void* x,
+                  int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
+                  float* part_pp, cudaStream_t stream) {
   GemmParams p;
-  vmm_gemm_seg segs[3];
-  VMM_TRY(estep_common(p, segs, rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent,
-                       m_views, sigma));
+  VMM_TRY(estep_common(p, rows, D, zk, z, w3, b3, x, ldx, k_latent, m_views, sigma));
   VMM_REQUIRE(part_e != nullptr, "part_e is null");
   p.part_e = part_e;
   p.part_sq = part_sq;
@@ -205,30 +214,29 @@ int estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const v
   return launch_major<EPI_ESTEP, float, 1>(p, false, false, stream);
 }
 
-int estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
-                   const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
-                   int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
-                   void* dpred_hi, void* dpred_lo, float* colsum, cudaStream_t stream) {
+int estep_backward(int rows, int D, int zk, const Planes& z, const Planes& w3, const float* b3, const void* x,
+                   int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
+                   const float* beta, const float* kappa, const Planes& dpred, float* colsum, cudaStream_t stream) {
   GemmParams p;
-  vmm_gemm_seg segs[3];
-  VMM_TRY(estep_common(p, segs, rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent,
-                       m_views, sigma));
-  VMM_REQUIRE(alpha && beta && dpred_hi && (planes == 1 || dpred_lo), "null E-step backward argument");
-  VMM_REQUIRE((reinterpret_cast<uintptr_t>(dpred_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(dpred_lo) & 15) == 0,
-              "dpred planes must be 16-byte aligned");
+  VMM_TRY(estep_common(p, rows, D, zk, z, w3, b3, x, ldx, k_latent, m_views, sigma));
+  VMM_REQUIRE(alpha && beta && dpred.n >= 1 && dpred.n <= 3, "null E-step backward argument");
+  for (int i = 0; i < dpred.n; ++i) {
+    VMM_REQUIRE(dpred.p[i] && (reinterpret_cast<uintptr_t>(dpred.p[i]) & 15) == 0, "dpred planes must be 16-byte aligned");
+    p.out_p[i] = dpred.p[i];
+  }
   p.row_alpha = alpha;
   p.row_beta = beta;
   p.row_kappa = kappa;
-  p.out_hi = static_cast<__nv_bfloat16*>(dpred_hi);
-  p.out_lo = static_cast<__nv_bfloat16*>(dpred_lo);
   p.ldo = D;
   p.colsum = colsum;
-  if (planes == 2) {
-    if (x_is_bf16) return launch_major<EPI_EBWD, __nv_bfloat16, 2>(p, false, false, stream);
-    return launch_major<EPI_EBWD, float, 2>(p, false, false, stream);
+  if (x_is_bf16) {
+    if (dpred.n == 1) return launch_major<EPI_EBWD, __nv_bfloat16, 1>(p, false, false, stream);
+    if (dpred.n == 2) return launch_major<EPI_EBWD, __nv_bfloat16, 2>(p, false, false, stream);
+    return launch_major<EPI_EBWD, __nv_bfloat16, 3>(p, false, false, stream);
   }
-  if (x_is_bf16) return launch_major<EPI_EBWD, __nv_bfloat16, 1>(p, false, false, stream);
-  return launch_major<EPI_EBWD, float, 1>(p, false, false, stream);
+  if (dpred.n == 1) return launch_major<EPI_EBWD, float, 1>(p, false, false, stream);
+  if (dpred.n == 2) return launch_major<EPI_EBWD, float, 2>(p, false, false, stream);
+  return launch_major<EPI_EBWD, float, 3>(p, false, false, stream);
 }
 
 // ---- plain CUDA cross-check (tests only) ---------------------------------------------------
@@ -254,25 +262,30 @@ __global__ void gemm_check_kernel(int M, int N, int nseg, vmm_gemm_seg s0, vmm_g
   else *dst = acc + (bias ? bias[n] : 0.f);
 }
 
-__global__ void split_planes_kernel(const float* __restrict__ src, long long n, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo) {
+__global__ void split_planes_kernel(const float* __restrict__ src, long long n, __nv_bfloat16* __restrict__ p0,
+                                    __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float v = src[i];
+    float v = src[i];
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    hi[i] = h;
-    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    p0[i] = h;
+    if (p1) {
+      v -= __bfloat162float(h);
+      const __nv_bfloat16 m = __float2bfloat16_rn(v);
+      p1[i] = m;
+      if (p2) p2[i] = __float2bfloat16_rn(v - __bfloat162float(m));
+    }
   }
 }
 
-int split_planes(const float* src, long long n, void* hi, void* lo, cudaStream_t stream) {
+int split_planes(const float* src, long long n, const Planes& out, cudaStream_t stream) {
   if (n <= 0) return 0;
-  VMM_REQUIRE(src && hi, "null pointer");
+  VMM_REQUIRE(src && out.n >= 1 && out.n <= 3 && out.p[0], "split_planes: bad argument");
   long long blocks = (n + 255) / 256;
   const long long cap = static_cast<long long>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  split_planes_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, n, static_cast<__nv_bfloat16*>(hi),
-                                                                    static_cast<__nv_bfloat16*>(lo));
+  split_planes_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, n, out.p[0], out.n > 1 ? out.p[1] : nullptr,
+                                                                    out.n > 2 ? out.p[2] : nullptr);
   VMM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -286,9 +299,9 @@ int vmm_version(void) { return VMM_ABI_VERSION; }
 const char* vmm_last_error(void) { return vmm::g_err; }
 
 int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major, float* C,
-                  long long ldc, const float* bias, int accumulate, int splits, void* stream) {
+                  long long ldc, const float* bias, int accumulate, int splits, int chain_kblocks, void* stream) {
   return vmm::gemm_bf16(M, N, nseg, segs, a_mn_major != 0, b_mn_major != 0, C, ldc, bias, accumulate != 0, splits,
-                        static_cast<cudaStream_t>(stream));
+                        chain_kblocks, static_cast<cudaStream_t>(stream));
 }
 
 int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major, float* C,
@@ -306,25 +319,25 @@ int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_ma
   return 0;
 }
 
-int vmm_split_planes(const float* src, long long n, void* hi, void* lo, void* stream) {
-  return vmm::split_planes(src, n, hi, lo, static_cast<cudaStream_t>(stream));
+int vmm_split_planes(const float* src, long long n, const vmm_planes* out, void* stream) {
+  return vmm::split_planes(src, n, vmm::planes_from_c(out), static_cast<cudaStream_t>(stream));
 }
 
 int vmm_estep_num_blocks(int D) { return 2 * ((D + 255) / 256); }
 
-int vmm_estep_forward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
-                      const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
-                      int m_views, float sigma, float* part_e, float* part_sq, float* part_pp, void* stream) {
-  return vmm::estep_forward(rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent, m_views,
-                            sigma, part_e, part_sq, part_pp, static_cast<cudaStream_t>(stream));
+int vmm_estep_forward(int rows, int D, int zk, const vmm_planes* z, const vmm_planes* w3, const float* b3, const void* x,
+                      int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
+                      float* part_pp, void* stream) {
+  return vmm::estep_forward(rows, D, zk, vmm::planes_from_c(z), vmm::planes_from_c(w3), b3, x, x_is_bf16, ldx, k_latent,
+                            m_views, sigma, part_e, part_sq, part_pp, static_cast<cudaStream_t>(stream));
 }
 
-int vmm_estep_backward(int rows, int D, int zk, int planes, const void* z_hi, const void* z_lo, const void* w3_hi,
-                       const void* w3_lo, const float* b3, const void* x, int x_is_bf16, long long ldx, int k_latent,
-                       int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
-                       void* dpred_hi, void* dpred_lo, float* d_b3, void* stream) {
-  return vmm::estep_backward(rows, D, zk, planes, z_hi, z_lo, w3_hi, w3_lo, b3, x, x_is_bf16, ldx, k_latent, m_views,
-                             sigma, alpha, beta, kappa, dpred_hi, dpred_lo, d_b3, static_cast<cudaStream_t>(stream));
+int vmm_estep_backward(int rows, int D, int zk, const vmm_planes* z, const vmm_planes* w3, const float* b3, const void* x,
+                       int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
+                       const float* beta, const float* kappa, const vmm_planes* dpred, float* d_b3, void* stream) {
+  return vmm::estep_backward(rows, D, zk, vmm::planes_from_c(z), vmm::planes_from_c(w3), b3, x, x_is_bf16, ldx, k_latent,
+                             m_views, sigma, alpha, beta, kappa, vmm::planes_from_c(dpred), d_b3,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -4,9 +4,9 @@
 //
 // The K loop runs over up to VMM_MAX_SEG "segments", each with its own pair of TMA tensor
 // maps.  Segments are how the library gets fp32-class accuracy out of bf16 tensor cores
-// (error-compensated split: A = A_hi + A_lo, B = B_hi + B_lo -> segments (A_lo,B_hi),
-// (A_hi,B_lo), (A_hi,B_hi)) and how two contractions that land in the same output are
-// fused into one launch.
+// (error-compensated split: A = A_0 + A_1 (+ A_2) in successive bf16 residuals, likewise B, and
+// the segments are the cross terms A_i B_j with i + j below the split order) and how two
+// contractions that land in the same output are fused into one launch.
 //
 // One CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
 // (one elected lane), warps 2..9 = epilogue (two warps per 32-lane TMEM group, each taking half
@@ -30,7 +30,7 @@
 
 namespace vmm {
 
-constexpr int VMM_MAX_SEG = 8;
+constexpr int VMM_MAX_SEG = 12;
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int EPI_WARPS = 8;
@@ -43,9 +43,10 @@ enum { EPI_STORE = 0, EPI_RED = 1, EPI_ESTEP = 2, EPI_EBWD = 3 };
 struct alignas(64) GemmParams {
   CUtensorMap tma_a[VMM_MAX_SEG];
   CUtensorMap tma_b[VMM_MAX_SEG];
-  int kb_end[VMM_MAX_SEG];   // running total of k-blocks at the end of each segment
+  int seg_kb[VMM_MAX_SEG];   // k-blocks (of BK) in each segment
   int nseg;
-  int total_kb;
+  int chain_kb;              // k-blocks per segment accumulated in TMEM before the epilogue drains them
+  int total_chains;          // ceil(max seg_kb / chain_kb)
   int M, N;
   int num_m_blk, num_n_blk;
   int splits;
@@ -65,8 +66,7 @@ struct alignas(64) GemmParams {
   const float* row_alpha;    // EBWD per-row scalars
   const float* row_beta;
   const float* row_kappa;    // nullable
-  __nv_bfloat16* out_hi;     // EBWD output planes [M, ldo]
-  __nv_bfloat16* out_lo;     // nullable
+  __nv_bfloat16* out_p[3];   // EBWD output planes [M, ldo]: successive bf16 residuals (hi, mid, lo)
   long long ldo;
   float* colsum;             // EBWD: [N] += column sums of dL/dpred (dec3 bias gradient), nullable
 };
@@ -82,8 +82,13 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + BAR_BYTES;
 };
 
+// One work item = one output tile x one contiguous range of accumulation chains [c0, c1).
+// A chain is what the tensor core accumulates in TMEM before the epilogue drains it: the MMA
+// datapath truncates (round-toward-zero) at every accumulate step, so fp32-class modes keep
+// chains short and let the epilogue do the long-range accumulation in round-to-nearest fp32
+// (first chain stores, later chains add: same CTA, same thread, same address - no atomics).
 struct WorkItem {
-  int m_blk, n_blk, kb0, kb1;
+  int m_blk, n_blk, c0, c1;
 };
 
 __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work) {
@@ -97,8 +102,8 @@ __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work) {
   const int in_group = tile - group * per_group;
   w.m_blk = first_m + in_group % gsize;
   w.n_blk = in_group / gsize;
-  w.kb0 = static_cast<int>((static_cast<long long>(p.total_kb) * split) / p.splits);
-  w.kb1 = static_cast<int>((static_cast<long long>(p.total_kb) * (split + 1)) / p.splits);
+  w.c0 = static_cast<int>((static_cast<long long>(p.total_chains) * split) / p.splits);
+  w.c1 = static_cast<int>((static_cast<long long>(p.total_chains) * (split + 1)) / p.splits);
   return w;
 }
 
@@ -166,7 +171,7 @@ __device__ __forceinline__ void x_stage(const XRegs<XT>& xr, float4* st, int lan
 // STORE / RED: accumulator chunk -> staging (row per lane) -> coalesced 4-rows-per-instruction.
 template <int EPI>
 __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint32_t (&v)[32], float4* st, int row0,
-                                                int col0, int lane) {
+                                                int col0, int lane, bool add_to_c) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     st[st_slot(lane, j)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -181,7 +186,10 @@ __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint3
       float* dst = p.C + static_cast<long long>(grow) * p.ldc + gcol;
       if (p.vec_ok && gcol + 3 < p.N) {
         if constexpr (EPI == EPI_STORE) {
-          if (p.bias) {
+          if (add_to_c) {
+            const float4 o = *reinterpret_cast<const float4*>(dst);
+            val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+          } else if (p.bias) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
             val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
           }
@@ -194,7 +202,7 @@ __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint3
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           if (gcol + q < p.N) {
-            if constexpr (EPI == EPI_STORE) dst[q] = e[q] + (p.bias ? __ldg(p.bias + gcol + q) : 0.f);
+            if constexpr (EPI == EPI_STORE) dst[q] = e[q] + (add_to_c ? dst[q] : (p.bias ? __ldg(p.bias + gcol + q) : 0.f));
             else atomicAdd(dst + q, e[q]);
           }
       }
@@ -252,10 +260,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       uint32_t phase = 0;
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         const WorkItem w = decode_work(p, work);
-        int seg = 0;
-        for (int g = w.kb0; g < w.kb1; ++g) {
-          while (g >= p.kb_end[seg]) ++seg;
-          const int kb = g - (seg ? p.kb_end[seg - 1] : 0);
+        for (int ch = w.c0; ch < w.c1; ++ch)
+        for (int seg = 0; seg < p.nseg; ++seg) {
+        const int k_lo = ch * p.chain_kb, k_hi = min(k_lo + p.chain_kb, p.seg_kb[seg]);
+        for (int kb = k_lo; kb < k_hi; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -276,6 +284,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        }
       }
     }
   } else if (warp == 1) {
@@ -287,10 +296,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     uint32_t acc_phase = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       const WorkItem w = decode_work(p, work);
+      for (int ch = w.c0; ch < w.c1; ++ch) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-      for (int g = w.kb0; g < w.kb1; ++g) {
+      bool first = true;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+      const int k_lo = ch * p.chain_kb, k_hi = min(k_lo + p.chain_kb, p.seg_kb[seg]);
+      for (int kb = k_lo; kb < k_hi; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
@@ -305,16 +318,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                                         : umma_smem_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_base + k * 2048, 64 * BK * 2, 1024)
                                         : umma_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (g > w.kb0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (g == w.kb1 - 1) umma_commit(&tfull_bar[acc]);
         }
+        first = false;
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      }
+      if (lane == 0) umma_commit(&tfull_bar[acc]);       // arrives once every MMA of this chain has completed
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+      }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -332,6 +349,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const WorkItem w = decode_work(p, work);
       const int row0 = w.m_blk * BM + lane_grp * 32;                 // first row of this warp
       const int nbase = w.n_blk * BN + col_half * (BN / 2);
+      for (int ch = w.c0; ch < w.c1; ++ch) {
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                               static_cast<uint32_t>(acc * BN + col_half * (BN / 2));
 
@@ -362,7 +380,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr0 + static_cast<uint32_t>((c + 1) * 32), vn);
         if (col0 < p.N) {                                            // warp-uniform
           if constexpr (!kFused) {
-            epi_store_chunk<EPI>(p, v, st, row0, col0, lane);
+            epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0);
           } else {
             x_stage<XT>(xr, st, lane);
             if (c + 1 < NCH) x_fetch<XT>(p, xr, row0, col0 + 32, lane);
@@ -410,18 +428,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 uint32_t w16[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                  float a = out[2 * q], b = out[2 * q + 1];
-                  if (pl == 1) {
-                    a -= __bfloat162float(__float2bfloat16_rn(a));
-                    b -= __bfloat162float(__float2bfloat16_rn(b));
+                  w16[q] = pack_bf16x2(out[2 * q], out[2 * q + 1]);
+                  if (pl + 1 < OPL) {                                // residual for the next plane
+                    out[2 * q] -= bf16_bits_to_float(w16[q] & 0xffffu);
+                    out[2 * q + 1] -= bf16_bits_to_float(w16[q] >> 16);
                   }
-                  w16[q] = pack_bf16x2(a, b);
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                   stw[lane * 4 + (q ^ ((lane >> 1) & 3))] = make_uint4(w16[4 * q], w16[4 * q + 1], w16[4 * q + 2], w16[4 * q + 3]);
                 __syncwarp();
-                __nv_bfloat16* outp = pl == 0 ? p.out_hi : p.out_lo;
+                __nv_bfloat16* outp = p.out_p[pl];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const int r = j * 8 + (lane >> 2), q = lane & 3;
@@ -449,6 +466,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+      }
     }
   }
 

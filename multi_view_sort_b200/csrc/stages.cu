@@ -41,25 +41,31 @@ __device__ __forceinline__ float act_grad(int act, float y) {
   return 1.f;
 }
 
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, float4 v) {
-  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u;
-  u.x = *reinterpret_cast<const uint32_t*>(&h0);
-  u.y = *reinterpret_cast<const uint32_t*>(&h1);
-  *reinterpret_cast<uint2*>(hi + idx) = u;
-  if (lo) {
-    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
-    const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
-    u.x = *reinterpret_cast<const uint32_t*>(&l0);
-    u.y = *reinterpret_cast<const uint32_t*>(&l1);
-    *reinterpret_cast<uint2*>(lo + idx) = u;
+__device__ __forceinline__ void store_planes4(const Planes& P, long long idx, float4 v) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < P.n) {
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&h0);
+      u.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(P.p[i] + idx) = u;
+      if (i + 1 < P.n) {
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        v = make_float4(v.x - f0.x, v.y - f0.y, v.z - f1.x, v.w - f1.y);
+      }
+    }
   }
 }
-__device__ __forceinline__ void store_planes1(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx, float v) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  hi[idx] = h;
-  if (lo) lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+__device__ __forceinline__ void store_planes1(const Planes& P, long long idx, float v) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < P.n) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      P.p[i][idx] = h;
+      v -= __bfloat162float(h);
+    }
+  }
 }
 
 // Pre-normalisation value of 4 consecutive columns, and (LN_ENC1) the residual factor s with
@@ -85,8 +91,8 @@ __device__ __forceinline__ float4 ln_value4(const LnDesc& d, int row, long long 
 // LayerNorm (+activation) forward: one block per row.
 // ------------------------------------------------------------------------------------------
 template <int MODE, bool CACHED>
-__global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int act, __nv_bfloat16* out_hi,
-                                                                __nv_bfloat16* out_lo, float* mean_out, float* rstd_out) {
+__global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int act, Planes out,
+                                                                float* mean_out, float* rstd_out) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int ac
     o.y = act_fwd(act, fmaf((v.y - mean) * rstd, g.y, b.y));
     o.z = act_fwd(act, fmaf((v.z - mean) * rstd, g.z, b.z));
     o.w = act_fwd(act, fmaf((v.w - mean) * rstd, g.w, b.w));
-    store_planes4(out_hi, out_lo, obase + c, o);
+    store_planes4(out, obase + c, o);
   };
   if (CACHED) {
 #pragma unroll
@@ -167,8 +173,8 @@ __global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int ac
 template <int MODE>
 __global__ void __launch_bounds__(LN_THREADS) ln_backward_rows_kernel(
     LnDesc d, int act, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-    const float* __restrict__ d_out, long long ldd, __nv_bfloat16* dv_hi, __nv_bfloat16* dv_lo, float* c1_out,
-    float* c2_out, float* dgamma, float* dxw1, __nv_bfloat16* dg1_hi, __nv_bfloat16* dg1_lo) {
+    const float* __restrict__ d_out, long long ldd, Planes dvp, float* c1_out, float* c2_out, float* dgamma,
+    float* dxw1, Planes dg1) {
   __shared__ float red[32];
   const int tid = threadIdx.x;
   const int klat = (MODE == LN_ENC1) ? d.km / d.mv : 1;
@@ -225,9 +231,9 @@ __global__ void __launch_bounds__(LN_THREADS) ln_backward_rows_kernel(
         if (MODE == LN_ENC1) dgam = fmaf(dv[q], ss[q], dgam);
       }
       const long long o = static_cast<long long>(row) * d.width + c;
-      if (dv_hi) store_planes4(dv_hi, dv_lo, o, make_float4(dv[0], dv[1], dv[2], dv[3]));
+      if (dvp.n) store_planes4(dvp, o, make_float4(dv[0], dv[1], dv[2], dv[3]));
       if (MODE == LN_ENC1) {
-        if (dg1_hi) store_planes4(dg1_hi, dg1_lo, o, make_float4(-gam * dv[0], -gam * dv[1], -gam * dv[2], -gam * dv[3]));
+        if (dg1.n) store_planes4(dg1, o, make_float4(-gam * dv[0], -gam * dv[1], -gam * dv[2], -gam * dv[3]));
         if (dxw1) {
           float4* px = reinterpret_cast<float4*>(dxw1 + xrow * d.width + c);   // this block owns the row
           float4 a = *px;
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(256) gru_forward_kernel(int rows, int H, const
                                                           const float* __restrict__ gh, const float* __restrict__ b_ih,
                                                           const float* __restrict__ b_hh,
                                                           const float* __restrict__ h_prev, float* __restrict__ h_new,
-                                                          __nv_bfloat16* h_hi, __nv_bfloat16* h_lo) {
+                                                          Planes hp_out) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * H) return;
   const int row = static_cast<int>(idx / H), j = static_cast<int>(idx % H);
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(256) gru_forward_kernel(int rows, int H, const
   const float hp = h_prev[idx];
   const float h = (hp - n) * z + n;
   h_new[idx] = h;
-  store_planes1(h_hi, h_lo, idx, h);
+  store_planes1(hp_out, idx, h);
 }
 
 // thread per hidden column j, blockIdx.y strides over row chunks (bias gradients need column sums)
@@ -316,8 +322,7 @@ __global__ void __launch_bounds__(256) gru_backward_kernel(int rows, int H, int 
                                                            const float* __restrict__ gi, const float* __restrict__ gh,
                                                            const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                                                            const float* __restrict__ h_prev, const float* __restrict__ dh,
-                                                           __nv_bfloat16* dgi_hi, __nv_bfloat16* dgi_lo,
-                                                           __nv_bfloat16* dgh_hi, __nv_bfloat16* dgh_lo,
+                                                           Planes dgi, Planes dgh,
                                                            float* __restrict__ dh_prev, float* d_b_ih, float* d_b_hh) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= H) return;
@@ -342,12 +347,12 @@ __global__ void __launch_bounds__(256) gru_backward_kernel(int rows, int H, int 
     const float dr_pre = dn_pre * ghn * r * (1.f - r);
     const float dz_pre = dz * z * (1.f - z);
     const float dhn = dn_pre * r;
-    store_planes1(dgi_hi, dgi_lo, g0, dr_pre);
-    store_planes1(dgi_hi, dgi_lo, g0 + H, dz_pre);
-    store_planes1(dgi_hi, dgi_lo, g0 + 2 * H, dn_pre);
-    store_planes1(dgh_hi, dgh_lo, g0, dr_pre);
-    store_planes1(dgh_hi, dgh_lo, g0 + H, dz_pre);
-    store_planes1(dgh_hi, dgh_lo, g0 + 2 * H, dhn);
+    store_planes1(dgi, g0, dr_pre);
+    store_planes1(dgi, g0 + H, dz_pre);
+    store_planes1(dgi, g0 + 2 * H, dn_pre);
+    store_planes1(dgh, g0, dr_pre);
+    store_planes1(dgh, g0 + H, dz_pre);
+    store_planes1(dgh, g0 + 2 * H, dhn);
     dh_prev[hidx] = g * z;
     s_r += dr_pre;
     s_z += dz_pre;
@@ -569,8 +574,7 @@ __global__ void __launch_bounds__(256) colsum_acc_kernel(int rows, int width, in
   atomicAdd(out + j, s);
 }
 __global__ void __launch_bounds__(256) act_planes_kernel(int act, long long rows, int width,
-                                                         const float* __restrict__ src, long long ld,
-                                                         __nv_bfloat16* hi, __nv_bfloat16* lo) {
+                                                         const float* __restrict__ src, long long ld, Planes out) {
   const long long n4 = rows * (width / 4);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -578,7 +582,7 @@ __global__ void __launch_bounds__(256) act_planes_kernel(int act, long long rows
     const int c = static_cast<int>(i % (width / 4)) * 4;
     float4 v = ld4(src + r * ld + c);
     v.x = act_fwd(act, v.x); v.y = act_fwd(act, v.y); v.z = act_fwd(act, v.z); v.w = act_fwd(act, v.w);
-    store_planes4(hi, lo, r * width + c, v);
+    store_planes4(out, r * width + c, v);
   }
 }
 __global__ void __launch_bounds__(256) act_backward_kernel(int act, long long n, const float* __restrict__ pre,
@@ -614,39 +618,34 @@ static int check_ln(const LnDesc& d, int mode) {
   return 0;
 }
 
-int ln_forward(int mode, int act, const LnDesc& d, void* out_hi, void* out_lo, float* mean, float* rstd,
-               cudaStream_t stream) {
+int ln_forward(int mode, int act, const LnDesc& d, const Planes& out, float* mean, float* rstd, cudaStream_t stream) {
   VMM_TRY(check_ln(d, mode));
-  VMM_REQUIRE(out_hi && mean && rstd, "ln_forward: null output");
-  auto* hi = static_cast<__nv_bfloat16*>(out_hi);
-  auto* lo = static_cast<__nv_bfloat16*>(out_lo);
+  VMM_REQUIRE(out.n >= 1 && out.p[0] && mean && rstd, "ln_forward: null output");
   const bool cached = d.width <= LN_THREADS * 4 * LN_CACHE;
   if (mode == LN_BIAS) {
-    if (cached) ln_forward_kernel<LN_BIAS, true><<<d.rows, LN_THREADS, 0, stream>>>(d, act, hi, lo, mean, rstd);
-    else ln_forward_kernel<LN_BIAS, false><<<d.rows, LN_THREADS, 0, stream>>>(d, act, hi, lo, mean, rstd);
+    if (cached) ln_forward_kernel<LN_BIAS, true><<<d.rows, LN_THREADS, 0, stream>>>(d, act, out, mean, rstd);
+    else ln_forward_kernel<LN_BIAS, false><<<d.rows, LN_THREADS, 0, stream>>>(d, act, out, mean, rstd);
   } else {
-    if (cached) ln_forward_kernel<LN_ENC1, true><<<d.rows, LN_THREADS, 0, stream>>>(d, act, hi, lo, mean, rstd);
-    else ln_forward_kernel<LN_ENC1, false><<<d.rows, LN_THREADS, 0, stream>>>(d, act, hi, lo, mean, rstd);
+    if (cached) ln_forward_kernel<LN_ENC1, true><<<d.rows, LN_THREADS, 0, stream>>>(d, act, out, mean, rstd);
+    else ln_forward_kernel<LN_ENC1, false><<<d.rows, LN_THREADS, 0, stream>>>(d, act, out, mean, rstd);
   }
   VMM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out,
-                     long long ldd, void* dv_hi, void* dv_lo, float* c1, float* c2, float* dgamma, float* dxw1,
-                     void* dg1_hi, void* dg1_lo, cudaStream_t stream) {
+                     long long ldd, const Planes& dv, float* c1, float* c2, float* dgamma, float* dxw1, const Planes& dg1,
+                     cudaStream_t stream) {
   VMM_TRY(check_ln(d, mode));
-  VMM_REQUIRE(mean && rstd && d_out && c1 && c2 && ldd % 4 == 0 && (dv_hi || mode == LN_ENC1), "ln_backward_rows: null argument");
-  auto* hi = static_cast<__nv_bfloat16*>(dv_hi);
-  auto* lo = static_cast<__nv_bfloat16*>(dv_lo);
+  VMM_REQUIRE(mean && rstd && d_out && c1 && c2 && ldd % 4 == 0 && (dv.n > 0 || mode == LN_ENC1),
+              "ln_backward_rows: null argument");
   if (mode == LN_BIAS) {
-    ln_backward_rows_kernel<LN_BIAS><<<d.rows, LN_THREADS, 0, stream>>>(d, act, mean, rstd, d_out, ldd, hi, lo, c1, c2,
-                                                                          nullptr, nullptr, nullptr, nullptr);
+    ln_backward_rows_kernel<LN_BIAS><<<d.rows, LN_THREADS, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2, nullptr,
+                                                                          nullptr, Planes());
   } else {
     const int groups = d.rows / d.km * d.mv;      // feature rows (b, m)
-    ln_backward_rows_kernel<LN_ENC1><<<groups, LN_THREADS, 0, stream>>>(
-        d, act, mean, rstd, d_out, ldd, hi, lo, c1, c2, dgamma, dxw1, static_cast<__nv_bfloat16*>(dg1_hi),
-        static_cast<__nv_bfloat16*>(dg1_lo));
+    ln_backward_rows_kernel<LN_ENC1><<<groups, LN_THREADS, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2, dgamma,
+                                                                          dxw1, dg1);
   }
   VMM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -671,27 +670,25 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
 }
 
 int gru_forward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
-                const float* h_prev, float* h_new, void* h_hi, void* h_lo, cudaStream_t stream) {
-  VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && h_new && h_hi, "gru_forward: bad argument");
+                const float* h_prev, float* h_new, const Planes& hp, cudaStream_t stream) {
+  VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && h_new && hp.n >= 1, "gru_forward: bad argument");
   const long long n = static_cast<long long>(rows) * H;
-  gru_forward_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      rows, H, gi, gh, b_ih, b_hh, h_prev, h_new, static_cast<__nv_bfloat16*>(h_hi), static_cast<__nv_bfloat16*>(h_lo));
+  gru_forward_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, h_new,
+                                                                                 hp);
   VMM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int gru_backward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
-                 const float* h_prev, const float* dh, void* dgi_hi, void* dgi_lo, void* dgh_hi, void* dgh_lo,
-                 float* dh_prev, float* d_b_ih, float* d_b_hh, cudaStream_t stream) {
-  VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && dh && dgi_hi && dgh_hi && dh_prev && d_b_ih &&
-                  d_b_hh, "gru_backward: bad argument");
+                 const float* h_prev, const float* dh, const Planes& dgi, const Planes& dgh, float* dh_prev, float* d_b_ih,
+                 float* d_b_hh, cudaStream_t stream) {
+  VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && dh && dgi.n >= 1 && dgh.n >= 1 && dh_prev &&
+                  d_b_ih && d_b_hh, "gru_backward: bad argument");
   const int col_blocks = ceil_div(H, 256);
   const int rpb = pick_rows_per_block(rows, col_blocks);
   dim3 grid(col_blocks, ceil_div(rows, rpb));
-  gru_backward_kernel<<<grid, 256, 0, stream>>>(rows, H, rpb, gi, gh, b_ih, b_hh, h_prev, dh,
-                                                static_cast<__nv_bfloat16*>(dgi_hi), static_cast<__nv_bfloat16*>(dgi_lo),
-                                                static_cast<__nv_bfloat16*>(dgh_hi), static_cast<__nv_bfloat16*>(dgh_lo),
-                                                dh_prev, d_b_ih, d_b_hh);
+  gru_backward_kernel<<<grid, 256, 0, stream>>>(rows, H, rpb, gi, gh, b_ih, b_hh, h_prev, dh, dgi, dgh, dh_prev, d_b_ih,
+                                                d_b_hh);
   VMM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -764,16 +761,14 @@ int colsum_acc(int rows, int width, const float* src, long long ld, float* out, 
   VMM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-int act_planes(int act, long long rows, int width, const float* src, long long ld, void* hi, void* lo,
+int act_planes(int act, long long rows, int width, const float* src, long long ld, const Planes& out,
                cudaStream_t stream) {
-  VMM_REQUIRE(width % 4 == 0 && ld % 4 == 0 && src && hi, "act_planes: bad argument");
+  VMM_REQUIRE(width % 4 == 0 && ld % 4 == 0 && src && out.n >= 1, "act_planes: bad argument");
   if (rows <= 0) return 0;
   long long blocks = (rows * (width / 4) + 255) / 256;
   const long long cap = static_cast<long long>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  act_planes_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, rows, width, src, ld,
-                                                                       static_cast<__nv_bfloat16*>(hi),
-                                                                       static_cast<__nv_bfloat16*>(lo));
+  act_planes_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, rows, width, src, ld, out);
   VMM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

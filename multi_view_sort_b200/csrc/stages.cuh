@@ -4,7 +4,7 @@
 // Every kernel reads the fp32 output of a contraction and writes the bf16 operand planes the
 // next contraction consumes.
 #pragma once
-#include "common.h"
+#include "internal.h"
 
 namespace vmm {
 
@@ -32,8 +32,7 @@ struct LnDesc {
   float eps;
 };
 
-int ln_forward(int mode, int act, const LnDesc& d, void* out_hi, void* out_lo, float* mean, float* rstd,
-               cudaStream_t stream);
+int ln_forward(int mode, int act, const LnDesc& d, const Planes& out, float* mean, float* rstd, cudaStream_t stream);
 
 // Backward through activation + LayerNorm (+ the enc1 prologue).  d_out is the gradient w.r.t.
 // the stage output [rows, width] (fp32).  Produces dv = dL/d(pre-normalisation value) as operand
@@ -41,8 +40,8 @@ int ln_forward(int mode, int act, const LnDesc& d, void* out_hi, void* out_lo, f
 // also dgamma[row] (nullable), dxw1 += gamma*dv summed over the K latent rows that share a feature
 // row, and dG1 = -gamma*dv as operand planes (nullable).
 int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out,
-                     long long ldd, void* dv_hi, void* dv_lo, float* c1, float* c2, float* dgamma, float* dxw1,
-                     void* dg1_hi, void* dg1_lo, cudaStream_t stream);
+                     long long ldd, const Planes& dv, float* c1, float* c2, float* dgamma, float* dxw1, const Planes& dg1,
+                     cudaStream_t stream);
 
 // Column reductions of the same stage, accumulated (+=) into fp32 parameter gradients:
 // d_ln_g += sum_rows dy*xhat, d_ln_b += sum_rows dy, d_bias += sum_rows dv, and for LN_ENC1
@@ -54,12 +53,12 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
 // GRUCell gate math (train_nem.py:177,232; torch.nn.GRUCell, gate order r,z,n).
 // gi = e Wih^T, gh = h Whh^T are the raw contraction outputs [rows, 3H] (biases added here).
 int gru_forward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
-                const float* h_prev, float* h_new, void* h_hi, void* h_lo, cudaStream_t stream);
+                const float* h_prev, float* h_new, const Planes& hp, cudaStream_t stream);
 // dh is the total gradient w.r.t. h_new.  Writes dgi/dgh operand planes [rows,3H], the direct
 // path dh_prev = dh * z (the Whh contraction adds the rest), and accumulates the bias gradients.
 int gru_backward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
-                 const float* h_prev, const float* dh, void* dgi_hi, void* dgi_lo, void* dgh_hi, void* dgh_lo,
-                 float* dh_prev, float* d_b_ih, float* d_b_hh, cudaStream_t stream);
+                 const float* h_prev, const float* dh, const Planes& dgi, const Planes& dgh, float* dh_prev,
+                 float* d_b_ih, float* d_b_hh, cudaStream_t stream);
 
 // Responsibilities from the fused E-step partial sums (train_nem.py:253-270):
 //   p = coef * sum_d exp(..) + 1e-10,  gamma = p / sum_k p.   Also folds the partial sums of
@@ -84,7 +83,7 @@ int gemv_rows(int n, int k, const float* W, const float* v, float* out, cudaStre
 int rank1_update(int n, int k, const float* u, const float* v, float* W, cudaStream_t stream);            // W[i,j] += u[i] v[j]
 int gemv_cols_acc(int n, int k, const float* W, const float* u, float* out, cudaStream_t stream);         // out[j] += sum_i u[i] W[i,j]
 int colsum_acc(int rows, int width, const float* src, long long ld, float* out, cudaStream_t stream);     // out[j] += sum_r src[r,j]
-int act_planes(int act, long long rows, int width, const float* src, long long ld, void* hi, void* lo,
+int act_planes(int act, long long rows, int width, const float* src, long long ld, const Planes& out,
                cudaStream_t stream);                                                                     // planes(act(src))
 int act_backward(int act, long long n, const float* pre, float* grad, cudaStream_t stream);              // grad *= act'(pre)
 

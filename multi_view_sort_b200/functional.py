@@ -18,8 +18,8 @@ from ._lib import check, lib, ptr, stream_ptr
 # ---- ctypes mirrors of include/vmm_b200.h ----------------------------------------------------
 class EMConfig(C.Structure):
     _fields_ = [("B", C.c_int), ("K", C.c_int), ("M", C.c_int), ("D", C.c_int), ("H", C.c_int), ("T", C.c_int),
-                ("planes", C.c_int), ("x_is_bf16", C.c_int), ("if_gamma_prior", C.c_int), ("stop_gamma_grad", C.c_int),
-                ("training", C.c_int), ("sigma", C.c_float), ("ln_eps", C.c_float)]
+                ("planes", C.c_int), ("planes_bwd", C.c_int), ("x_is_bf16", C.c_int), ("if_gamma_prior", C.c_int), ("stop_gamma_grad", C.c_int),
+                ("training", C.c_int), ("accum_chain", C.c_int), ("sigma", C.c_float), ("ln_eps", C.c_float)]
 
 
 EM_PARAM_FIELDS = [
@@ -60,11 +60,33 @@ def _bytes(fn, cfg) -> int:
     return int(n)
 
 
+# precision name -> (operand planes of the forward contractions, operand planes of the gradient
+# contractions, accumulation-chain bound in 64-wide K blocks).  Measured on B200 against the
+# reference at cfg1 (tests/test_em_gpu.py, tools/precision_sweep.py): the E-step amplifies forward
+# errors by 1/sigma^2 and dec1's ReLU turns them into gradient flips, so the forward pass needs
+# more bits than the backward pass.
+PRECISIONS = {
+    "fp32": (3, 2, 4),         # fp32-class: max grad error ~1.4e-5 (tolerance 1e-4)
+    "fp32_strict": (3, 3, 4),  # 6 passes everywhere: ~7e-6
+    "bf16": (2, 2, 8),         # "bf16 features" mode, tolerance 1e-2
+    "bf16_fast": (1, 1, 0),    # single-pass bf16, inference grade (h ~2e-2)
+}
+
+
+def precision_planes(precision):
+    if isinstance(precision, (tuple, list)):
+        p = tuple(int(v) for v in precision)
+        return p if len(p) == 3 else (p[0], p[1], 4 if p[0] == 3 else 0)
+    return PRECISIONS[precision]
+
+
 def make_config(module, B, T, x_is_bf16, training) -> EMConfig:
-    planes = {"fp32": 2, "bf16": 1}[module.precision]
+    planes, planes_bwd, chain = precision_planes(module.precision)
     return EMConfig(B=B, K=module.k, M=module.m, D=module.input_dim, H=module.rnn_hidden_size, T=T, planes=planes,
+                    planes_bwd=planes_bwd,
                     x_is_bf16=int(x_is_bf16), if_gamma_prior=int(module.if_gamma_prior),
-                    stop_gamma_grad=int(module.stop_gamma_grad), training=int(training), sigma=float(module.e_sigma),
+                    stop_gamma_grad=int(module.stop_gamma_grad), training=int(training),
+                    accum_chain=chain, sigma=float(module.e_sigma),
                     ln_eps=float(module.enc1[1].eps))
 
 
@@ -76,7 +98,7 @@ class _WeightCache:
         self.buf = None
 
     def get(self, cfg: EMConfig, params):
-        key = (cfg.planes, cfg.M, cfg.D, cfg.H) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (cfg.planes, cfg.planes_bwd, cfg.accum_chain, cfg.M, cfg.D, cfg.H) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self.key:
             nbytes = _bytes(lib().vmm_em_weights_bytes, cfg)
             if self.buf is None or self.buf.numel() < nbytes or self.buf.device != params[0].device:

@@ -12,16 +12,16 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-from ._lib import GemmSeg, check, lib, ptr, stream_ptr
+from ._lib import GemmSeg, check, lib, planes_c, ptr, stream_ptr
 
 
-def split_planes(t: torch.Tensor, planes: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """fp32 tensor -> (hi, lo) bf16 operand planes (lo is None when planes == 1)."""
-    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
-    hi = torch.empty_like(t, dtype=torch.bfloat16)
-    lo = torch.empty_like(t, dtype=torch.bfloat16) if planes == 2 else None
-    check(lib().vmm_split_planes(ptr(t), C.c_longlong(t.numel()), ptr(hi), ptr(lo), stream_ptr()))
-    return hi, lo
+def split_planes(t: torch.Tensor, planes: int):
+    """fp32 tensor -> tuple of `planes` bf16 operand planes (successive residuals)."""
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and 1 <= planes <= 3
+    out = tuple(torch.empty_like(t, dtype=torch.bfloat16) for _ in range(planes))
+    pc = planes_c(out)
+    check(lib().vmm_split_planes(ptr(t), C.c_longlong(t.numel()), C.byref(pc), stream_ptr()))
+    return out
 
 
 def _segs(pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]], a_mn: bool, b_mn: bool):
@@ -39,7 +39,7 @@ def _segs(pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]], a_mn: bool, b_mn: 
     return arr, M, N
 
 
-def gemm(pairs, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, splits=0, check_kernel=False):
+def gemm(pairs, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, splits=0, chain=0, check_kernel=False):
     """C[M,N] (+)= sum_i A_i B_i^T.  A_i is (M,K) when a_mn is False, (K,M) when True; same for B."""
     arr, M, N = _segs(pairs, a_mn, b_mn)
     if out is None:
@@ -51,16 +51,20 @@ def gemm(pairs, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, s
                                    ptr(bias), int(accumulate), stream_ptr()))
     else:
         check(lib().vmm_gemm_bf16(M, N, len(pairs), arr, int(a_mn), int(b_mn), ptr(out), C.c_longlong(out.stride(0)),
-                                  ptr(bias), int(accumulate), int(splits), stream_ptr()))
+                                  ptr(bias), int(accumulate), int(splits), int(chain), stream_ptr()))
     return out
 
 
 def plane_pairs(a_planes, b_planes):
-    """Error-compensated segment list for operands given as (hi, lo) planes."""
-    (ah, al), (bh, bl) = a_planes, b_planes
-    if al is None or bl is None:
-        return [(ah, bh)]
-    return [(al, bh), (ah, bl), (ah, bh)]
+    """Error-compensated segment list: cross terms A_i B_j with i + j < max(na, nb), least significant first."""
+    order = max(len(a_planes), len(b_planes))
+    out = []
+    for tot in range(order - 1, -1, -1):
+        for i in range(len(a_planes)):
+            j = tot - i
+            if 0 <= j < len(b_planes):
+                out.append((a_planes[i], b_planes[j]))
+    return out
 
 
 def estep_num_blocks(D: int) -> int:
@@ -69,35 +73,30 @@ def estep_num_blocks(D: int) -> int:
 
 def estep_forward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, want_sq=True, want_pp=False):
     """Fused dec3 + E-step.  z planes (rows, zk), W3 planes (D, zk), x (B*M, D) float or bf16.
-    Returns per-row sums (e, sq, pp) each (rows,) - partial sums over n-blocks are reduced here
-    only for the convenience of tests; the library's gamma kernel consumes the partials."""
-    zh, zl = z_planes
-    wh, wl = w3_planes
-    rows, zk = zh.shape
-    D = wh.shape[0]
+    Returns the per-(row, half-tile) partial sums (e, sq, pp); sum over dim 1 for the row totals."""
+    rows, zk = z_planes[0].shape
+    D = w3_planes[0].shape[0]
     nb = estep_num_blocks(D)
-    dev = zh.device
+    dev = z_planes[0].device
     pe = torch.empty(rows, nb, device=dev)
     psq = torch.empty(rows, nb, device=dev) if want_sq else None
     ppp = torch.empty(rows, nb, device=dev) if want_pp else None
-    planes = 1 if zl is None else 2
     assert x.dtype in (torch.float32, torch.bfloat16) and x.stride(-1) == 1
-    check(lib().vmm_estep_forward(rows, D, zk, planes, ptr(zh), ptr(zl), ptr(wh), ptr(wl), ptr(b3), ptr(x),
-                                  int(x.dtype == torch.bfloat16), C.c_longlong(x.stride(-2)), int(k_latent),
-                                  int(m_views), C.c_float(sigma), ptr(pe), ptr(psq), ptr(ppp), stream_ptr()))
+    zc, wc = planes_c(z_planes), planes_c(w3_planes)
+    check(lib().vmm_estep_forward(rows, D, zk, C.byref(zc), C.byref(wc), ptr(b3), ptr(x), int(x.dtype == torch.bfloat16),
+                                  C.c_longlong(x.stride(-2)), int(k_latent), int(m_views), C.c_float(sigma), ptr(pe),
+                                  ptr(psq), ptr(ppp), stream_ptr()))
     return pe, psq, ppp
 
 
-def estep_backward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, alpha, beta, kappa=None, d_b3=None):
-    zh, zl = z_planes
-    wh, wl = w3_planes
-    rows, zk = zh.shape
-    D = wh.shape[0]
-    planes = 1 if zl is None else 2
-    dh = torch.empty(rows, D, device=zh.device, dtype=torch.bfloat16)
-    dl = torch.empty(rows, D, device=zh.device, dtype=torch.bfloat16) if planes == 2 else None
-    check(lib().vmm_estep_backward(rows, D, zk, planes, ptr(zh), ptr(zl), ptr(wh), ptr(wl), ptr(b3), ptr(x),
-                                   int(x.dtype == torch.bfloat16), C.c_longlong(x.stride(-2)), int(k_latent),
-                                   int(m_views), C.c_float(sigma), ptr(alpha), ptr(beta), ptr(kappa), ptr(dh), ptr(dl),
-                                   ptr(d_b3), stream_ptr()))
-    return dh, dl
+def estep_backward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, alpha, beta, kappa=None, d_b3=None,
+                   out_planes=None):
+    rows, zk = z_planes[0].shape
+    D = w3_planes[0].shape[0]
+    n_out = len(z_planes) if out_planes is None else out_planes
+    outs = tuple(torch.empty(rows, D, device=z_planes[0].device, dtype=torch.bfloat16) for _ in range(n_out))
+    zc, wc, oc = planes_c(z_planes), planes_c(w3_planes), planes_c(outs)
+    check(lib().vmm_estep_backward(rows, D, zk, C.byref(zc), C.byref(wc), ptr(b3), ptr(x), int(x.dtype == torch.bfloat16),
+                                   C.c_longlong(x.stride(-2)), int(k_latent), int(m_views), C.c_float(sigma), ptr(alpha),
+                                   ptr(beta), ptr(kappa), C.byref(oc), ptr(d_b3), stream_ptr()))
+    return outs
