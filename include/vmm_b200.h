@@ -192,6 +192,48 @@ VMM_API int vmm_em_backward(const vmm_em_config* cfg, const vmm_em_params* param
  * "g2", "e_hi", "gi", "gh", "h", "h_hi", "g4", "u_hi", "g5", "z_hi", "z_lo", "gamma", "row_sq". */
 VMM_API const void* vmm_em_workspace_ptr(const vmm_em_config* cfg, const void* workspace, const char* name, int iter);
 
+/* ---------------------------------------------------------------------------------------
+ * Head: latent-view scoring, sort + concat (or max-pool) over K, 3-layer classifier
+ * (replaces Multi_View_Net.forward, train_nem.py:328-380, eval-mode semantics) and its
+ * backward.  h is the last hidden state [B*K, H]; gamma [B,K,M] is read only for if_sort == 2.
+ * ------------------------------------------------------------------------------------- */
+typedef struct vmm_head_config {
+  int B, K, H, C, W, M; /* objects, latent views, hidden, classes, classifier width (4096), views */
+  int planes, planes_bwd, accum_chain;
+  int if_sort;          /* 0 unsorted concat, 1 sort by score, 2 sort by responsibility spread    */
+  int if_pooling;       /* 1: max over the K latent views instead of concat                       */
+} vmm_head_config;
+
+/* att.0.{weight,bias}, net.0.*, net.3.*, net.6.* of the reference's state_dict (train_nem.py:310,326). */
+typedef struct vmm_head_params {
+  const float *att_w, *att_b; /* [H] [1]                 */
+  const float *w0, *b0;       /* [W, K*H or H] [W]       */
+  const float *w3, *b3;       /* [W, W] [W]              */
+  const float *w6, *b6;       /* [C, W] [C]              */
+} vmm_head_params;
+typedef struct vmm_head_grads {
+  float *att_w, *att_b, *w0, *b0, *w3, *b3, *w6, *b6; /* accumulated (+=) */
+} vmm_head_grads;
+
+VMM_API long long vmm_head_weights_bytes(const vmm_head_config* cfg);
+VMM_API long long vmm_head_workspace_bytes(const vmm_head_config* cfg);
+VMM_API long long vmm_head_scratch_bytes(const vmm_head_config* cfg);
+VMM_API int vmm_head_prepare(const vmm_head_config* cfg, const vmm_head_params* params, void* weights, void* stream);
+/* logits [B,C] and/or descriptor [B,W] (the output of the 2nd Linear, pre-ReLU: what save_feature=1
+ * returns, train_nem.py:357-361); either may be NULL. */
+VMM_API int vmm_head_forward(const vmm_head_config* cfg, const vmm_head_params* params, const void* weights,
+                             const float* h, const float* gamma, void* workspace, float* logits, float* descriptor,
+                             void* stream);
+VMM_API int vmm_head_backward(const vmm_head_config* cfg, const vmm_head_params* params, const void* weights,
+                              const float* h, const void* workspace, void* scratch, const float* d_logits,
+                              const float* d_descriptor, const vmm_head_grads* grads, float* d_h, void* stream);
+
+/* Softmax cross-entropy of the logits (replaces nn.CrossEntropyLoss at tools/Trainer.py:202):
+ * loss_sum[0] += scale * sum_b CE_b, d_logits = scale * (softmax - onehot) (nullable),
+ * pred[b] = argmax (nullable).  scale = 1/B for the batch mean (1/B_global when sharded). */
+VMM_API int vmm_cross_entropy(int B, int C, const float* logits, const long long* labels, float scale, float* loss_sum,
+                              float* d_logits, int* pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

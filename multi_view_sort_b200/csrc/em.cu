@@ -20,25 +20,6 @@ namespace {
 constexpr int E1 = 1024;   // enc1 width, dec3 input width (train_nem.py:171,185)
 constexpr int E2 = 4096;   // enc2 / dec1 width (train_nem.py:175,181)
 
-struct Bump {
-  char* base;
-  long long off = 0;
-  explicit Bump(void* b) : base(static_cast<char*>(b)) {}
-  template <typename T>
-  T* take(long long count) {
-    off = (off + 255) & ~255ll;
-    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-    off += count * static_cast<long long>(sizeof(T));
-    return p;
-  }
-  Planes planes(long long count, int n) {
-    Planes p;
-    p.n = n;
-    for (int i = 0; i < n; ++i) p.p[i] = take<__nv_bfloat16>(count);
-    return p;
-  }
-};
-
 struct Dims {
   int B, K, M, D, H, T, planes, pb;   // pb: operand planes of the gradient contractions
   int chain;                          // accumulation chain length in k-blocks (0 = unlimited)

@@ -23,6 +23,26 @@ inline Planes planes_from_c(const vmm_planes* c) {
   }
   return r;
 }
+// Bump allocator over a caller-owned buffer (base == nullptr: size query only); 256-byte aligned.
+struct Bump {
+  char* base;
+  long long off = 0;
+  explicit Bump(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(long long count) {
+    off = (off + 255) & ~255ll;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * static_cast<long long>(sizeof(T));
+    return p;
+  }
+  Planes planes(long long count, int n) {
+    Planes p;
+    p.n = n;
+    for (int i = 0; i < n; ++i) p.p[i] = take<__nv_bfloat16>(count);
+    return p;
+  }
+};
+
 // Cross terms A_i B_j with i + j < max(na, nb), least significant first.  Returns the count.
 int make_segs(vmm_gemm_seg* s, const Planes& a, long long lda, const Planes& b, long long ldb, long long k);
 

@@ -187,5 +187,127 @@ def em_step(module, x, state):
     raise NotImplementedError("step-level NEM.forward: use NEM.run_em (fused path)")
 
 
+# ---- head ---------------------------------------------------------------------------------------
+class HeadConfig(C.Structure):
+    _fields_ = [("B", C.c_int), ("K", C.c_int), ("H", C.c_int), ("C", C.c_int), ("W", C.c_int), ("M", C.c_int),
+                ("planes", C.c_int), ("planes_bwd", C.c_int), ("accum_chain", C.c_int), ("if_sort", C.c_int),
+                ("if_pooling", C.c_int)]
+
+
+HEAD_PARAM_FIELDS = [("att_w", "att.0.weight"), ("att_b", "att.0.bias"), ("w0", "net.0.weight"), ("b0", "net.0.bias"),
+                     ("w3", "net.3.weight"), ("b3", "net.3.bias"), ("w6", "net.6.weight"), ("b6", "net.6.bias")]
+
+
+class HeadPointers(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f, _ in HEAD_PARAM_FIELDS]
+
+
+def _head_pointers(tensors) -> HeadPointers:
+    s = HeadPointers()
+    for (f, _), t in zip(HEAD_PARAM_FIELDS, tensors):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), f
+        setattr(s, f, t.data_ptr())
+    return s
+
+
+def head_param_tensors(module):
+    named = dict(module.named_parameters())
+    return [named[k] for _, k in HEAD_PARAM_FIELDS]
+
+
+def make_head_config(module, B, M) -> HeadConfig:
+    planes, planes_bwd, chain = precision_planes(module.precision)
+    return HeadConfig(B=B, K=module.k, H=module.rnn_hidden_size, C=module.nclasses, W=module.net[3].in_features, M=M,
+                      planes=planes, planes_bwd=planes_bwd, accum_chain=chain, if_sort=int(module.if_sort),
+                      if_pooling=int(module.if_pooling))
+
+
+class _HeadWeightCache:
+    def __init__(self):
+        self.key, self.buf = None, None
+
+    def get(self, cfg, params):
+        key = (cfg.planes, cfg.K, cfg.H, cfg.C, cfg.W, cfg.if_pooling) + tuple((p.data_ptr(), p._version) for p in params)
+        if key != self.key:
+            nbytes = _bytes(lib().vmm_head_weights_bytes, cfg)
+            if self.buf is None or self.buf.numel() < nbytes or self.buf.device != params[0].device:
+                self.buf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
+            pp = _head_pointers(params)
+            check(lib().vmm_head_prepare(C.byref(cfg), C.byref(pp), ptr(self.buf), stream_ptr()))
+            self.key = key
+        return self.buf
+
+
+class _HeadFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, want_descriptor, h, gamma, *params):
+        B = h.shape[0] // module.k
+        dev = h.device
+        M = gamma.shape[2] if gamma is not None else 1
+        cfg = make_head_config(module, B, M)
+        with torch.cuda.device(dev):
+            wc = module.__dict__.setdefault("_vmm_weight_cache", _HeadWeightCache())
+            weights = wc.get(cfg, params)
+            ws = torch.empty(_bytes(lib().vmm_head_workspace_bytes, cfg), dtype=torch.uint8, device=dev)
+            out = torch.empty(B, cfg.W if want_descriptor else cfg.C, device=dev)
+            pp = _head_pointers(params)
+            check(lib().vmm_head_forward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(h), ptr(gamma), ptr(ws),
+                                         None if want_descriptor else ptr(out), ptr(out) if want_descriptor else None,
+                                         stream_ptr()))
+        ctx.cfg, ctx.want_descriptor = cfg, want_descriptor
+        ctx.save_for_backward(h, ws, weights, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        h, ws, weights = ctx.saved_tensors[:3]
+        params = ctx.saved_tensors[3:]
+        cfg, dev = ctx.cfg, h.device
+        with torch.cuda.device(dev):
+            scratch = torch.empty(_bytes(lib().vmm_head_scratch_bytes, cfg), dtype=torch.uint8, device=dev)
+            grads = [torch.zeros_like(p) for p in params]
+            gp, pp = _head_pointers(grads), _head_pointers(params)
+            d_h = torch.empty_like(h)
+            d_out = d_out.contiguous().float()
+            check(lib().vmm_head_backward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(h), ptr(ws), ptr(scratch),
+                                          None if ctx.want_descriptor else ptr(d_out),
+                                          ptr(d_out) if ctx.want_descriptor else None, C.byref(gp), ptr(d_h), stream_ptr()))
+        return (None, None, d_h, None, *grads)
+
+
 def head_forward(module, h, gamma):
-    raise NotImplementedError("head kernels are built in head.cu")
+    """Multi_View_Net.forward: logits (B, nclasses), or the 4096-d descriptor when save_fea == 1."""
+    if not h.is_cuda:
+        raise RuntimeError("multi_view_sort_b200 has no CPU path: h must be a CUDA tensor")
+    h = h.contiguous().float()
+    g = None
+    if gamma is not None:
+        B = h.shape[0] // module.k
+        g = gamma.detach().to(h.device, torch.float32).reshape(B, module.k, -1).contiguous()
+    return _HeadFunction.apply(module, bool(module.save_fea), h, g, *head_param_tensors(module))
+
+
+class _CrossEntropyFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, scale):
+        B, Cn = logits.shape
+        with torch.cuda.device(logits.device):
+            loss = torch.zeros(1, device=logits.device)
+            d_logits = torch.empty_like(logits)
+            check(lib().vmm_cross_entropy(B, Cn, ptr(logits), ptr(labels), C.c_float(scale), ptr(loss), ptr(d_logits), None,
+                                          stream_ptr()))
+        ctx.save_for_backward(d_logits)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_logits,) = ctx.saved_tensors
+        return d_logits * g, None, None
+
+
+def cross_entropy(logits, labels, scale=None):
+    """Mean softmax cross-entropy (nn.CrossEntropyLoss semantics); `scale` overrides 1/B, e.g. 1/B_global
+    when the batch is sharded over ranks."""
+    logits = logits.contiguous().float()
+    labels = labels.to(logits.device, torch.int64).contiguous()
+    return _CrossEntropyFunction.apply(logits, labels, float(1.0 / logits.shape[0] if scale is None else scale))
