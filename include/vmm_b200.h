@@ -53,6 +53,13 @@ typedef struct vmm_planes {
 
 VMM_API int vmm_version(void);
 VMM_API const char* vmm_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+VMM_API long long vmm_launch_count(void);
+/* Measurement aid: while enabled, every tensor-core contraction launch is bracketed by CUDA
+ * events on its stream; _read() waits for them, returns the summed device time, the executed
+ * tensor-core FLOPs (all split passes) and the launch count since the last call, and resets. */
+VMM_API int vmm_gemm_profile(int enable);
+VMM_API int vmm_gemm_profile_read(double* total_ms, double* executed_flops, long long* launches);
 
 /* ---------------------------------------------------------------------------------------
  * Tensor-core contraction (replaces every nn.Linear / GRUCell matmul on the path:

@@ -39,6 +39,15 @@ int device_sm_count();
     if (_r != 0) return _r;      \
   } while (0)
 
+// Every kernel launch site ends with VMM_LAUNCHED(): counts the launch (vmm_launch_count) and
+// surfaces launch-configuration errors.
+void count_launch();
+#define VMM_LAUNCHED()                     \
+  do {                                     \
+    ::vmm::count_launch();                 \
+    VMM_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
+
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 }  // namespace vmm

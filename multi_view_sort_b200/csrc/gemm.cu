@@ -1,6 +1,8 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map construction, tile/split planning, launch,
 // and the extern "C" entry points vmm_gemm_bf16 / vmm_estep_forward / vmm_estep_backward.
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.h"
 #include "gemm.cuh"
@@ -27,6 +29,22 @@ int device_sm_count() {
   }
   return cached[dev];
 }
+
+// ---- launch counter and per-launch GEMM timing (bench.py's roofline) ------------------------
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// When enabled, every tcgen05 GEMM launch is bracketed by two CUDA events on its own stream;
+// vmm_gemm_profile_read() sums the elapsed times.  Events are recorded, never synchronised on,
+// inside the timed region.
+struct GemmProfile {
+  std::mutex mu;
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;     // pairs
+  std::vector<double> flops;       // executed tensor-core FLOPs of each launch
+  size_t used = 0;
+};
+static GemmProfile g_prof;
 
 // ---- TMA descriptors ----------------------------------------------------------------------
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -88,8 +106,29 @@ static int launch_one(const GemmParams& p, cudaStream_t stream) {
   }
   const int total_work = p.num_m_blk * p.num_n_blk * p.splits;
   const int grid = total_work < device_sm_count() ? total_work : device_sm_count();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.enabled) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (g_prof.used + 2 > g_prof.ev.size()) {
+      for (int i = 0; i < 256; ++i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) break;
+        g_prof.ev.push_back(e);
+      }
+    }
+    if (g_prof.used + 2 <= g_prof.ev.size()) {
+      e0 = g_prof.ev[g_prof.used];
+      e1 = g_prof.ev[g_prof.used + 1];
+      g_prof.used += 2;
+      double k = 0;
+      for (int s = 0; s < p.nseg; ++s) k += static_cast<double>(p.seg_kb[s]) * BK;
+      g_prof.flops.push_back(2.0 * p.M * p.N * k);
+    }
+  }
+  if (e0) cudaEventRecord(e0, stream);
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  if (e1) cudaEventRecord(e1, stream);
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -286,7 +325,7 @@ int split_planes(const float* src, long long n, const Planes& out, cudaStream_t 
   if (blocks > cap) blocks = cap;
   split_planes_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, n, out.p[0], out.n > 1 ? out.p[1] : nullptr,
                                                                     out.n > 2 ? out.p[2] : nullptr);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -296,6 +335,36 @@ int split_planes(const float* src, long long n, const Planes& out, cudaStream_t 
 extern "C" {
 
 int vmm_version(void) { return VMM_ABI_VERSION; }
+long long vmm_launch_count(void) { return vmm::g_launches.load(); }
+
+int vmm_gemm_profile(int enable) {
+  std::lock_guard<std::mutex> lk(vmm::g_prof.mu);
+  vmm::g_prof.enabled = enable != 0;
+  vmm::g_prof.used = 0;
+  vmm::g_prof.flops.clear();
+  return 0;
+}
+int vmm_gemm_profile_read(double* total_ms, double* executed_flops, long long* launches) {
+  std::lock_guard<std::mutex> lk(vmm::g_prof.mu);
+  double ms = 0, fl = 0;
+  const size_t n = vmm::g_prof.used / 2;
+  for (size_t i = 0; i < n; ++i) {
+    float t = 0.f;
+    if (cudaEventSynchronize(vmm::g_prof.ev[2 * i + 1]) != cudaSuccess ||
+        cudaEventElapsedTime(&t, vmm::g_prof.ev[2 * i], vmm::g_prof.ev[2 * i + 1]) != cudaSuccess) {
+      vmm::set_error("vmm_gemm_profile_read: event query failed");
+      return VMM_E_CUDA;
+    }
+    ms += t;
+    fl += vmm::g_prof.flops[i];
+  }
+  if (total_ms) *total_ms = ms;
+  if (executed_flops) *executed_flops = fl;
+  if (launches) *launches = static_cast<long long>(n);
+  vmm::g_prof.used = 0;
+  vmm::g_prof.flops.clear();
+  return 0;
+}
 const char* vmm_last_error(void) { return vmm::g_err; }
 
 int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major, float* C,
@@ -315,7 +384,7 @@ int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_ma
   vmm::gemm_check_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(M, N, nseg, s[0], s[1], s[2], s[3],
                                                                                a_mn_major, b_mn_major, C, ldc, bias,
                                                                                accumulate);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 

@@ -331,7 +331,7 @@ int head_forward(const vmm_head_config* c, const vmm_head_params* p, const void*
   HWorkspace ws(*c, workspace);
   head_score_kernel<<<d.B, 256, 0, st>>>(d.K, d.H, d.M, c->if_sort, c->if_pooling, h, gamma, p->att_w, p->att_b, ws.score,
                                          ws.order, ws.argmax, ws.feat);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   VMM_TRY(lin_fwd(ws.feat, w.w0, d.B, d.W, d.FW, ws.t0, p->b0, d.chain, st));
   VMM_TRY(act_planes(ACT_RELU, d.B, d.W, ws.t0, d.W, ws.t1, st));
   VMM_TRY(lin_fwd(ws.t1, w.w3, d.B, d.W, d.W, ws.t3, p->b3, d.chain, st));
@@ -355,14 +355,14 @@ int head_backward(const vmm_head_config* c, const vmm_head_params* p, const void
   const long long BW = 1ll * d.B * d.W;
   if (d_logits) {
     pad_planes_kernel<<<blocks_for(1ll * d.B * d.Cp), 256, 0, st>>>(d.B, d.C, d.Cp, d_logits, sc.dl);
-    VMM_CHECK_CUDA(cudaGetLastError());
+    VMM_LAUNCHED();
     VMM_TRY(colsum_acc(d.B, d.C, d_logits, d.C, g->b6, st));
     VMM_TRY(lin_wgrad(sc.dl, d.Cp, ws.t3r, d.B, d.C, d.W, g->w6, d.chain, st));
     VMM_TRY(lin_dgrad(sc.dl, d.Cp, w.w6, d.B, d.C, d.W, sc.dt3f, d.chain, st));
     VMM_TRY(act_backward(ACT_RELU, BW, ws.t3, sc.dt3f, st));
     if (d_descriptor) {
       add_kernel<<<blocks_for(BW), 256, 0, st>>>(BW, d_descriptor, sc.dt3f);
-      VMM_CHECK_CUDA(cudaGetLastError());
+      VMM_LAUNCHED();
     }
   } else {
     VMM_CHECK_CUDA(cudaMemcpyAsync(sc.dt3f, d_descriptor, sizeof(float) * BW, cudaMemcpyDeviceToDevice, st));
@@ -378,10 +378,10 @@ int head_backward(const vmm_head_config* c, const vmm_head_params* p, const void
   VMM_TRY(lin_dgrad(sc.dt0, d.W, w.w0, d.B, d.W, d.FW, sc.dfeat, d.chain, st));
   head_score_backward_kernel<<<d.B, 256, 0, st>>>(d.K, d.H, c->if_pooling, h, p->att_w, ws.score, ws.order, ws.argmax,
                                                   sc.dfeat, d_h, sc.ds_pre);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   VMM_TRY(gemv_cols_acc(static_cast<int>(d.R), d.H, h, sc.ds_pre, g->att_w, st));
   sum_acc_kernel<<<1, 256, 0, st>>>(d.R, sc.ds_pre, g->att_b);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -389,7 +389,7 @@ int cross_entropy(int B, int C, const float* logits, const long long* labels, fl
                   float* d_logits, int* pred, cudaStream_t st) {
   VMM_REQUIRE(B > 0 && C > 0 && logits && labels && loss_sum, "cross_entropy: bad argument");
   cross_entropy_kernel<<<(B + 3) / 4, 128, 0, st>>>(B, C, logits, labels, scale, loss_sum, d_logits, pred);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 

@@ -629,7 +629,7 @@ int ln_forward(int mode, int act, const LnDesc& d, const Planes& out, float* mea
     if (cached) ln_forward_kernel<LN_ENC1, true><<<d.rows, LN_THREADS, 0, stream>>>(d, act, out, mean, rstd);
     else ln_forward_kernel<LN_ENC1, false><<<d.rows, LN_THREADS, 0, stream>>>(d, act, out, mean, rstd);
   }
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -647,7 +647,7 @@ int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, cons
     ln_backward_rows_kernel<LN_ENC1><<<groups, LN_THREADS, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2, dgamma,
                                                                           dxw1, dg1);
   }
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -665,7 +665,7 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
   else
     ln_backward_cols_kernel<LN_ENC1><<<grid, 256, 0, stream>>>(d, act, mean, rstd, c1, c2, d_out, ldd, rpb, d_ln_g, d_ln_b,
                                                                 d_bias, d_w1b3);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -675,7 +675,7 @@ int gru_forward(int rows, int H, const float* gi, const float* gh, const float* 
   const long long n = static_cast<long long>(rows) * H;
   gru_forward_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, h_new,
                                                                                  hp);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -689,7 +689,7 @@ int gru_backward(int rows, int H, const float* gi, const float* gh, const float*
   dim3 grid(col_blocks, ceil_div(rows, rpb));
   gru_backward_kernel<<<grid, 256, 0, stream>>>(rows, H, rpb, gi, gh, b_ih, b_hh, h_prev, dh, dgi, dgh, dh_prev, d_b_ih,
                                                 d_b_hh);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -700,7 +700,7 @@ int gamma_forward(int B, int K, int Mv, int nblk, float sigma, const float* part
   VMM_REQUIRE(B > 0 && K > 0 && Mv > 0 && nblk > 0 && part_e && gamma && inv_s, "gamma_forward: bad argument");
   gamma_forward_kernel<<<ceil_div(B * Mv, 128), 128, 0, stream>>>(B, K, Mv, nblk, gauss_coef(sigma), part_e, part_sq, part_pp,
                                                                   gamma, inv_s, row_sq, row_pp);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -709,7 +709,7 @@ int gamma_backward(int B, int K, int Mv, float sigma, const float* gamma, const 
   VMM_REQUIRE(B > 0 && K > 0 && Mv > 0 && gamma && inv_s && dgamma && alpha, "gamma_backward: bad argument");
   gamma_backward_kernel<<<ceil_div(B * Mv, 128), 128, 0, stream>>>(B, K, Mv, gauss_coef(sigma) / (sigma * sigma), gamma, inv_s,
                                                                    dgamma, alpha);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -718,7 +718,7 @@ int loss_forward(int B, int K, int Mv, int D, int if_gamma_prior, const float* g
   VMM_REQUIRE(if_gamma_prior >= 0 && if_gamma_prior <= 2, "if_gamma_prior must be 0, 1 or 2");
   VMM_REQUIRE(gamma && row_sq && out3 && (if_gamma_prior == 0 ? row_pp != nullptr : prior != nullptr), "loss_forward: null argument");
   loss_forward_kernel<<<1, 1024, 0, stream>>>(B, K, Mv, D, if_gamma_prior, gamma, prior, row_sq, row_pp, out3);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
@@ -730,19 +730,19 @@ int loss_backward(int B, int K, int Mv, int D, int if_gamma_prior, int stop_gamm
               "loss_backward: null argument");
   loss_backward_kernel<<<ceil_div(B * K, 128), 128, 0, stream>>>(B, K, Mv, D, if_gamma_prior, stop_gamma_grad, gamma,
                                                                  prior ? prior : gamma, row_sq, row_pp, g3, dgamma, beta, kappa);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
 int gemv_rows(int n, int k, const float* W, const float* v, float* out, cudaStream_t stream) {
   gemv_rows_kernel<<<n, 256, 0, stream>>>(n, k, W, v, out);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 int rank1_update(int n, int k, const float* u, const float* v, float* W, cudaStream_t stream) {
   const long long t = static_cast<long long>(n) * k;
   rank1_update_kernel<<<static_cast<unsigned>((t + 255) / 256), 256, 0, stream>>>(n, k, u, v, W);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 int gemv_cols_acc(int n, int k, const float* W, const float* u, float* out, cudaStream_t stream) {
@@ -750,7 +750,7 @@ int gemv_cols_acc(int n, int k, const float* W, const float* u, float* out, cuda
   const int rpb = pick_rows_per_block(n, col_blocks);
   dim3 grid(col_blocks, ceil_div(n, rpb));
   gemv_cols_acc_kernel<<<grid, 256, 0, stream>>>(n, k, rpb, W, u, out);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 int colsum_acc(int rows, int width, const float* src, long long ld, float* out, cudaStream_t stream) {
@@ -758,7 +758,7 @@ int colsum_acc(int rows, int width, const float* src, long long ld, float* out, 
   const int rpb = pick_rows_per_block(rows, col_blocks);
   dim3 grid(col_blocks, ceil_div(rows, rpb));
   colsum_acc_kernel<<<grid, 256, 0, stream>>>(rows, width, rpb, src, ld, out);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 int act_planes(int act, long long rows, int width, const float* src, long long ld, const Planes& out,
@@ -769,7 +769,7 @@ int act_planes(int act, long long rows, int width, const float* src, long long l
   const long long cap = static_cast<long long>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   act_planes_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, rows, width, src, ld, out);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 int act_backward(int act, long long n, const float* pre, float* grad, cudaStream_t stream) {
@@ -778,7 +778,7 @@ int act_backward(int act, long long n, const float* pre, float* grad, cudaStream
   const long long cap = static_cast<long long>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   act_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, n, pre, grad);
-  VMM_CHECK_CUDA(cudaGetLastError());
+  VMM_LAUNCHED();
   return 0;
 }
 
