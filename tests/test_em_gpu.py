@@ -238,3 +238,35 @@ def test_head_options_match_oracle():
         named = dict(head.named_parameters())
         for n, p in ph.items():
             assert rel_err(named[n].grad, p.grad) < 1e-4, (if_sort, if_pool, n)
+
+
+def test_cfg3_80_views_matches_reference_golden():
+    """Reduced BASELINE configs[2]: 80 views x 4096-d, K = 5 (NEM(view_num=80): 700 M parameters, LayerNorm over
+    81,920 columns, enc2 K-dim 81,920) - full training step against the frozen reference outputs."""
+    from helpers import grad_summary
+    from multi_view_sort_b200.functional import cross_entropy
+    z, cfg = load_golden("cfg3_b2_k5_m80_t3")
+    nem, head = seeded_models(cfg)
+    x, y = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    nem, head = nem.cuda(), head.cuda()
+    h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda(), cfg["T"])
+    logits = head(h, gamma)
+    loss = cross_entropy(logits, y.cuda()) + nem_loss
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel_err(h, z["h"]) < 1e-4
+    assert rel_err(gamma.reshape(z["gamma"].shape), z["gamma"]) < 1e-4
+    assert rel_err(logits, z["logits"]) < 1e-4
+    assert (logits.argmax(1).cpu().numpy() == z["logits"].argmax(1)).all()
+    assert abs(loss.item() - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
+    worst = {}
+    for prefix, mod in (("nem.", nem), ("head.", head)):
+        for n, p in mod.named_parameters():
+            g = z["grad/" + prefix + n]
+            if g.size == 1:
+                assert p.grad is None, n
+                continue
+            mine = grad_summary(p.grad)
+            worst[prefix + n] = max(abs(mine[1] - g[1]) / g[1], float(abs(mine[3:] - g[3:]).max() / g[1]))
+    bad = {k: v for k, v in worst.items() if not v < (5e-4 if k.endswith("att.0.bias") else 1e-4)}
+    assert not bad, bad
