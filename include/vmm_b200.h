@@ -49,7 +49,22 @@ extern "C" {
 typedef struct vmm_planes {
   void* p[VMM_MAX_PLANES];
   int n;
+  int fmt; /* VMM_FMT_BF16 or VMM_FMT_F16PAIR */
 } vmm_planes;
+
+/* VMM_FMT_BF16: p[i] are successive bf16 residuals (above).
+ * VMM_FMT_F16PAIR: p[0] = fp16(v), p[1] = fp16((v - p[0]) * 2^11): 22 mantissa bits in two planes.
+ * A contraction accumulates the scaled cross terms first and folds them into the main product
+ * with tcgen05.mma's scale_input_d = 11 (D = A*B + D * 2^-11): 3 passes for fp32-class operands
+ * instead of 6.  Range is fp16's (|v| < 65504, saturating): used for forward operands
+ * (features, activations, weights); gradients stay bf16. */
+#define VMM_FMT_BF16 0
+#define VMM_FMT_F16PAIR 1
+
+/* vmm_gemm_seg.flags */
+#define VMM_SEG_A_F16 1       /* A of this segment is fp16 (else bf16) */
+#define VMM_SEG_B_F16 2       /* B of this segment is fp16 (else bf16) */
+#define VMM_SEG_RESCALE11 4   /* scale what the chain has accumulated so far by 2^-11 before this segment */
 
 VMM_API int vmm_version(void);
 VMM_API const char* vmm_last_error(void);
@@ -84,6 +99,7 @@ typedef struct vmm_gemm_seg {
   const void* b; /* bf16 */
   long long ldb;
   long long k;
+  unsigned flags; /* VMM_SEG_* */
 } vmm_gemm_seg;
 
 VMM_API int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
@@ -135,8 +151,9 @@ VMM_API int vmm_estep_backward(int rows, int D, int zk, const vmm_planes* z, con
  * ------------------------------------------------------------------------------------- */
 typedef struct vmm_em_config {
   int B, K, M, D, H, T;
-  int planes;          /* operand planes of the forward contractions (1, 2 or 3)               */
-  int planes_bwd;      /* operand planes of the gradient contractions (1 .. planes)            */
+  int planes;          /* operand planes of the forward contractions (1..3; 1..2 with fwd_fp16)   */
+  int planes_bwd;      /* bf16 operand planes of the gradient contractions (1..3)               */
+  int fwd_fp16;        /* forward operands are VMM_FMT_F16PAIR instead of bf16 residual planes  */
   int x_is_bf16;       /* features are bf16 ("bf16 features" mode) instead of float             */
   int if_gamma_prior;  /* 0,1,2 as in tools/NEM_utilities.py:98-106                             */
   int stop_gamma_grad; /* detach gamma inside the intra loss (NEM_utilities.py:118-123)         */
@@ -206,7 +223,7 @@ VMM_API const void* vmm_em_workspace_ptr(const vmm_em_config* cfg, const void* w
  * ------------------------------------------------------------------------------------- */
 typedef struct vmm_head_config {
   int B, K, H, C, W, M; /* objects, latent views, hidden, classes, classifier width (4096), views */
-  int planes, planes_bwd, accum_chain;
+  int planes, planes_bwd, fwd_fp16, accum_chain;
   int if_sort;          /* 0 unsorted concat, 1 sort by score, 2 sort by responsibility spread    */
   int if_pooling;       /* 1: max over the K latent views instead of concat                       */
 } vmm_head_config;

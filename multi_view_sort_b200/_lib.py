@@ -18,19 +18,22 @@ class VMMError(RuntimeError):
 
 
 class GemmSeg(C.Structure):
-    _fields_ = [("a", C.c_void_p), ("lda", C.c_longlong), ("b", C.c_void_p), ("ldb", C.c_longlong), ("k", C.c_longlong)]
+    _fields_ = [("a", C.c_void_p), ("lda", C.c_longlong), ("b", C.c_void_p), ("ldb", C.c_longlong), ("k", C.c_longlong),
+                ("flags", C.c_uint)]
 
 
 class PlanesC(C.Structure):
     """vmm_planes: up to 3 bf16 residual planes of one matrix."""
-    _fields_ = [("p", C.c_void_p * 3), ("n", C.c_int)]
+    _fields_ = [("p", C.c_void_p * 3), ("n", C.c_int), ("fmt", C.c_int)]
 
 
 def planes_c(planes):
     """Sequence of bf16 tensors (most significant first) -> vmm_planes."""
     planes = [t for t in planes if t is not None]
+    import torch
     s = PlanesC()
     s.n = len(planes)
+    s.fmt = 1 if planes and planes[0].dtype == torch.float16 else 0
     for i, t in enumerate(planes):
         s.p[i] = t.data_ptr()
     return s

@@ -23,29 +23,30 @@ constexpr int E2 = 4096;   // enc2 / dec1 width (train_nem.py:175,181)
 struct Dims {
   int B, K, M, D, H, T, planes, pb;   // pb: operand planes of the gradient contractions
   int chain;                          // accumulation chain length in k-blocks (0 = unlimited)
+  int f16;                            // forward operands are fp16 pairs
   long long R, RM, BM, ZW;   // B*K, B*K*M, B*M, 1024*M
   int nblk;
   explicit Dims(const vmm_em_config& c)
-      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), R(1ll * c.B * c.K),
+      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16), R(1ll * c.B * c.K),
         RM(1ll * c.B * c.K * c.M), BM(1ll * c.B * c.M), ZW(1ll * E1 * c.M), nblk(2 * ((c.D + 255) / 256)) {}
 };
 
 struct Weights {
-  Planes w1, w2, wih, whh, w4, w5, w3, w13;
+  Op w1, w2, wih, whh, w4, w5, w3, w13;
   float* w13f;
   float* w1b3;
   long long bytes;
   Weights(const vmm_em_config& c, void* base) {
     Dims d(c);
     Bump b(base);
-    w1 = b.planes(1ll * E1 * d.D, d.planes);
-    w2 = b.planes(1ll * E2 * d.ZW, d.planes);
-    wih = b.planes(3ll * d.H * E2, d.planes);
-    whh = b.planes(3ll * d.H * d.H, d.planes);
-    w4 = b.planes(1ll * E2 * d.H, d.planes);
-    w5 = b.planes(d.ZW * E2, d.planes);
-    w3 = b.planes(1ll * d.D * E1, d.planes);
-    w13 = b.planes(1ll * E1 * E1, d.planes);
+    w1 = b.op(1ll * E1 * d.D, d.planes, d.f16, d.pb);
+    w2 = b.op(1ll * E2 * d.ZW, d.planes, d.f16, d.pb);
+    wih = b.op(3ll * d.H * E2, d.planes, d.f16, d.pb);
+    whh = b.op(3ll * d.H * d.H, d.planes, d.f16, d.pb);
+    w4 = b.op(1ll * E2 * d.H, d.planes, d.f16, d.pb);
+    w5 = b.op(d.ZW * E2, d.planes, d.f16, d.pb);
+    w3 = b.op(1ll * d.D * E1, d.planes, d.f16, d.pb);
+    w13 = b.op(1ll * E1 * E1, d.planes, d.f16, d.pb);
     w13f = b.take<float>(1ll * E1 * E1);
     w1b3 = b.take<float>(E1);
     bytes = b.off + 256;
@@ -54,20 +55,20 @@ struct Weights {
 
 struct IterBufs {
   float *g1, *mean1, *rstd1;
-  Planes a;
+  Op a;
   float *g2, *mean2, *rstd2;
-  Planes e;
+  Op e;
   float *gi, *gh, *h;
-  Planes hp;
+  Op hp;
   float *g4, *mean4, *rstd4;
-  Planes u;
+  Op u;
   float *g5, *mean5, *rstd5;
-  Planes z;
+  Op z;
   float *gamma, *inv_s;
 };
 
 struct Workspace {
-  Planes x;          // operand planes of the features (hi aliases x itself when x is bf16)
+  Op x;              // operand planes of the features
   float* xw1;        // [B*M, 1024]
   float* h0;         // zeros [R, H]
   float *row_sq, *row_pp;
@@ -78,7 +79,8 @@ struct Workspace {
   Dims d;
   Workspace(const vmm_em_config& c, void* wsbase) : base(static_cast<char*>(wsbase)), d(c) {
     Bump b(wsbase);
-    if (!c.x_is_bf16) x = b.planes(d.BM * d.D, d.planes);
+    if (!c.x_is_bf16) x = b.op(d.BM * d.D, d.planes, d.f16, d.pb);
+    else if (d.f16) x.f = b.planes(d.BM * d.D, 1, VMM_FMT_F16PAIR);   // bf16 features up-cast to one exact fp16 plane
     xw1 = b.take<float>(d.BM * E1);
     h0 = b.take<float>(d.R * d.H);
     row_sq = b.take<float>(d.RM);
@@ -96,23 +98,23 @@ struct Workspace {
     t.g1 = b.take<float>(d.RM * E1);
     t.mean1 = b.take<float>(d.RM);
     t.rstd1 = b.take<float>(d.RM);
-    t.a = b.planes(d.RM * E1, d.planes);
+    t.a = b.op(d.RM * E1, d.planes, d.f16, d.pb);
     t.g2 = b.take<float>(d.R * E2);
     t.mean2 = b.take<float>(d.R);
     t.rstd2 = b.take<float>(d.R);
-    t.e = b.planes(d.R * E2, d.planes);
+    t.e = b.op(d.R * E2, d.planes, d.f16, d.pb);
     t.gi = b.take<float>(d.R * 3 * d.H);
     t.gh = b.take<float>(d.R * 3 * d.H);
     t.h = b.take<float>(d.R * d.H);
-    t.hp = b.planes(d.R * d.H, d.planes);
+    t.hp = b.op(d.R * d.H, d.planes, d.f16, d.pb);
     t.g4 = b.take<float>(d.R * E2);
     t.mean4 = b.take<float>(d.R);
     t.rstd4 = b.take<float>(d.R);
-    t.u = b.planes(d.R * E2, d.planes);
+    t.u = b.op(d.R * E2, d.planes, d.f16, d.pb);
     t.g5 = b.take<float>(d.R * d.ZW);
     t.mean5 = b.take<float>(d.R);
     t.rstd5 = b.take<float>(d.R);
-    t.z = b.planes(d.RM * E1, d.planes);
+    t.z = b.op(d.RM * E1, d.planes, d.f16, d.pb);
     t.gamma = b.take<float>(d.RM);
     t.inv_s = b.take<float>(d.BM);
     if (o) *o = t;
@@ -174,7 +176,8 @@ int check_cfg(const vmm_em_config* c) {
   VMM_REQUIRE(c->B > 0 && c->K > 0 && c->M > 0 && c->D > 0 && c->H > 0 && c->T > 0, "non-positive dimension");
   VMM_REQUIRE(c->D % 8 == 0 && c->H % 8 == 0, "D and H must be multiples of 8");
   VMM_REQUIRE(c->planes >= 1 && c->planes <= 3, "planes must be 1, 2 or 3");
-  VMM_REQUIRE(c->planes_bwd >= 1 && c->planes_bwd <= c->planes, "planes_bwd must be in [1, planes]");
+  VMM_REQUIRE(c->planes_bwd >= 1 && c->planes_bwd <= 3, "planes_bwd must be 1, 2 or 3");
+  VMM_REQUIRE(c->fwd_fp16 ? c->planes <= 2 : c->planes_bwd <= c->planes, "fp16 pairs have at most 2 planes; bf16 planes_bwd <= planes");
   VMM_REQUIRE(c->if_gamma_prior >= 0 && c->if_gamma_prior <= 2, "if_gamma_prior must be 0, 1 or 2");
   VMM_REQUIRE(c->sigma > 0.f && c->ln_eps > 0.f, "sigma and ln_eps must be positive");
   VMM_REQUIRE(c->accum_chain >= 0, "accum_chain must be >= 0");
@@ -193,14 +196,14 @@ int linear_fwd(const Planes& a, const Planes& w, long long rows, int n, long lon
 int linear_dgrad(const Planes& dy, const Planes& w, long long rows, int n, long long k, float* dx, bool accumulate,
                  int chain, cudaStream_t st) {
   vmm_gemm_seg s[9];
-  const int ns = make_segs(s, dy, n, w.first(dy.n), k, n);
+  const int ns = make_segs(s, dy, n, w, k, n);
   return gemm_bf16(static_cast<int>(rows), static_cast<int>(k), ns, s, false, true, dx, k, nullptr, accumulate, 1, chain, st);
 }
 // dw[n, k] += dy[rows, n]^T * x[rows, k]     (weight gradient; both operands read MN-major, split-K)
 int linear_wgrad(const Planes& dy, const Planes& x, long long rows, int n, long long k, float* dw, int chain,
                  cudaStream_t st) {
   vmm_gemm_seg s[9];
-  const int ns = make_segs(s, dy, n, x.first(dy.n), k, rows);
+  const int ns = make_segs(s, dy, n, x, k, rows);
   return gemm_bf16(n, static_cast<int>(k), ns, s, true, true, dw, k, nullptr, true, 0, chain, st);
 }
 
@@ -228,19 +231,19 @@ int em_prepare(const vmm_em_config* c, const vmm_em_params* p, void* weights, vo
   (void)scratch;
   Dims d(*c);
   Weights w(*c, weights);
-  VMM_TRY(split_planes(p->enc1_w, 1ll * E1 * d.D, w.w1, st));
-  VMM_TRY(split_planes(p->enc2_w, 1ll * E2 * d.ZW, w.w2, st));
-  VMM_TRY(split_planes(p->gru_w_ih, 3ll * d.H * E2, w.wih, st));
-  VMM_TRY(split_planes(p->gru_w_hh, 3ll * d.H * d.H, w.whh, st));
-  VMM_TRY(split_planes(p->dec1_w, 1ll * E2 * d.H, w.w4, st));
-  VMM_TRY(split_planes(p->dec2_w, d.ZW * E2, w.w5, st));
-  VMM_TRY(split_planes(p->dec3_w, 1ll * d.D * E1, w.w3, st));
+  VMM_TRY(split_op(p->enc1_w, 1ll * E1 * d.D, w.w1, st));
+  VMM_TRY(split_op(p->enc2_w, 1ll * E2 * d.ZW, w.w2, st));
+  VMM_TRY(split_op(p->gru_w_ih, 3ll * d.H * E2, w.wih, st));
+  VMM_TRY(split_op(p->gru_w_hh, 3ll * d.H * d.H, w.whh, st));
+  VMM_TRY(split_op(p->dec1_w, 1ll * E2 * d.H, w.w4, st));
+  VMM_TRY(split_op(p->dec2_w, d.ZW * E2, w.w5, st));
+  VMM_TRY(split_op(p->dec3_w, 1ll * d.D * E1, w.w3, st));
   // W13[i, j] = sum_d W1[i, d] W3[d, j]:  A = W1 (K-major over d), B[n=j][k=d] = W3[d][j] (N-major)
   {
     vmm_gemm_seg s[9];
-    const int ns = make_segs(s, w.w1, d.D, w.w3, E1, d.D);
+    const int ns = make_segs(s, w.w1.f, d.D, w.w3.f, E1, d.D);
     VMM_TRY(gemm_bf16(E1, E1, ns, s, false, true, w.w13f, E1, nullptr, false, 1, d.chain, st));
-    VMM_TRY(split_planes(w.w13f, 1ll * E1 * E1, w.w13, st));
+    VMM_TRY(split_op(w.w13f, 1ll * E1 * E1, w.w13, st));
   }
   VMM_TRY(gemv_rows(E1, d.D, p->enc1_w, p->dec3_b, w.w1b3, st));
   return 0;
@@ -259,15 +262,17 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
   const float eps = c->ln_eps;
 
   // operand planes of the features and W1 x (once per batch)
-  Planes xp = ws.x;
+  Op xp = ws.x;
   if (c->x_is_bf16) {
-    xp = Planes();
-    xp.n = 1;
-    xp.p[0] = static_cast<__nv_bfloat16*>(const_cast<void*>(x));     // bf16 features are their own (exact) plane
+    xp.b = Planes();
+    xp.b.n = 1;
+    xp.b.p[0] = static_cast<__nv_bfloat16*>(const_cast<void*>(x));   // bf16 features are their own (exact) plane
+    if (d.f16) VMM_TRY(bf16_to_f16(x, d.BM * d.D, xp.f.p[0], st));
+    else xp.f = xp.b;
   } else {
-    VMM_TRY(split_planes(static_cast<const float*>(x), d.BM * d.D, xp, st));
+    VMM_TRY(split_op(static_cast<const float*>(x), d.BM * d.D, xp, st));
   }
-  VMM_TRY(linear_fwd(xp, w.w1, d.BM, E1, d.D, ws.xw1, d.chain, st));
+  VMM_TRY(linear_fwd(xp.f, w.w1.f, d.BM, E1, d.D, ws.xw1, d.chain, st));
   VMM_CHECK_CUDA(cudaMemsetAsync(ws.h0, 0, sizeof(float) * d.R * d.H, st));
 
   for (int t = 0; t < d.T; ++t) {
@@ -276,7 +281,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
     const bool last = (t == d.T - 1);
     const float* gam_prev = t > 0 ? prev.gamma : gamma0;
     // --- enc1 on the responsibility-weighted residual (train_nem.py:280-284, 226)
-    if (t > 0) VMM_TRY(linear_fwd(prev.z, w.w13, d.RM, E1, E1, cur.g1, d.chain, st));
+    if (t > 0) VMM_TRY(linear_fwd(prev.z.f, w.w13.f, d.RM, E1, E1, cur.g1, d.chain, st));
     {
       LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps);
       ln.xw1 = ws.xw1;
@@ -287,25 +292,25 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
       VMM_TRY(ln_forward(LN_ENC1, ACT_ELU, ln, cur.a, cur.mean1, cur.rstd1, st));
     }
     // --- enc2 (train_nem.py:228-229)
-    VMM_TRY(linear_fwd(cur.a, w.w2, d.R, E2, d.ZW, cur.g2, d.chain, st));
+    VMM_TRY(linear_fwd(cur.a.f, w.w2.f, d.R, E2, d.ZW, cur.g2, d.chain, st));
     VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps), cur.e,
                        cur.mean2, cur.rstd2, st));
     // --- GRU (train_nem.py:232)
-    VMM_TRY(linear_fwd(cur.e, w.wih, d.R, 3 * d.H, E2, cur.gi, d.chain, st));
-    if (t > 0) VMM_TRY(linear_fwd(prev.hp, w.whh, d.R, 3 * d.H, d.H, cur.gh, d.chain, st));
+    VMM_TRY(linear_fwd(cur.e.f, w.wih.f, d.R, 3 * d.H, E2, cur.gi, d.chain, st));
+    if (t > 0) VMM_TRY(linear_fwd(prev.hp.f, w.whh.f, d.R, 3 * d.H, d.H, cur.gh, d.chain, st));
     else VMM_CHECK_CUDA(cudaMemsetAsync(cur.gh, 0, sizeof(float) * d.R * 3 * d.H, st));
     VMM_TRY(gru_forward(static_cast<int>(d.R), d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, t > 0 ? prev.h : ws.h0, cur.h,
                         cur.hp, st));
     // --- dec1, dec2 (train_nem.py:238-240)
-    VMM_TRY(linear_fwd(cur.hp, w.w4, d.R, E2, d.H, cur.g4, d.chain, st));
+    VMM_TRY(linear_fwd(cur.hp.f, w.w4.f, d.R, E2, d.H, cur.g4, d.chain, st));
     VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps), cur.u,
                        cur.mean4, cur.rstd4, st));
-    VMM_TRY(linear_fwd(cur.u, w.w5, d.R, static_cast<int>(d.ZW), E2, cur.g5, d.chain, st));
+    VMM_TRY(linear_fwd(cur.u.f, w.w5.f, d.R, static_cast<int>(d.ZW), E2, cur.g5, d.chain, st));
     VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps), cur.z,
                        cur.mean5, cur.rstd5, st));
     // --- dec3 fused with the E-step (train_nem.py:241-270)
     const bool want_pp = last && c->if_gamma_prior == 0;
-    VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, cur.z, w.w3, p->dec3_b, x,
+    VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, cur.z.f, w.w3.f, p->dec3_b, x,
                           c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
                           want_pp ? sc.part_pp : nullptr, st));
     VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
@@ -334,11 +339,11 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
   const float eps = c->ln_eps;
   const int R = static_cast<int>(d.R);
 
-  Planes xp = ws.x;
+  Op xp = ws.x;
   if (c->x_is_bf16) {
-    xp = Planes();
-    xp.n = 1;
-    xp.p[0] = static_cast<__nv_bfloat16*>(const_cast<void*>(x));
+    xp.b = Planes();
+    xp.b.n = 1;
+    xp.b.p[0] = static_cast<__nv_bfloat16*>(const_cast<void*>(x));
   }
   if (d_h) VMM_CHECK_CUDA(cudaMemcpyAsync(sc.dh, d_h, sizeof(float) * d.R * d.H, cudaMemcpyDeviceToDevice, st));
   else VMM_CHECK_CUDA(cudaMemsetAsync(sc.dh, 0, sizeof(float) * d.R * d.H, st));
@@ -365,14 +370,14 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_CHECK_CUDA(cudaMemsetAsync(sc.beta, 0, sizeof(float) * d.RM, st));
     }
     VMM_TRY(gamma_backward(d.B, d.K, d.M, c->sigma, cur.gamma, cur.inv_s, sc.dgamma, sc.alpha, st));
-    VMM_TRY(estep_backward(static_cast<int>(d.RM), d.D, E1, cur.z, w.w3, p->dec3_b, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
+    VMM_TRY(estep_backward(static_cast<int>(d.RM), d.D, E1, cur.z.f, w.w3.f, p->dec3_b, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
                            sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st));
     // --- dec3: weight gradient; dz = dpred W3 (+ dG1_{t+1} W13, the path through the next residual)
-    VMM_TRY(linear_wgrad(sc.dpred, cur.z, d.RM, d.D, E1, g->dec3_w, d.chain, st));
+    VMM_TRY(linear_wgrad(sc.dpred, cur.z.b, d.RM, d.D, E1, g->dec3_w, d.chain, st));
     {
       vmm_gemm_seg s[18];
-      int ns = make_segs(s, sc.dpred, d.D, w.w3.first(d.pb), E1, d.D);
-      if (!last) ns += make_segs(s + ns, sc.dg1, E1, w.w13.first(d.pb), E1, E1);
+      int ns = make_segs(s, sc.dpred, d.D, w.w3.b, E1, d.D);
+      if (!last) ns += make_segs(s + ns, sc.dg1, E1, w.w13.b, E1, E1);
       VMM_TRY(gemm_bf16(static_cast<int>(d.RM), E1, ns, s, false, true, sc.dz, E1, nullptr, false, 1, d.chain, st));
     }
     // --- dec2: LayerNorm(1024*M) backward, dgrad, wgrad
@@ -383,8 +388,8 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_NONE, ln, cur.mean5, cur.rstd5, sc.c1, sc.c2, sc.dz, d.ZW, g->dec2_ln_g,
                                g->dec2_ln_b, g->dec2_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv5, w.w5, d.R, static_cast<int>(d.ZW), E2, sc.du, false, d.chain, st));
-    VMM_TRY(linear_wgrad(sc.dv5, cur.u, d.R, static_cast<int>(d.ZW), E2, g->dec2_w, d.chain, st));
+    VMM_TRY(linear_dgrad(sc.dv5, w.w5.b, d.R, static_cast<int>(d.ZW), E2, sc.du, false, d.chain, st));
+    VMM_TRY(linear_wgrad(sc.dv5, cur.u.b, d.R, static_cast<int>(d.ZW), E2, g->dec2_w, d.chain, st));
     // --- dec1
     {
       LnDesc ln = ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps);
@@ -393,16 +398,16 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.c1, sc.c2, sc.du, E2, g->dec1_ln_g,
                                g->dec1_ln_b, g->dec1_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv4, w.w4, d.R, E2, d.H, dh, true, d.chain, st));          // dh += dG4 W4
-    VMM_TRY(linear_wgrad(sc.dv4, cur.hp, d.R, E2, d.H, g->dec1_w, d.chain, st));
+    VMM_TRY(linear_dgrad(sc.dv4, w.w4.b, d.R, E2, d.H, dh, true, d.chain, st));          // dh += dG4 W4
+    VMM_TRY(linear_wgrad(sc.dv4, cur.hp.b, d.R, E2, d.H, g->dec1_w, d.chain, st));
     // --- GRU
     VMM_TRY(gru_backward(R, d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, t > 0 ? prev.h : ws.h0, dh, sc.dgi, sc.dgh,
                          dh_prev, g->gru_b_ih, g->gru_b_hh, st));
-    VMM_TRY(linear_dgrad(sc.dgi, w.wih, d.R, 3 * d.H, E2, sc.de, false, d.chain, st));
-    VMM_TRY(linear_wgrad(sc.dgi, cur.e, d.R, 3 * d.H, E2, g->gru_w_ih, d.chain, st));
+    VMM_TRY(linear_dgrad(sc.dgi, w.wih.b, d.R, 3 * d.H, E2, sc.de, false, d.chain, st));
+    VMM_TRY(linear_wgrad(sc.dgi, cur.e.b, d.R, 3 * d.H, E2, g->gru_w_ih, d.chain, st));
     if (t > 0) {
-      VMM_TRY(linear_dgrad(sc.dgh, w.whh, d.R, 3 * d.H, d.H, dh_prev, true, d.chain, st));   // dh_{t-1} += dgh Whh
-      VMM_TRY(linear_wgrad(sc.dgh, prev.hp, d.R, 3 * d.H, d.H, g->gru_w_hh, d.chain, st));
+      VMM_TRY(linear_dgrad(sc.dgh, w.whh.b, d.R, 3 * d.H, d.H, dh_prev, true, d.chain, st));   // dh_{t-1} += dgh Whh
+      VMM_TRY(linear_wgrad(sc.dgh, prev.hp.b, d.R, 3 * d.H, d.H, g->gru_w_hh, d.chain, st));
     }
     {
       float* tmp = dh;
@@ -417,8 +422,8 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.c1, sc.c2, sc.de, E2, g->enc2_ln_g,
                                g->enc2_ln_b, g->enc2_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv2, w.w2, d.R, E2, d.ZW, sc.da, false, d.chain, st));
-    VMM_TRY(linear_wgrad(sc.dv2, cur.a, d.R, E2, d.ZW, g->enc2_w, d.chain, st));
+    VMM_TRY(linear_dgrad(sc.dv2, w.w2.b, d.R, E2, d.ZW, sc.da, false, d.chain, st));
+    VMM_TRY(linear_wgrad(sc.dv2, cur.a.b, d.R, E2, d.ZW, g->enc2_w, d.chain, st));
     // --- enc1 + residual: dgamma_{t-1}, dXW1, dG1 (-> dz_{t-1} and dW13)
     {
       LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps);
@@ -432,19 +437,19 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_TRY(ln_backward_cols(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.c1, sc.c2, sc.da, E1, g->enc1_ln_g,
                                g->enc1_ln_b, g->enc1_b, t > 0 ? sc.dw1b3 : nullptr, st));
     }
-    if (t > 0) VMM_TRY(linear_wgrad(sc.dg1, prev.z, d.RM, E1, E1, sc.dw13, d.chain, st));
+    if (t > 0) VMM_TRY(linear_wgrad(sc.dg1, prev.z.b, d.RM, E1, E1, sc.dw13, d.chain, st));
   }
   // --- parameters behind the fold: XW1 = x W1^T, W13 = W1 W3, w1b3 = W1 b3
   VMM_TRY(split_planes(sc.dxw1, d.BM * E1, sc.dxw1p, st));
-  VMM_TRY(linear_wgrad(sc.dxw1p, xp, d.BM, E1, d.D, g->enc1_w, d.chain, st));                       // dW1 += dXW1^T x
+  VMM_TRY(linear_wgrad(sc.dxw1p, xp.b, d.BM, E1, d.D, g->enc1_w, d.chain, st));                       // dW1 += dXW1^T x
   VMM_TRY(split_planes(sc.dw13, 1ll * E1 * E1, sc.dw13p, st));
   {
     vmm_gemm_seg s[9];
     // dW1[i, d] += sum_j dW13[i, j] W3[d, j]
-    int ns = make_segs(s, sc.dw13p, E1, w.w3.first(d.pb), E1, E1);
+    int ns = make_segs(s, sc.dw13p, E1, w.w3.b, E1, E1);
     VMM_TRY(gemm_bf16(E1, d.D, ns, s, false, false, g->enc1_w, d.D, nullptr, true, 0, d.chain, st));
     // dW3[d, j] += sum_i W1[i, d] dW13[i, j]
-    ns = make_segs(s, w.w1.first(d.pb), d.D, sc.dw13p, E1, E1);
+    ns = make_segs(s, w.w1.b, d.D, sc.dw13p, E1, E1);
     VMM_TRY(gemm_bf16(d.D, E1, ns, s, true, true, g->dec3_w, E1, nullptr, true, 0, d.chain, st));
   }
   VMM_TRY(rank1_update(E1, d.D, sc.dw1b3, p->dec3_b, g->enc1_w, st));                       // dW1 += dw1b3 b3^T
@@ -489,8 +494,8 @@ const void* vmm_em_workspace_ptr(const vmm_em_config* cfg, const void* workspace
   vmm::Workspace ws(*cfg, const_cast<void*>(workspace));
   const vmm::IterBufs b = ws.slot(iter);
   struct { const char* n; const void* p; } tab[] = {
-      {"xw1", ws.xw1}, {"g1", b.g1}, {"a_hi", b.a.p[0]}, {"g2", b.g2}, {"e_hi", b.e.p[0]}, {"gi", b.gi}, {"gh", b.gh},
-      {"h", b.h}, {"h_hi", b.hp.p[0]}, {"g4", b.g4}, {"u_hi", b.u.p[0]}, {"g5", b.g5}, {"z_hi", b.z.p[0]}, {"z_lo", b.z.p[1]},
+      {"xw1", ws.xw1}, {"g1", b.g1}, {"a_hi", b.a.f.p[0]}, {"g2", b.g2}, {"e_hi", b.e.f.p[0]}, {"gi", b.gi}, {"gh", b.gh},
+      {"h", b.h}, {"h_hi", b.hp.f.p[0]}, {"g4", b.g4}, {"u_hi", b.u.f.p[0]}, {"g5", b.g5}, {"z_hi", b.z.f.p[0]}, {"z_lo", b.z.f.p[1]},
       {"gamma", b.gamma}, {"row_sq", ws.row_sq}};
   for (auto& e : tab)
     if (strcmp(e.n, name) == 0) return e.p;

@@ -4,6 +4,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.h"
 #include "gemm.cuh"
 #include "internal.h"
@@ -164,6 +166,7 @@ static int fill_common(GemmParams& p, int M, int N, int nseg, const vmm_gemm_seg
     if (!b_mn) VMM_TRY(make_tmap_bf16(&p.tma_b[s], g.b, g.k, N, g.ldb, BK, BN));
     else       VMM_TRY(make_tmap_bf16(&p.tma_b[s], g.b, N, g.k, g.ldb, 64, BK));
     p.seg_kb[s] = ceil_div(g.k, BK);
+    p.seg_flags[s] = g.flags;
     if (p.seg_kb[s] > nkb_max) nkb_max = p.seg_kb[s];
   }
   // Accumulation chains and split-K.  chain_req > 0 bounds the k-blocks one TMEM accumulation may
@@ -206,14 +209,38 @@ int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool 
   return launch_major<EPI_STORE, float, 1>(p, a_mn, b_mn, stream);
 }
 
+// Segment list of A (planes) x B (planes), least significant terms first.
+//  bf16 x bf16 residual planes : cross terms A_i B_j with i + j < max(na, nb).
+//  fp16 pairs (hi, lo' = lo * 2^11): the scaled cross terms (lo'_a hi_b, hi_a lo'_b) are accumulated
+//  first, then folded in by rescaling the accumulator by 2^-11 at the first MMA of the main terms.
+//  Mixed (bf16 gradient planes x fp16-pair weights/activations): (a_0 lo'_b) scaled, then a_i hi_b.
 int make_segs(vmm_gemm_seg* s, const Planes& a, long long lda, const Planes& b, long long ldb, long long k) {
-  const int order = a.n > b.n ? a.n : b.n;
+  const bool af = a.fmt == VMM_FMT_F16PAIR, bf = b.fmt == VMM_FMT_F16PAIR;
+  const unsigned ff = (af ? VMM_SEG_A_F16 : 0u) | (bf ? VMM_SEG_B_F16 : 0u);
   int n = 0;
-  for (int sum = order - 1; sum >= 0; --sum)
-    for (int i = 0; i < a.n; ++i) {
+  if (!af && !bf) {
+    const int order = a.n > b.n ? a.n : b.n;
+    for (int sum = order - 1; sum >= 0; --sum)
+      for (int i = 0; i < a.n; ++i) {
+        const int j = sum - i;
+        if (j < 0 || j >= b.n) continue;
+        s[n++] = {a.p[i], lda, b.p[j], ldb, k, 0u};
+      }
+    return n;
+  }
+  // scaled group
+  if (af && a.n > 1) s[n++] = {a.p[1], lda, b.p[0], ldb, k, ff};
+  if (bf && b.n > 1) s[n++] = {a.p[0], lda, b.p[1], ldb, k, ff};
+  const int scaled = n;
+  // main group: residual planes of the bf16 side (if any) against the hi plane of the fp16 side
+  const int na = af ? 1 : a.n, nb = bf ? 1 : b.n;
+  for (int sum = na + nb - 2; sum >= 0; --sum)
+    for (int i = 0; i < na; ++i) {
       const int j = sum - i;
-      if (j < 0 || j >= b.n) continue;
-      s[n++] = {a.p[i], lda, b.p[j], ldb, k};
+      if (j < 0 || j >= nb) continue;
+      s[n] = {a.p[i], lda, b.p[j], ldb, k, ff};
+      if (n == scaled && scaled > 0) s[n].flags |= VMM_SEG_RESCALE11;
+      ++n;
     }
   return n;
 }
@@ -290,9 +317,12 @@ __global__ void gemm_check_kernel(int M, int N, int nseg, vmm_gemm_seg s0, vmm_g
   for (int s = 0; s < nseg; ++s) {
     const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(segs[s].a);
     const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(segs[s].b);
+    if (segs[s].flags & VMM_SEG_RESCALE11) acc *= (1.0f / 2048.f);
     for (long long k = 0; k < segs[s].k; ++k) {
-      const float av = __bfloat162float(a_mn ? a[k * segs[s].lda + m] : a[m * segs[s].lda + k]);
-      const float bv = __bfloat162float(b_mn ? b[k * segs[s].ldb + n] : b[n * segs[s].ldb + k]);
+      const __nv_bfloat16 ar = a_mn ? a[k * segs[s].lda + m] : a[m * segs[s].lda + k];
+      const __nv_bfloat16 br = b_mn ? b[k * segs[s].ldb + n] : b[n * segs[s].ldb + k];
+      const float av = (segs[s].flags & VMM_SEG_A_F16) ? __half2float(*reinterpret_cast<const __half*>(&ar)) : __bfloat162float(ar);
+      const float bv = (segs[s].flags & VMM_SEG_B_F16) ? __half2float(*reinterpret_cast<const __half*>(&br)) : __bfloat162float(br);
       acc = fmaf(av, bv, acc);
     }
   }
@@ -302,10 +332,17 @@ __global__ void gemm_check_kernel(int M, int N, int nseg, vmm_gemm_seg s0, vmm_g
 }
 
 __global__ void split_planes_kernel(const float* __restrict__ src, long long n, __nv_bfloat16* __restrict__ p0,
-                                    __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2) {
+                                    __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2, int fmt) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     float v = src[i];
+    if (fmt == VMM_FMT_F16PAIR) {
+      const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+      reinterpret_cast<__half*>(p0)[i] = h;
+      if (p1) reinterpret_cast<__half*>(p1)[i] =
+          __float2half_rn(fminf(fmaxf((v - __half2float(h)) * 2048.f, -65504.f), 65504.f));
+      continue;
+    }
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     p0[i] = h;
     if (p1) {
@@ -320,11 +357,34 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long long n, 
 int split_planes(const float* src, long long n, const Planes& out, cudaStream_t stream) {
   if (n <= 0) return 0;
   VMM_REQUIRE(src && out.n >= 1 && out.n <= 3 && out.p[0], "split_planes: bad argument");
+  VMM_REQUIRE(out.fmt == VMM_FMT_BF16 || (out.fmt == VMM_FMT_F16PAIR && out.n <= 2), "split_planes: bad plane format");
   long long blocks = (n + 255) / 256;
   const long long cap = static_cast<long long>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   split_planes_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, n, out.p[0], out.n > 1 ? out.p[1] : nullptr,
-                                                                    out.n > 2 ? out.p[2] : nullptr);
+                                                                    out.n > 2 ? out.p[2] : nullptr, out.fmt);
+  VMM_LAUNCHED();
+  return 0;
+}
+
+int split_op(const float* src, long long n, const Op& out, cudaStream_t stream) {
+  VMM_TRY(split_planes(src, n, out.f, stream));
+  if (out.b.n > 0 && out.b.p[0] != out.f.p[0]) VMM_TRY(split_planes(src, n, out.b, stream));
+  return 0;
+}
+
+__global__ void bf16_to_f16_kernel(const __nv_bfloat16* __restrict__ src, long long n, __half* __restrict__ dst) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2half_rn(fminf(fmaxf(__bfloat162float(src[i]), -65504.f), 65504.f));
+}
+int bf16_to_f16(const void* src, long long n, void* dst, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  bf16_to_f16_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), n,
+                                                                   static_cast<__half*>(dst));
   VMM_LAUNCHED();
   return 0;
 }

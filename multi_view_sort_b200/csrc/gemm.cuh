@@ -44,6 +44,7 @@ struct alignas(64) GemmParams {
   CUtensorMap tma_a[VMM_MAX_SEG];
   CUtensorMap tma_b[VMM_MAX_SEG];
   int seg_kb[VMM_MAX_SEG];   // k-blocks (of BK) in each segment
+  unsigned seg_flags[VMM_MAX_SEG];   // VMM_SEG_* bits of each segment
   int nseg;
   int chain_kb;              // k-blocks per segment accumulated in TMEM before the epilogue drains them
   int total_chains;          // ceil(max seg_kb / chain_kb)
@@ -289,7 +290,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -303,6 +303,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       bool first = true;
       for (int seg = 0; seg < p.nseg; ++seg) {
       const int k_lo = ch * p.chain_kb, k_hi = min(k_lo + p.chain_kb, p.seg_kb[seg]);
+      const unsigned fl = p.seg_flags[seg];
+      const uint32_t idesc = umma_idesc_16b(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, fl & 1u, (fl >> 1) & 1u);
+      bool rescale = (fl & 4u) != 0;                     // fold the scaled low-order terms accumulated so far
       for (int kb = k_lo; kb < k_hi; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -318,11 +321,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                                         : umma_smem_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_base + k * 2048, 64 * BK * 2, 1024)
                                         : umma_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
+            if (rescale && !first && k == 0) umma_f16_ss_rescale11(tmem_d, adesc, bdesc, idesc);
+            else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
         }
         first = false;
+        rescale = false;
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }

@@ -2,6 +2,7 @@
 // the K latent views, and the 3-layer classifier (reference: Multi_View_Net.forward,
 // train_nem.py:328-380, eval-mode semantics), with its hand-written backward; plus the softmax
 // cross-entropy the trainer applies to the logits (tools/Trainer.py:202).
+#include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
 
@@ -12,24 +13,24 @@ namespace vmm {
 namespace {
 
 struct HDims {
-  int B, K, H, C, W, M, planes, pb, chain;
+  int B, K, H, C, W, M, planes, pb, chain, f16;
   int FW;          // classifier input width: K*H (concat) or H (max-pool)
   int Cp;          // class count padded to the 8-element pitch TMA needs
   long long R;
   explicit HDims(const vmm_head_config& c)
-      : B(c.B), K(c.K), H(c.H), C(c.C), W(c.W), M(c.M), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain),
+      : B(c.B), K(c.K), H(c.H), C(c.C), W(c.W), M(c.M), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16),
         FW(c.if_pooling ? c.H : c.K * c.H), Cp((c.C + 7) / 8 * 8), R(1ll * c.B * c.K) {}
 };
 
 struct HWeights {
-  Planes w0, w3, w6;
+  Op w0, w3, w6;
   long long bytes;
   HWeights(const vmm_head_config& c, void* base) {
     HDims d(c);
     Bump b(base);
-    w0 = b.planes(1ll * d.W * d.FW, d.planes);
-    w3 = b.planes(1ll * d.W * d.W, d.planes);
-    w6 = b.planes(1ll * d.C * d.W, d.planes);
+    w0 = b.op(1ll * d.W * d.FW, d.planes, d.f16, d.pb);
+    w3 = b.op(1ll * d.W * d.W, d.planes, d.f16, d.pb);
+    w6 = b.op(1ll * d.C * d.W, d.planes, d.f16, d.pb);
     bytes = b.off + 256;
   }
 };
@@ -38,11 +39,11 @@ struct HWorkspace {
   float* score;    // [B*K] sigmoid scores
   int* order;      // [B*K] latent index placed in slot j (concat) ...
   int* argmax;     // [B*H] winning latent per column (max-pool)
-  Planes feat;     // [B, FW]
+  Op feat;         // [B, FW]
   float* t0;       // [B, W]  Linear0 output (bias added)
-  Planes t1;       // relu(t0)
+  Op t1;           // relu(t0)
   float* t3;       // [B, W]  Linear3 output = the retrieval descriptor
-  Planes t3r;      // relu(t3)
+  Op t3r;          // relu(t3)
   long long bytes;
   HWorkspace(const vmm_head_config& c, void* base) {
     HDims d(c);
@@ -50,11 +51,11 @@ struct HWorkspace {
     score = b.take<float>(d.R);
     order = b.take<int>(d.R);
     argmax = b.take<int>(1ll * d.B * d.H);
-    feat = b.planes(1ll * d.B * d.FW, d.planes);
+    feat = b.op(1ll * d.B * d.FW, d.planes, d.f16, d.pb);
     t0 = b.take<float>(1ll * d.B * d.W);
-    t1 = b.planes(1ll * d.B * d.W, d.planes);
+    t1 = b.op(1ll * d.B * d.W, d.planes, d.f16, d.pb);
     t3 = b.take<float>(1ll * d.B * d.W);
-    t3r = b.planes(1ll * d.B * d.W, d.planes);
+    t3r = b.op(1ll * d.B * d.W, d.planes, d.f16, d.pb);
     bytes = b.off + 256;
   }
 };
@@ -81,7 +82,8 @@ int check_head(const vmm_head_config* c) {
   VMM_REQUIRE(c != nullptr, "null head config");
   VMM_REQUIRE(c->B > 0 && c->K > 0 && c->K <= 32 && c->H > 0 && c->C > 0 && c->W > 0, "bad head dimension");
   VMM_REQUIRE(c->H % 8 == 0 && c->W % 8 == 0, "H and W must be multiples of 8");
-  VMM_REQUIRE(c->planes >= 1 && c->planes <= 3 && c->planes_bwd >= 1 && c->planes_bwd <= c->planes, "bad plane counts");
+  VMM_REQUIRE(c->planes >= 1 && c->planes <= 3 && c->planes_bwd >= 1 && c->planes_bwd <= 3 &&
+                  (c->fwd_fp16 ? c->planes <= 2 : c->planes_bwd <= c->planes), "bad plane counts");
   VMM_REQUIRE(c->if_sort >= 0 && c->if_sort <= 2, "if_sort must be 0, 1 or 2");
   VMM_REQUIRE(c->if_sort != 2 || c->M > 0, "if_sort == 2 needs M");
   return 0;
@@ -93,6 +95,13 @@ __device__ __forceinline__ float wsum(float v) {
   return v;
 }
 __device__ __forceinline__ void put_planes(const Planes& P, long long idx, float v) {
+  if (P.fmt == VMM_FMT_F16PAIR) {
+    const float c = fminf(fmaxf(v, -65504.f), 65504.f);
+    const __half h = __float2half_rn(c);
+    reinterpret_cast<__half*>(P.p[0])[idx] = h;
+    if (P.n > 1) reinterpret_cast<__half*>(P.p[1])[idx] = __float2half_rn((c - __half2float(h)) * 2048.f);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 3; ++i)
     if (i < P.n) {
@@ -101,13 +110,17 @@ __device__ __forceinline__ void put_planes(const Planes& P, long long idx, float
       v -= __bfloat162float(h);
     }
 }
+__device__ __forceinline__ void put_op(const Op& o, long long idx, float v) {
+  put_planes(o.f, idx, v);
+  if (o.b.n > 0 && o.b.p[0] != o.f.p[0]) put_planes(o.b, idx, v);
+}
 
 // One block (256 threads) per object: scores, ordering, and the classifier input.
 __global__ void __launch_bounds__(256) head_score_kernel(int K, int H, int M, int if_sort, int if_pooling,
                                                          const float* __restrict__ h, const float* __restrict__ gamma,
                                                          const float* __restrict__ att_w, const float* __restrict__ att_b,
                                                          float* __restrict__ score, int* __restrict__ order,
-                                                         int* __restrict__ argmax, Planes feat) {
+                                                         int* __restrict__ argmax, Op feat) {
   __shared__ float s_score[32], s_key[32], red[8];
   __shared__ int s_order[32];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -157,7 +170,7 @@ __global__ void __launch_bounds__(256) head_score_kernel(int K, int H, int M, in
   if (!if_pooling) {
     for (int i = tid; i < K * H; i += 256) {
       const int slot = i / H, j = i % H, k = s_order[slot];
-      put_planes(feat, static_cast<long long>(b) * K * H + i, s_score[k] * h[(static_cast<long long>(b) * K + k) * H + j]);
+      put_op(feat, static_cast<long long>(b) * K * H + i, s_score[k] * h[(static_cast<long long>(b) * K + k) * H + j]);
     }
   } else {
     for (int j = tid; j < H; j += 256) {
@@ -168,7 +181,7 @@ __global__ void __launch_bounds__(256) head_score_kernel(int K, int H, int M, in
         if (v > best) { best = v; bk = k; }
       }
       argmax[static_cast<long long>(b) * H + j] = bk;
-      put_planes(feat, static_cast<long long>(b) * H + j, best);
+      put_op(feat, static_cast<long long>(b) * H + j, best);
     }
   }
 }
@@ -280,13 +293,13 @@ int lin_fwd(const Planes& a, const Planes& w, long long rows, int n, long long k
 int lin_dgrad(const Planes& dy, long long ldy, const Planes& w, long long rows, int n, long long k, float* dx, int chain,
               cudaStream_t st) {
   vmm_gemm_seg s[9];
-  const int ns = make_segs(s, dy, ldy, w.first(dy.n), k, n);
+  const int ns = make_segs(s, dy, ldy, w, k, n);
   return gemm_bf16(static_cast<int>(rows), static_cast<int>(k), ns, s, false, true, dx, k, nullptr, false, 1, chain, st);
 }
 int lin_wgrad(const Planes& dy, long long ldy, const Planes& x, long long rows, int n, long long k, float* dw, int chain,
               cudaStream_t st) {
   vmm_gemm_seg s[9];
-  const int ns = make_segs(s, dy, ldy, x.first(dy.n), k, rows);
+  const int ns = make_segs(s, dy, ldy, x, k, rows);
   return gemm_bf16(n, static_cast<int>(k), ns, s, true, true, dw, k, nullptr, true, 0, chain, st);
 }
 
@@ -315,9 +328,9 @@ int head_prepare(const vmm_head_config* c, const vmm_head_params* p, void* weigh
   VMM_REQUIRE(p && weights, "null argument");
   HDims d(*c);
   HWeights w(*c, weights);
-  VMM_TRY(split_planes(p->w0, 1ll * d.W * d.FW, w.w0, st));
-  VMM_TRY(split_planes(p->w3, 1ll * d.W * d.W, w.w3, st));
-  VMM_TRY(split_planes(p->w6, 1ll * d.C * d.W, w.w6, st));
+  VMM_TRY(split_op(p->w0, 1ll * d.W * d.FW, w.w0, st));
+  VMM_TRY(split_op(p->w3, 1ll * d.W * d.W, w.w3, st));
+  VMM_TRY(split_op(p->w6, 1ll * d.C * d.W, w.w6, st));
   return 0;
 }
 
@@ -332,13 +345,13 @@ int head_forward(const vmm_head_config* c, const vmm_head_params* p, const void*
   head_score_kernel<<<d.B, 256, 0, st>>>(d.K, d.H, d.M, c->if_sort, c->if_pooling, h, gamma, p->att_w, p->att_b, ws.score,
                                          ws.order, ws.argmax, ws.feat);
   VMM_LAUNCHED();
-  VMM_TRY(lin_fwd(ws.feat, w.w0, d.B, d.W, d.FW, ws.t0, p->b0, d.chain, st));
+  VMM_TRY(lin_fwd(ws.feat.f, w.w0.f, d.B, d.W, d.FW, ws.t0, p->b0, d.chain, st));
   VMM_TRY(act_planes(ACT_RELU, d.B, d.W, ws.t0, d.W, ws.t1, st));
-  VMM_TRY(lin_fwd(ws.t1, w.w3, d.B, d.W, d.W, ws.t3, p->b3, d.chain, st));
+  VMM_TRY(lin_fwd(ws.t1.f, w.w3.f, d.B, d.W, d.W, ws.t3, p->b3, d.chain, st));
   if (descriptor) VMM_CHECK_CUDA(cudaMemcpyAsync(descriptor, ws.t3, sizeof(float) * d.B * d.W, cudaMemcpyDeviceToDevice, st));
   if (logits) {
     VMM_TRY(act_planes(ACT_RELU, d.B, d.W, ws.t3, d.W, ws.t3r, st));
-    VMM_TRY(lin_fwd(ws.t3r, w.w6, d.B, d.C, d.W, logits, p->b6, d.chain, st));
+    VMM_TRY(lin_fwd(ws.t3r.f, w.w6.f, d.B, d.C, d.W, logits, p->b6, d.chain, st));
   }
   return 0;
 }
@@ -357,8 +370,8 @@ int head_backward(const vmm_head_config* c, const vmm_head_params* p, const void
     pad_planes_kernel<<<blocks_for(1ll * d.B * d.Cp), 256, 0, st>>>(d.B, d.C, d.Cp, d_logits, sc.dl);
     VMM_LAUNCHED();
     VMM_TRY(colsum_acc(d.B, d.C, d_logits, d.C, g->b6, st));
-    VMM_TRY(lin_wgrad(sc.dl, d.Cp, ws.t3r, d.B, d.C, d.W, g->w6, d.chain, st));
-    VMM_TRY(lin_dgrad(sc.dl, d.Cp, w.w6, d.B, d.C, d.W, sc.dt3f, d.chain, st));
+    VMM_TRY(lin_wgrad(sc.dl, d.Cp, ws.t3r.b, d.B, d.C, d.W, g->w6, d.chain, st));
+    VMM_TRY(lin_dgrad(sc.dl, d.Cp, w.w6.b, d.B, d.C, d.W, sc.dt3f, d.chain, st));
     VMM_TRY(act_backward(ACT_RELU, BW, ws.t3, sc.dt3f, st));
     if (d_descriptor) {
       add_kernel<<<blocks_for(BW), 256, 0, st>>>(BW, d_descriptor, sc.dt3f);
@@ -369,13 +382,13 @@ int head_backward(const vmm_head_config* c, const vmm_head_params* p, const void
   }
   VMM_TRY(split_planes(sc.dt3f, BW, sc.dt3, st));
   VMM_TRY(colsum_acc(d.B, d.W, sc.dt3f, d.W, g->b3, st));
-  VMM_TRY(lin_wgrad(sc.dt3, d.W, ws.t1, d.B, d.W, d.W, g->w3, d.chain, st));
-  VMM_TRY(lin_dgrad(sc.dt3, d.W, w.w3, d.B, d.W, d.W, sc.dt0f, d.chain, st));
+  VMM_TRY(lin_wgrad(sc.dt3, d.W, ws.t1.b, d.B, d.W, d.W, g->w3, d.chain, st));
+  VMM_TRY(lin_dgrad(sc.dt3, d.W, w.w3.b, d.B, d.W, d.W, sc.dt0f, d.chain, st));
   VMM_TRY(act_backward(ACT_RELU, BW, ws.t0, sc.dt0f, st));
   VMM_TRY(split_planes(sc.dt0f, BW, sc.dt0, st));
   VMM_TRY(colsum_acc(d.B, d.W, sc.dt0f, d.W, g->b0, st));
-  VMM_TRY(lin_wgrad(sc.dt0, d.W, ws.feat, d.B, d.W, d.FW, g->w0, d.chain, st));
-  VMM_TRY(lin_dgrad(sc.dt0, d.W, w.w0, d.B, d.W, d.FW, sc.dfeat, d.chain, st));
+  VMM_TRY(lin_wgrad(sc.dt0, d.W, ws.feat.b, d.B, d.W, d.FW, g->w0, d.chain, st));
+  VMM_TRY(lin_dgrad(sc.dt0, d.W, w.w0.b, d.B, d.W, d.FW, sc.dfeat, d.chain, st));
   head_score_backward_kernel<<<d.B, 256, 0, st>>>(d.K, d.H, c->if_pooling, h, p->att_w, ws.score, ws.order, ws.argmax,
                                                   sc.dfeat, d_h, sc.ds_pre);
   VMM_LAUNCHED();

@@ -6,19 +6,28 @@ namespace vmm {
 
 // Operand planes: successive bf16 residuals of one matrix (see vmm_planes in the C header).
 struct Planes {
-  __nv_bfloat16* p[3] = {nullptr, nullptr, nullptr};
+  __nv_bfloat16* p[3] = {nullptr, nullptr, nullptr};   // fp16 bits when fmt == VMM_FMT_F16PAIR
   int n = 0;
+  int fmt = VMM_FMT_BF16;
   Planes first(int k) const {          // the k most significant planes
     Planes r;
     r.n = k < n ? k : n;
+    r.fmt = fmt;
     for (int i = 0; i < r.n; ++i) r.p[i] = p[i];
     return r;
   }
+};
+// A forward tensor that is consumed both by forward contractions (f: bf16 residual planes or an fp16
+// pair) and by gradient contractions (b: bf16 planes; kind::f16 cannot mix bf16 and fp16 operands).
+// With bf16 forward planes, b aliases the leading planes of f.
+struct Op {
+  Planes f, b;
 };
 inline Planes planes_from_c(const vmm_planes* c) {
   Planes r;
   if (c) {
     r.n = c->n;
+    r.fmt = c->fmt;
     for (int i = 0; i < 3; ++i) r.p[i] = i < c->n ? static_cast<__nv_bfloat16*>(c->p[i]) : nullptr;
   }
   return r;
@@ -35,11 +44,25 @@ struct Bump {
     off += count * static_cast<long long>(sizeof(T));
     return p;
   }
-  Planes planes(long long count, int n) {
+  Planes planes(long long count, int n, int fmt = VMM_FMT_BF16) {
     Planes p;
     p.n = n;
+    p.fmt = fmt;
     for (int i = 0; i < n; ++i) p.p[i] = take<__nv_bfloat16>(count);
     return p;
+  }
+  // forward operand with n_f planes (fp16 pair when fwd_fp16) + n_b bf16 planes for the gradient contractions
+  Op op(long long count, int n_f, int fwd_fp16, int n_b) {
+    Op o;
+    if (fwd_fp16) {
+      o.f = planes(count, n_f, VMM_FMT_F16PAIR);
+      o.b = planes(count, n_b, VMM_FMT_BF16);
+    } else {
+      o.f = planes(count, n_f > n_b ? n_f : n_b, VMM_FMT_BF16);
+      o.b = o.f.first(n_b);
+      o.f = o.f.first(n_f);
+    }
+    return o;
   }
 };
 
@@ -55,5 +78,7 @@ int estep_backward(int rows, int D, int zk, const Planes& z, const Planes& w3, c
                    int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
                    const float* beta, const float* kappa, const Planes& dpred, float* colsum, cudaStream_t stream);
 int split_planes(const float* src, long long n, const Planes& out, cudaStream_t stream);
+int split_op(const float* src, long long n, const Op& out, cudaStream_t stream);   // both operand sets
+int bf16_to_f16(const void* src_bf16, long long n, void* dst_f16, cudaStream_t stream);
 
 }  // namespace vmm

@@ -93,6 +93,16 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, but the accumulator is first scaled by 2^-11 (D = A*B + D * 2^-11): folds the scaled low-order
+// cross terms of an fp16 hi/lo operand pair into the main product (precision).
+__device__ __forceinline__ void umma_f16_ss_rescale11(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base_lane+i).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -120,14 +130,14 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D
-// (cute::UMMA::InstrDescriptor): c_format[4,6)=1 (F32), a_format[7,10)=1 (BF16),
-// b_format[10,13)=1, a_major bit15, b_major bit16 (0 = K-major, 1 = MN-major),
-// n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
-         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
+// Instruction descriptor for kind::f16 with 16-bit A/B and fp32 D (cute::UMMA::InstrDescriptor):
+// c_format[4,6)=1 (F32), a_format[7,10) / b_format[10,13): 0 = F16, 1 = BF16, a_major bit15,
+// b_major bit16 (0 = K-major, 1 = MN-major), n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
+__host__ __device__ constexpr uint32_t umma_idesc_16b(int m, int n, int a_mn_major, int b_mn_major, int a_is_f16,
+                                                      int b_is_f16) {
+  return (1u << 4) | ((a_is_f16 ? 0u : 1u) << 7) | ((b_is_f16 ? 0u : 1u) << 10) |
+         (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // ---- small utilities ------------------------------------------------------------------

@@ -3,6 +3,7 @@
 // reductions by warp shuffle + smem), one thread per column for the column reductions.
 #include "stages.cuh"
 
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace vmm {
@@ -42,6 +43,24 @@ __device__ __forceinline__ float act_grad(int act, float y) {
 }
 
 __device__ __forceinline__ void store_planes4(const Planes& P, long long idx, float4 v) {
+  if (P.fmt == VMM_FMT_F16PAIR) {
+    const float c[4] = {fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f),
+                        fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f)};
+    const __half2 h0 = __floats2half2_rn(c[0], c[1]), h1 = __floats2half2_rn(c[2], c[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&h0);
+    u.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(P.p[0] + idx) = u;
+    if (P.n > 1) {
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      const __half2 l0 = __floats2half2_rn((c[0] - f0.x) * 2048.f, (c[1] - f0.y) * 2048.f);
+      const __half2 l1 = __floats2half2_rn((c[2] - f1.x) * 2048.f, (c[3] - f1.y) * 2048.f);
+      u.x = *reinterpret_cast<const uint32_t*>(&l0);
+      u.y = *reinterpret_cast<const uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(P.p[1] + idx) = u;
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if (i < P.n) {
@@ -58,6 +77,13 @@ __device__ __forceinline__ void store_planes4(const Planes& P, long long idx, fl
   }
 }
 __device__ __forceinline__ void store_planes1(const Planes& P, long long idx, float v) {
+  if (P.fmt == VMM_FMT_F16PAIR) {
+    const float c = fminf(fmaxf(v, -65504.f), 65504.f);
+    const __half h = __float2half_rn(c);
+    reinterpret_cast<__half*>(P.p[0])[idx] = h;
+    if (P.n > 1) reinterpret_cast<__half*>(P.p[1])[idx] = __float2half_rn((c - __half2float(h)) * 2048.f);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if (i < P.n) {
@@ -66,6 +92,15 @@ __device__ __forceinline__ void store_planes1(const Planes& P, long long idx, fl
       v -= __bfloat162float(h);
     }
   }
+}
+// both operand sets of a forward tensor (the bf16 set is skipped when it aliases the forward planes)
+__device__ __forceinline__ void store_op4(const Op& o, long long idx, float4 v) {
+  store_planes4(o.f, idx, v);
+  if (o.b.n > 0 && o.b.p[0] != o.f.p[0]) store_planes4(o.b, idx, v);
+}
+__device__ __forceinline__ void store_op1(const Op& o, long long idx, float v) {
+  store_planes1(o.f, idx, v);
+  if (o.b.n > 0 && o.b.p[0] != o.f.p[0]) store_planes1(o.b, idx, v);
 }
 
 // Pre-normalisation value of 4 consecutive columns, and (LN_ENC1) the residual factor s with
@@ -91,7 +126,7 @@ __device__ __forceinline__ float4 ln_value4(const LnDesc& d, int row, long long 
 // LayerNorm (+activation) forward: one block per row.
 // ------------------------------------------------------------------------------------------
 template <int MODE, bool CACHED>
-__global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int act, Planes out,
+__global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int act, Op out,
                                                                 float* mean_out, float* rstd_out) {
   __shared__ float red[32];
   const int row = blockIdx.x;
@@ -152,7 +187,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int ac
     o.y = act_fwd(act, fmaf((v.y - mean) * rstd, g.y, b.y));
     o.z = act_fwd(act, fmaf((v.z - mean) * rstd, g.z, b.z));
     o.w = act_fwd(act, fmaf((v.w - mean) * rstd, g.w, b.w));
-    store_planes4(out, obase + c, o);
+    store_op4(out, obase + c, o);
   };
   if (CACHED) {
 #pragma unroll
@@ -303,7 +338,7 @@ __global__ void __launch_bounds__(256) gru_forward_kernel(int rows, int H, const
                                                           const float* __restrict__ gh, const float* __restrict__ b_ih,
                                                           const float* __restrict__ b_hh,
                                                           const float* __restrict__ h_prev, float* __restrict__ h_new,
-                                                          Planes hp_out) {
+                                                          Op hp_out) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * H) return;
   const int row = static_cast<int>(idx / H), j = static_cast<int>(idx % H);
@@ -314,7 +349,7 @@ __global__ void __launch_bounds__(256) gru_forward_kernel(int rows, int H, const
   const float hp = h_prev[idx];
   const float h = (hp - n) * z + n;
   h_new[idx] = h;
-  store_planes1(hp_out, idx, h);
+  store_op1(hp_out, idx, h);
 }
 
 // thread per hidden column j, blockIdx.y strides over row chunks (bias gradients need column sums)
@@ -574,7 +609,7 @@ __global__ void __launch_bounds__(256) colsum_acc_kernel(int rows, int width, in
   atomicAdd(out + j, s);
 }
 __global__ void __launch_bounds__(256) act_planes_kernel(int act, long long rows, int width,
-                                                         const float* __restrict__ src, long long ld, Planes out) {
+                                                         const float* __restrict__ src, long long ld, Op out) {
   const long long n4 = rows * (width / 4);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -582,7 +617,7 @@ __global__ void __launch_bounds__(256) act_planes_kernel(int act, long long rows
     const int c = static_cast<int>(i % (width / 4)) * 4;
     float4 v = ld4(src + r * ld + c);
     v.x = act_fwd(act, v.x); v.y = act_fwd(act, v.y); v.z = act_fwd(act, v.z); v.w = act_fwd(act, v.w);
-    store_planes4(out, r * width + c, v);
+    store_op4(out, r * width + c, v);
   }
 }
 __global__ void __launch_bounds__(256) act_backward_kernel(int act, long long n, const float* __restrict__ pre,
@@ -618,9 +653,9 @@ static int check_ln(const LnDesc& d, int mode) {
   return 0;
 }
 
-int ln_forward(int mode, int act, const LnDesc& d, const Planes& out, float* mean, float* rstd, cudaStream_t stream) {
+int ln_forward(int mode, int act, const LnDesc& d, const Op& out, float* mean, float* rstd, cudaStream_t stream) {
   VMM_TRY(check_ln(d, mode));
-  VMM_REQUIRE(out.n >= 1 && out.p[0] && mean && rstd, "ln_forward: null output");
+  VMM_REQUIRE(out.f.n >= 1 && out.f.p[0] && mean && rstd, "ln_forward: null output");
   const bool cached = d.width <= LN_THREADS * 4 * LN_CACHE;
   if (mode == LN_BIAS) {
     if (cached) ln_forward_kernel<LN_BIAS, true><<<d.rows, LN_THREADS, 0, stream>>>(d, act, out, mean, rstd);
@@ -670,8 +705,8 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
 }
 
 int gru_forward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
-                const float* h_prev, float* h_new, const Planes& hp, cudaStream_t stream) {
-  VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && h_new && hp.n >= 1, "gru_forward: bad argument");
+                const float* h_prev, float* h_new, const Op& hp, cudaStream_t stream) {
+  VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && h_new && hp.f.n >= 1, "gru_forward: bad argument");
   const long long n = static_cast<long long>(rows) * H;
   gru_forward_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, h_new,
                                                                                  hp);
@@ -761,9 +796,9 @@ int colsum_acc(int rows, int width, const float* src, long long ld, float* out, 
   VMM_LAUNCHED();
   return 0;
 }
-int act_planes(int act, long long rows, int width, const float* src, long long ld, const Planes& out,
+int act_planes(int act, long long rows, int width, const float* src, long long ld, const Op& out,
                cudaStream_t stream) {
-  VMM_REQUIRE(width % 4 == 0 && ld % 4 == 0 && src && out.n >= 1, "act_planes: bad argument");
+  VMM_REQUIRE(width % 4 == 0 && ld % 4 == 0 && src && out.f.n >= 1, "act_planes: bad argument");
   if (rows <= 0) return 0;
   long long blocks = (rows * (width / 4) + 255) / 256;
   const long long cap = static_cast<long long>(device_sm_count()) * 16;

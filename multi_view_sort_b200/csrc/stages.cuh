@@ -32,7 +32,7 @@ struct LnDesc {
   float eps;
 };
 
-int ln_forward(int mode, int act, const LnDesc& d, const Planes& out, float* mean, float* rstd, cudaStream_t stream);
+int ln_forward(int mode, int act, const LnDesc& d, const Op& out, float* mean, float* rstd, cudaStream_t stream);
 
 // Backward through activation + LayerNorm (+ the enc1 prologue).  d_out is the gradient w.r.t.
 // the stage output [rows, width] (fp32).  Produces dv = dL/d(pre-normalisation value) as operand
@@ -53,7 +53,7 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
 // GRUCell gate math (train_nem.py:177,232; torch.nn.GRUCell, gate order r,z,n).
 // gi = e Wih^T, gh = h Whh^T are the raw contraction outputs [rows, 3H] (biases added here).
 int gru_forward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
-                const float* h_prev, float* h_new, const Planes& hp, cudaStream_t stream);
+                const float* h_prev, float* h_new, const Op& hp, cudaStream_t stream);
 // dh is the total gradient w.r.t. h_new.  Writes dgi/dgh operand planes [rows,3H], the direct
 // path dh_prev = dh * z (the Whh contraction adds the rest), and accumulates the bias gradients.
 int gru_backward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
@@ -83,7 +83,7 @@ int gemv_rows(int n, int k, const float* W, const float* v, float* out, cudaStre
 int rank1_update(int n, int k, const float* u, const float* v, float* W, cudaStream_t stream);            // W[i,j] += u[i] v[j]
 int gemv_cols_acc(int n, int k, const float* W, const float* u, float* out, cudaStream_t stream);         // out[j] += sum_i u[i] W[i,j]
 int colsum_acc(int rows, int width, const float* src, long long ld, float* out, cudaStream_t stream);     // out[j] += sum_r src[r,j]
-int act_planes(int act, long long rows, int width, const float* src, long long ld, const Planes& out,
+int act_planes(int act, long long rows, int width, const float* src, long long ld, const Op& out,
                cudaStream_t stream);                                                                     // planes(act(src))
 int act_backward(int act, long long n, const float* pre, float* grad, cudaStream_t stream);              // grad *= act'(pre)
 

@@ -18,7 +18,7 @@ from ._lib import check, lib, ptr, stream_ptr
 # ---- ctypes mirrors of include/vmm_b200.h ----------------------------------------------------
 class EMConfig(C.Structure):
     _fields_ = [("B", C.c_int), ("K", C.c_int), ("M", C.c_int), ("D", C.c_int), ("H", C.c_int), ("T", C.c_int),
-                ("planes", C.c_int), ("planes_bwd", C.c_int), ("x_is_bf16", C.c_int), ("if_gamma_prior", C.c_int), ("stop_gamma_grad", C.c_int),
+                ("planes", C.c_int), ("planes_bwd", C.c_int), ("fwd_fp16", C.c_int), ("x_is_bf16", C.c_int), ("if_gamma_prior", C.c_int), ("stop_gamma_grad", C.c_int),
                 ("training", C.c_int), ("accum_chain", C.c_int), ("sigma", C.c_float), ("ln_eps", C.c_float)]
 
 
@@ -60,30 +60,31 @@ def _bytes(fn, cfg) -> int:
     return int(n)
 
 
-# precision name -> (operand planes of the forward contractions, operand planes of the gradient
-# contractions, accumulation-chain bound in 64-wide K blocks).  Measured on B200 against the
-# reference at cfg1 (tests/test_em_gpu.py, tools/precision_sweep.py): the E-step amplifies forward
-# errors by 1/sigma^2 and dec1's ReLU turns them into gradient flips, so the forward pass needs
-# more bits than the backward pass.
+# precision name -> (forward operand planes, forward planes are fp16 pairs, bf16 planes of the gradient
+# contractions, accumulation-chain bound in 64-wide K blocks).  Measured on B200 against the reference
+# (tests/test_em_gpu.py, tools/precision_sweep.py): the E-step amplifies forward errors by 1/sigma^2 and
+# dec1's ReLU turns them into gradient flips, so the forward pass needs fp32-class operands (an fp16
+# hi/lo pair = 22 mantissa bits in 3 tensor-core passes) and short accumulation chains, while the
+# gradient contractions get by with fewer bits.
 PRECISIONS = {
-    "fp32": (3, 2, 16),        # fp32-class: max grad error ~1.5e-5 at cfg1 (tolerance 1e-4)
-    "fp32_strict": (3, 3, 4),  # 6 passes everywhere, 256-element chains: ~7e-6
-    "bf16": (3, 1, 16),        # "bf16 features" mode (tolerance 1e-2): fp32-class forward, bf16 gradients
-    "bf16_fast": (1, 1, 0),    # single-pass bf16, inference grade (h ~2e-2)
+    "fp32": (2, 1, 2, 16),          # fp32-class forward, 2 bf16 planes backward        (tolerance 1e-4)
+    "fp32_strict": (2, 1, 3, 4),    # + 3 bf16 planes backward, 256-element chains
+    "bf16": (2, 1, 1, 8),           # "bf16 features" mode: fp32-class forward, bf16 gradients (1e-2)
+    "bf16_fast": (1, 0, 1, 0),      # single-pass bf16 everywhere: inference grade (h ~2e-2)
+    "fp32_bf16planes": (3, 0, 2, 16),   # the same accuracy from 3 bf16 residual planes (6 forward passes)
 }
 
 
 def precision_planes(precision):
     if isinstance(precision, (tuple, list)):
-        p = tuple(int(v) for v in precision)
-        return p if len(p) == 3 else (p[0], p[1], 4 if p[0] == 3 else 0)
+        return tuple(int(v) for v in precision)
     return PRECISIONS[precision]
 
 
 def make_config(module, B, T, x_is_bf16, training) -> EMConfig:
-    planes, planes_bwd, chain = precision_planes(module.precision)
+    planes, f16, planes_bwd, chain = precision_planes(module.precision)
     return EMConfig(B=B, K=module.k, M=module.m, D=module.input_dim, H=module.rnn_hidden_size, T=T, planes=planes,
-                    planes_bwd=planes_bwd,
+                    planes_bwd=planes_bwd, fwd_fp16=f16,
                     x_is_bf16=int(x_is_bf16), if_gamma_prior=int(module.if_gamma_prior),
                     stop_gamma_grad=int(module.stop_gamma_grad), training=int(training),
                     accum_chain=chain, sigma=float(module.e_sigma),
@@ -98,7 +99,7 @@ class _WeightCache:
         self.buf = None
 
     def get(self, cfg: EMConfig, params):
-        key = (cfg.planes, cfg.planes_bwd, cfg.accum_chain, cfg.M, cfg.D, cfg.H) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (cfg.planes, cfg.planes_bwd, cfg.fwd_fp16, cfg.accum_chain, cfg.M, cfg.D, cfg.H) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self.key:
             nbytes = _bytes(lib().vmm_em_weights_bytes, cfg)
             if self.buf is None or self.buf.numel() < nbytes or self.buf.device != params[0].device:
@@ -190,8 +191,8 @@ def em_step(module, x, state):
 # ---- head ---------------------------------------------------------------------------------------
 class HeadConfig(C.Structure):
     _fields_ = [("B", C.c_int), ("K", C.c_int), ("H", C.c_int), ("C", C.c_int), ("W", C.c_int), ("M", C.c_int),
-                ("planes", C.c_int), ("planes_bwd", C.c_int), ("accum_chain", C.c_int), ("if_sort", C.c_int),
-                ("if_pooling", C.c_int)]
+                ("planes", C.c_int), ("planes_bwd", C.c_int), ("fwd_fp16", C.c_int), ("accum_chain", C.c_int),
+                ("if_sort", C.c_int), ("if_pooling", C.c_int)]
 
 
 HEAD_PARAM_FIELDS = [("att_w", "att.0.weight"), ("att_b", "att.0.bias"), ("w0", "net.0.weight"), ("b0", "net.0.bias"),
@@ -216,9 +217,9 @@ def head_param_tensors(module):
 
 
 def make_head_config(module, B, M) -> HeadConfig:
-    planes, planes_bwd, chain = precision_planes(module.precision)
+    planes, f16, planes_bwd, chain = precision_planes(module.precision)
     return HeadConfig(B=B, K=module.k, H=module.rnn_hidden_size, C=module.nclasses, W=module.net[3].in_features, M=M,
-                      planes=planes, planes_bwd=planes_bwd, accum_chain=chain, if_sort=int(module.if_sort),
+                      planes=planes, planes_bwd=planes_bwd, fwd_fp16=f16, accum_chain=chain, if_sort=int(module.if_sort),
                       if_pooling=int(module.if_pooling))
 
 
@@ -227,7 +228,7 @@ class _HeadWeightCache:
         self.key, self.buf = None, None
 
     def get(self, cfg, params):
-        key = (cfg.planes, cfg.K, cfg.H, cfg.C, cfg.W, cfg.if_pooling) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (cfg.planes, cfg.planes_bwd, cfg.fwd_fp16, cfg.K, cfg.H, cfg.C, cfg.W, cfg.if_pooling) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self.key:
             nbytes = _bytes(lib().vmm_head_weights_bytes, cfg)
             if self.buf is None or self.buf.numel() < nbytes or self.buf.device != params[0].device:

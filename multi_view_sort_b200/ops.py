@@ -15,10 +15,14 @@ import torch
 from ._lib import GemmSeg, check, lib, planes_c, ptr, stream_ptr
 
 
-def split_planes(t: torch.Tensor, planes: int):
-    """fp32 tensor -> tuple of `planes` bf16 operand planes (successive residuals)."""
-    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and 1 <= planes <= 3
-    out = tuple(torch.empty_like(t, dtype=torch.bfloat16) for _ in range(planes))
+SEG_A_F16, SEG_B_F16, SEG_RESCALE11 = 1, 2, 4
+
+
+def split_planes(t: torch.Tensor, planes: int, fp16_pair: bool = False):
+    """fp32 tensor -> tuple of operand planes: `planes` successive bf16 residuals, or (fp16_pair) the
+    fp16 pair (hi, (v - hi) * 2^11) - the dtype of the returned tensors tells the format."""
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and 1 <= planes <= (2 if fp16_pair else 3)
+    out = tuple(torch.empty_like(t, dtype=torch.float16 if fp16_pair else torch.bfloat16) for _ in range(planes))
     pc = planes_c(out)
     check(lib().vmm_split_planes(ptr(t), C.c_longlong(t.numel()), C.byref(pc), stream_ptr()))
     return out
@@ -27,15 +31,18 @@ def split_planes(t: torch.Tensor, planes: int):
 def _segs(pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]], a_mn: bool, b_mn: bool):
     arr = (GemmSeg * len(pairs))()
     M = N = None
-    for i, (a, b) in enumerate(pairs):
-        assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
+    for i, pair in enumerate(pairs):
+        a, b = pair[0], pair[1]
+        flags = pair[2] if len(pair) > 2 else 0
+        flags |= (SEG_A_F16 if a.dtype == torch.float16 else 0) | (SEG_B_F16 if b.dtype == torch.float16 else 0)
+        assert a.dtype in (torch.bfloat16, torch.float16) and b.dtype in (torch.bfloat16, torch.float16) and a.is_cuda and b.is_cuda
         assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
         ka, m = (a.shape[0], a.shape[1]) if a_mn else (a.shape[1], a.shape[0])
         kb, n = (b.shape[0], b.shape[1]) if b_mn else (b.shape[1], b.shape[0])
         assert ka == kb, "K mismatch"
         assert M in (None, m) and N in (None, n)
         M, N = m, n
-        arr[i] = GemmSeg(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), ka)
+        arr[i] = GemmSeg(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), ka, flags)
     return arr, M, N
 
 
@@ -56,14 +63,28 @@ def gemm(pairs, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, s
 
 
 def plane_pairs(a_planes, b_planes):
-    """Error-compensated segment list: cross terms A_i B_j with i + j < max(na, nb), least significant first."""
-    order = max(len(a_planes), len(b_planes))
+    """Segment list (least significant first) for operands given as planes - mirrors make_segs() in gemm.cu."""
+    af, bf = a_planes[0].dtype == torch.float16, b_planes[0].dtype == torch.float16
     out = []
-    for tot in range(order - 1, -1, -1):
-        for i in range(len(a_planes)):
+    if not af and not bf:
+        order = max(len(a_planes), len(b_planes))
+        for tot in range(order - 1, -1, -1):
+            for i in range(len(a_planes)):
+                j = tot - i
+                if 0 <= j < len(b_planes):
+                    out.append((a_planes[i], b_planes[j]))
+        return out
+    if af and len(a_planes) > 1:
+        out.append((a_planes[1], b_planes[0]))
+    if bf and len(b_planes) > 1:
+        out.append((a_planes[0], b_planes[1]))
+    scaled = len(out)
+    na, nb = (1 if af else len(a_planes)), (1 if bf else len(b_planes))
+    for tot in range(na + nb - 2, -1, -1):
+        for i in range(na):
             j = tot - i
-            if 0 <= j < len(b_planes):
-                out.append((a_planes[i], b_planes[j]))
+            if 0 <= j < nb:
+                out.append((a_planes[i], b_planes[j], SEG_RESCALE11 if (len(out) == scaled and scaled > 0) else 0))
     return out
 
 

@@ -151,3 +151,38 @@ def test_estep_fused_forward_backward(B, K, Mv, D, zk, planes, xdt):
     assert err < {1: 6e-3, 2: 3e-5, 3: 1e-5}[planes], f"dpred rel err {err:.3e}"
     # fused dec3-bias gradient: exact fp32 column sums, accumulated into the caller's buffer
     assert _relmax(d_b3 - 0.5, dref.reshape(rows, D).sum(0)) < tol
+
+
+def test_gemm_fp16_pair_planes():
+    """fp16 hi/lo' pair (lo' = lo * 2^11) with the accumulator rescale (tcgen05.mma scale_input_d = 11):
+    3 passes give ~22 mantissa bits.  (kind::f16 rejects mixed bf16 x fp16 operands - illegal
+    instruction, measured - so gradient contractions use bf16 planes on both sides.)"""
+    from multi_view_sort_b200 import ops
+    M, N, K = 384, 640, 2048
+    A, B = _rand((M, K), 41), _rand((N, K), 42, 0.02)
+    ref = A.double() @ B.double().t()
+    errs = {}
+    out = ops.gemm(ops.plane_pairs(ops.split_planes(A, 1, True), ops.split_planes(B, 1, True)))
+    errs["f16x1"] = _relmax(out, ref)
+    pairs = ops.plane_pairs(ops.split_planes(A, 2, True), ops.split_planes(B, 2, True))
+    assert len(pairs) == 3
+    chk = ops.gemm(pairs, check_kernel=True)
+    errs["f16pair_check_kernel"] = _relmax(chk, ref)
+    for chain in (0, 4):
+        out = ops.gemm(pairs, chain=chain)
+        errs[f"f16pair_chain{chain}"] = _relmax(out, ref)
+    # weight-gradient layout (both MN-major), accumulate + split-K
+    At, Bt = A.t().contiguous(), B.t().contiguous()
+    acc = torch.zeros(M, N, device="cuda")
+    ops.gemm(ops.plane_pairs(ops.split_planes(At, 2, True), ops.split_planes(Bt, 2, True)), True, True, out=acc,
+             accumulate=True, splits=4, chain=4)
+    errs["mn_f16pair"] = _relmax(acc, ref)
+    # an fp16 pair against a single exact fp16 plane (bf16 features up-cast to fp16)
+    Ab = A.bfloat16().float()
+    out = ops.gemm(ops.plane_pairs(ops.split_planes(Ab, 1, True), ops.split_planes(B, 2, True)), chain=4)
+    errs["f16x1_f16pair"] = _relmax(out, Ab.double() @ B.double().t())
+    torch.cuda.synchronize()
+    print(errs)
+    assert errs["f16x1"] < 2e-3
+    assert errs["f16pair_check_kernel"] < 2e-6, "reference semantics of the fp16 pair are wrong"
+    assert errs["f16pair_chain4"] < 2e-6 and errs["mn_f16pair"] < 2e-6 and errs["f16x1_f16pair"] < 2e-6

@@ -15,7 +15,7 @@ for name in ["cfg1_b8_k3_m12_t10", "prior0_b5_k2_m12_t3"]:
     nem, _ = seeded_models(cfg)
     x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
     ref, pn = _oracle(cfg, nem, x, torch.float32)
-    for combo in [(3, 3, 4), (3, 2, 4), (3, 2, 8), (3, 2, 16), (2, 2, 0), (2, 2, 8), (2, 2, 4), (2, 1, 8), (1, 1, 0), (1, 1, 8)]:
+    for combo in [(2, 1, 3, 4), (2, 1, 2, 16), (2, 1, 1, 16), (2, 1, 2, 0), (3, 0, 2, 16), (3, 0, 1, 16), (1, 1, 1, 16), (1, 0, 1, 0)]:
         for p in nem.parameters():
             p.grad = None
         res, nem_c = _cuda(cfg, nem, x, combo, torch.float32)
