@@ -24,10 +24,11 @@ struct Dims {
   int B, K, M, D, H, T, planes, pb;   // pb: operand planes of the gradient contractions
   int chain;                          // accumulation chain length in k-blocks (0 = unlimited)
   int f16;                            // forward operands are fp16 pairs
+  int chain_b;                        // chain bound of the gradient contractions (single bf16 plane: none needed)
   long long R, RM, BM, ZW;   // B*K, B*K*M, B*M, 1024*M
   int nblk;
   explicit Dims(const vmm_em_config& c)
-      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16), R(1ll * c.B * c.K),
+      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16), chain_b(c.planes_bwd >= 2 ? c.accum_chain : 0), R(1ll * c.B * c.K),
         RM(1ll * c.B * c.K * c.M), BM(1ll * c.B * c.M), ZW(1ll * E1 * c.M), nblk(2 * ((c.D + 255) / 256)) {}
 };
 
@@ -373,12 +374,12 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     VMM_TRY(estep_backward(static_cast<int>(d.RM), d.D, E1, cur.z.f, w.w3.f, p->dec3_b, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
                            sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st));
     // --- dec3: weight gradient; dz = dpred W3 (+ dG1_{t+1} W13, the path through the next residual)
-    VMM_TRY(linear_wgrad(sc.dpred, cur.z.b, d.RM, d.D, E1, g->dec3_w, d.chain, st));
+    VMM_TRY(linear_wgrad(sc.dpred, cur.z.b, d.RM, d.D, E1, g->dec3_w, d.chain_b, st));
     {
       vmm_gemm_seg s[18];
       int ns = make_segs(s, sc.dpred, d.D, w.w3.b, E1, d.D);
       if (!last) ns += make_segs(s + ns, sc.dg1, E1, w.w13.b, E1, E1);
-      VMM_TRY(gemm_bf16(static_cast<int>(d.RM), E1, ns, s, false, true, sc.dz, E1, nullptr, false, 1, d.chain, st));
+      VMM_TRY(gemm_bf16(static_cast<int>(d.RM), E1, ns, s, false, true, sc.dz, E1, nullptr, false, 1, d.chain_b, st));
     }
     // --- dec2: LayerNorm(1024*M) backward, dgrad, wgrad
     {
@@ -388,8 +389,8 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_NONE, ln, cur.mean5, cur.rstd5, sc.c1, sc.c2, sc.dz, d.ZW, g->dec2_ln_g,
                                g->dec2_ln_b, g->dec2_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv5, w.w5.b, d.R, static_cast<int>(d.ZW), E2, sc.du, false, d.chain, st));
-    VMM_TRY(linear_wgrad(sc.dv5, cur.u.b, d.R, static_cast<int>(d.ZW), E2, g->dec2_w, d.chain, st));
+    VMM_TRY(linear_dgrad(sc.dv5, w.w5.b, d.R, static_cast<int>(d.ZW), E2, sc.du, false, d.chain_b, st));
+    VMM_TRY(linear_wgrad(sc.dv5, cur.u.b, d.R, static_cast<int>(d.ZW), E2, g->dec2_w, d.chain_b, st));
     // --- dec1
     {
       LnDesc ln = ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps);
@@ -398,16 +399,16 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.c1, sc.c2, sc.du, E2, g->dec1_ln_g,
                                g->dec1_ln_b, g->dec1_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv4, w.w4.b, d.R, E2, d.H, dh, true, d.chain, st));          // dh += dG4 W4
-    VMM_TRY(linear_wgrad(sc.dv4, cur.hp.b, d.R, E2, d.H, g->dec1_w, d.chain, st));
+    VMM_TRY(linear_dgrad(sc.dv4, w.w4.b, d.R, E2, d.H, dh, true, d.chain_b, st));          // dh += dG4 W4
+    VMM_TRY(linear_wgrad(sc.dv4, cur.hp.b, d.R, E2, d.H, g->dec1_w, d.chain_b, st));
     // --- GRU
     VMM_TRY(gru_backward(R, d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, t > 0 ? prev.h : ws.h0, dh, sc.dgi, sc.dgh,
                          dh_prev, g->gru_b_ih, g->gru_b_hh, st));
-    VMM_TRY(linear_dgrad(sc.dgi, w.wih.b, d.R, 3 * d.H, E2, sc.de, false, d.chain, st));
-    VMM_TRY(linear_wgrad(sc.dgi, cur.e.b, d.R, 3 * d.H, E2, g->gru_w_ih, d.chain, st));
+    VMM_TRY(linear_dgrad(sc.dgi, w.wih.b, d.R, 3 * d.H, E2, sc.de, false, d.chain_b, st));
+    VMM_TRY(linear_wgrad(sc.dgi, cur.e.b, d.R, 3 * d.H, E2, g->gru_w_ih, d.chain_b, st));
     if (t > 0) {
-      VMM_TRY(linear_dgrad(sc.dgh, w.whh.b, d.R, 3 * d.H, d.H, dh_prev, true, d.chain, st));   // dh_{t-1} += dgh Whh
-      VMM_TRY(linear_wgrad(sc.dgh, prev.hp.b, d.R, 3 * d.H, d.H, g->gru_w_hh, d.chain, st));
+      VMM_TRY(linear_dgrad(sc.dgh, w.whh.b, d.R, 3 * d.H, d.H, dh_prev, true, d.chain_b, st));   // dh_{t-1} += dgh Whh
+      VMM_TRY(linear_wgrad(sc.dgh, prev.hp.b, d.R, 3 * d.H, d.H, g->gru_w_hh, d.chain_b, st));
     }
     {
       float* tmp = dh;
@@ -422,8 +423,8 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.c1, sc.c2, sc.de, E2, g->enc2_ln_g,
                                g->enc2_ln_b, g->enc2_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv2, w.w2.b, d.R, E2, d.ZW, sc.da, false, d.chain, st));
-    VMM_TRY(linear_wgrad(sc.dv2, cur.a.b, d.R, E2, d.ZW, g->enc2_w, d.chain, st));
+    VMM_TRY(linear_dgrad(sc.dv2, w.w2.b, d.R, E2, d.ZW, sc.da, false, d.chain_b, st));
+    VMM_TRY(linear_wgrad(sc.dv2, cur.a.b, d.R, E2, d.ZW, g->enc2_w, d.chain_b, st));
     // --- enc1 + residual: dgamma_{t-1}, dXW1, dG1 (-> dz_{t-1} and dW13)
     {
       LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps);
@@ -437,20 +438,20 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_TRY(ln_backward_cols(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.c1, sc.c2, sc.da, E1, g->enc1_ln_g,
                                g->enc1_ln_b, g->enc1_b, t > 0 ? sc.dw1b3 : nullptr, st));
     }
-    if (t > 0) VMM_TRY(linear_wgrad(sc.dg1, prev.z.b, d.RM, E1, E1, sc.dw13, d.chain, st));
+    if (t > 0) VMM_TRY(linear_wgrad(sc.dg1, prev.z.b, d.RM, E1, E1, sc.dw13, d.chain_b, st));
   }
   // --- parameters behind the fold: XW1 = x W1^T, W13 = W1 W3, w1b3 = W1 b3
   VMM_TRY(split_planes(sc.dxw1, d.BM * E1, sc.dxw1p, st));
-  VMM_TRY(linear_wgrad(sc.dxw1p, xp.b, d.BM, E1, d.D, g->enc1_w, d.chain, st));                       // dW1 += dXW1^T x
+  VMM_TRY(linear_wgrad(sc.dxw1p, xp.b, d.BM, E1, d.D, g->enc1_w, d.chain_b, st));                       // dW1 += dXW1^T x
   VMM_TRY(split_planes(sc.dw13, 1ll * E1 * E1, sc.dw13p, st));
   {
     vmm_gemm_seg s[9];
     // dW1[i, d] += sum_j dW13[i, j] W3[d, j]
     int ns = make_segs(s, sc.dw13p, E1, w.w3.b, E1, E1);
-    VMM_TRY(gemm_bf16(E1, d.D, ns, s, false, false, g->enc1_w, d.D, nullptr, true, 0, d.chain, st));
+    VMM_TRY(gemm_bf16(E1, d.D, ns, s, false, false, g->enc1_w, d.D, nullptr, true, 0, d.chain_b, st));
     // dW3[d, j] += sum_i W1[i, d] dW13[i, j]
     ns = make_segs(s, w.w1.b, d.D, sc.dw13p, E1, E1);
-    VMM_TRY(gemm_bf16(d.D, E1, ns, s, true, true, g->dec3_w, E1, nullptr, true, 0, d.chain, st));
+    VMM_TRY(gemm_bf16(d.D, E1, ns, s, true, true, g->dec3_w, E1, nullptr, true, 0, d.chain_b, st));
   }
   VMM_TRY(rank1_update(E1, d.D, sc.dw1b3, p->dec3_b, g->enc1_w, st));                       // dW1 += dw1b3 b3^T
   VMM_TRY(gemv_cols_acc(E1, d.D, p->enc1_w, sc.dw1b3, g->dec3_b, st));                      // db3 += W1^T dw1b3

@@ -173,6 +173,20 @@ __device__ __forceinline__ void x_stage(const XRegs<XT>& xr, float4* st, int lan
 template <int EPI>
 __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint32_t (&v)[32], float4* st, int row0,
                                                 int col0, int lane, bool add_to_c) {
+  // For the read-modify-write chains, issue all eight loads of the running sum before anything
+  // depends on them (one exposed L2 round trip per chunk instead of eight).
+  float4 old[8];
+  const bool rmw = (EPI == EPI_STORE) && add_to_c && p.vec_ok;
+  if (rmw) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = j * 4 + (lane >> 3), c4 = lane & 7;
+      const int grow = row0 + r, gcol = col0 + c4 * 4;
+      old[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grow < p.M && gcol + 3 < p.N)
+        old[j] = *reinterpret_cast<const float4*>(p.C + static_cast<long long>(grow) * p.ldc + gcol);
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     st[st_slot(lane, j)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -188,8 +202,7 @@ __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint3
       if (p.vec_ok && gcol + 3 < p.N) {
         if constexpr (EPI == EPI_STORE) {
           if (add_to_c) {
-            const float4 o = *reinterpret_cast<const float4*>(dst);
-            val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w;
+            val.x += old[j].x; val.y += old[j].y; val.z += old[j].z; val.w += old[j].w;
           } else if (p.bias) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
             val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;

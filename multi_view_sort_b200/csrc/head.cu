@@ -13,12 +13,12 @@ namespace vmm {
 namespace {
 
 struct HDims {
-  int B, K, H, C, W, M, planes, pb, chain, f16;
+  int B, K, H, C, W, M, planes, pb, chain, f16, chain_b;
   int FW;          // classifier input width: K*H (concat) or H (max-pool)
   int Cp;          // class count padded to the 8-element pitch TMA needs
   long long R;
   explicit HDims(const vmm_head_config& c)
-      : B(c.B), K(c.K), H(c.H), C(c.C), W(c.W), M(c.M), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16),
+      : B(c.B), K(c.K), H(c.H), C(c.C), W(c.W), M(c.M), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16), chain_b(c.planes_bwd >= 2 ? c.accum_chain : 0),
         FW(c.if_pooling ? c.H : c.K * c.H), Cp((c.C + 7) / 8 * 8), R(1ll * c.B * c.K) {}
 };
 
@@ -370,8 +370,8 @@ int head_backward(const vmm_head_config* c, const vmm_head_params* p, const void
     pad_planes_kernel<<<blocks_for(1ll * d.B * d.Cp), 256, 0, st>>>(d.B, d.C, d.Cp, d_logits, sc.dl);
     VMM_LAUNCHED();
     VMM_TRY(colsum_acc(d.B, d.C, d_logits, d.C, g->b6, st));
-    VMM_TRY(lin_wgrad(sc.dl, d.Cp, ws.t3r.b, d.B, d.C, d.W, g->w6, d.chain, st));
-    VMM_TRY(lin_dgrad(sc.dl, d.Cp, w.w6.b, d.B, d.C, d.W, sc.dt3f, d.chain, st));
+    VMM_TRY(lin_wgrad(sc.dl, d.Cp, ws.t3r.b, d.B, d.C, d.W, g->w6, d.chain_b, st));
+    VMM_TRY(lin_dgrad(sc.dl, d.Cp, w.w6.b, d.B, d.C, d.W, sc.dt3f, d.chain_b, st));
     VMM_TRY(act_backward(ACT_RELU, BW, ws.t3, sc.dt3f, st));
     if (d_descriptor) {
       add_kernel<<<blocks_for(BW), 256, 0, st>>>(BW, d_descriptor, sc.dt3f);
@@ -382,13 +382,13 @@ int head_backward(const vmm_head_config* c, const vmm_head_params* p, const void
   }
   VMM_TRY(split_planes(sc.dt3f, BW, sc.dt3, st));
   VMM_TRY(colsum_acc(d.B, d.W, sc.dt3f, d.W, g->b3, st));
-  VMM_TRY(lin_wgrad(sc.dt3, d.W, ws.t1.b, d.B, d.W, d.W, g->w3, d.chain, st));
-  VMM_TRY(lin_dgrad(sc.dt3, d.W, w.w3.b, d.B, d.W, d.W, sc.dt0f, d.chain, st));
+  VMM_TRY(lin_wgrad(sc.dt3, d.W, ws.t1.b, d.B, d.W, d.W, g->w3, d.chain_b, st));
+  VMM_TRY(lin_dgrad(sc.dt3, d.W, w.w3.b, d.B, d.W, d.W, sc.dt0f, d.chain_b, st));
   VMM_TRY(act_backward(ACT_RELU, BW, ws.t0, sc.dt0f, st));
   VMM_TRY(split_planes(sc.dt0f, BW, sc.dt0, st));
   VMM_TRY(colsum_acc(d.B, d.W, sc.dt0f, d.W, g->b0, st));
-  VMM_TRY(lin_wgrad(sc.dt0, d.W, ws.feat.b, d.B, d.W, d.FW, g->w0, d.chain, st));
-  VMM_TRY(lin_dgrad(sc.dt0, d.W, w.w0.b, d.B, d.W, d.FW, sc.dfeat, d.chain, st));
+  VMM_TRY(lin_wgrad(sc.dt0, d.W, ws.feat.b, d.B, d.W, d.FW, g->w0, d.chain_b, st));
+  VMM_TRY(lin_dgrad(sc.dt0, d.W, w.w0.b, d.B, d.W, d.FW, sc.dfeat, d.chain_b, st));
   head_score_backward_kernel<<<d.B, 256, 0, st>>>(d.K, d.H, c->if_pooling, h, p->att_w, ws.score, ws.order, ws.argmax,
                                                   sc.dfeat, d_h, sc.ds_pre);
   VMM_LAUNCHED();

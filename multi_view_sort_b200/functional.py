@@ -69,7 +69,7 @@ def _bytes(fn, cfg) -> int:
 PRECISIONS = {
     "fp32": (2, 1, 2, 16),          # fp32-class forward, 2 bf16 planes backward        (tolerance 1e-4)
     "fp32_strict": (2, 1, 3, 4),    # + 3 bf16 planes backward, 256-element chains
-    "bf16": (2, 1, 1, 8),           # "bf16 features" mode: fp32-class forward, bf16 gradients (1e-2)
+    "bf16": (2, 1, 1, 16),          # "bf16 features" mode: fp32-class forward, bf16 gradients (1e-2)
     "bf16_fast": (1, 0, 1, 0),      # single-pass bf16 everywhere: inference grade (h ~2e-2)
     "fp32_bf16planes": (3, 0, 2, 16),   # the same accuracy from 3 bf16 residual planes (6 forward passes)
 }
