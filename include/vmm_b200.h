@@ -211,6 +211,17 @@ VMM_API int vmm_em_backward(const vmm_em_config* cfg, const vmm_em_params* param
                             const float* d_h, const float* d_gamma, const float* d_loss, const vmm_em_grads* grads,
                             void* stream);
 
+/* Step-level API: ONE EM iteration from an arbitrary state - exactly NEM.forward(x, (h, pred, gamma))
+ * of the reference (train_nem.py:272-294), for callers that drive the loop themselves
+ * (tools/Trainer.py:322-336 validation, :433-446 descriptor export).  It materialises pred
+ * [B,K,M,D] (the reference returns it).  Forward only; workspace sized with training = 0,
+ * scratch with vmm_em_step_scratch_bytes. */
+VMM_API long long vmm_em_step_scratch_bytes(const vmm_em_config* cfg);
+VMM_API int vmm_em_step_forward(const vmm_em_config* cfg, const vmm_em_params* params, const void* weights,
+                                const void* x, const float* h_in, const float* pred_in, const float* gamma_in,
+                                void* workspace, void* scratch, float* h_out, float* pred_out, float* gamma_out,
+                                void* stream);
+
 /* Address of a named intermediate of iteration `iter` inside `workspace` (for stage-level
  * parity tests and debugging); returns NULL for an unknown name.  Names: "xw1", "g1", "a_hi",
  * "g2", "e_hi", "gi", "gh", "h", "h_hi", "g4", "u_hi", "g5", "z_hi", "z_lo", "gamma", "row_sq". */

@@ -327,6 +327,66 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
   return 0;
 }
 
+// ============================================================================================
+// Step-level API: ONE EM iteration from an arbitrary state, exactly NEM.forward(x, (h, pred, gamma))
+// (train_nem.py:272-294).  Unlike the fused loop it must materialise `pred` (the reference returns it),
+// so enc1 runs on the explicit residual instead of the W1*W3 fold.  Forward only.
+struct StepScratch {
+  Op masked, hin;
+  float* part_e;
+  long long bytes;
+  StepScratch(const vmm_em_config& c, void* base) {
+    Dims d(c);
+    Bump b(base);
+    masked = b.op(d.RM * d.D, d.planes, d.f16, 1);
+    hin = b.op(d.R * d.H, d.planes, d.f16, 1);
+    part_e = b.take<float>(d.RM * d.nblk);
+    bytes = b.off + 256;
+  }
+};
+
+int em_step_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weights, const void* x, const float* h_in,
+                    const float* pred_in, const float* gamma_in, void* workspace, void* scratch, float* h_out,
+                    float* pred_out, float* gamma_out, cudaStream_t st) {
+  VMM_TRY(check_cfg(c));
+  VMM_REQUIRE(p && weights && x && h_in && pred_in && gamma_in && workspace && scratch && h_out && pred_out && gamma_out,
+              "null argument");
+  Dims d(*c);
+  Weights w(*c, const_cast<void*>(weights));
+  vmm_em_config c1 = *c;
+  c1.training = 0;
+  Workspace ws(c1, workspace);
+  StepScratch sc(*c, scratch);
+  const IterBufs cur = ws.slot(0);
+  const float eps = c->ln_eps;
+  VMM_TRY(residual_op(d.RM, d.D, d.K * d.M, d.M, x, c->x_is_bf16, pred_in, gamma_in, sc.masked, st));
+  VMM_TRY(linear_fwd(sc.masked.f, w.w1.f, d.RM, E1, d.D, cur.g1, d.chain, st));
+  VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.RM, E1, cur.g1, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps), cur.a, cur.mean1,
+                     cur.rstd1, st));
+  VMM_TRY(linear_fwd(cur.a.f, w.w2.f, d.R, E2, d.ZW, cur.g2, d.chain, st));
+  VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps), cur.e, cur.mean2,
+                     cur.rstd2, st));
+  VMM_TRY(linear_fwd(cur.e.f, w.wih.f, d.R, 3 * d.H, E2, cur.gi, d.chain, st));
+  VMM_TRY(split_op(h_in, d.R * d.H, sc.hin, st));
+  VMM_TRY(linear_fwd(sc.hin.f, w.whh.f, d.R, 3 * d.H, d.H, cur.gh, d.chain, st));
+  VMM_TRY(gru_forward(static_cast<int>(d.R), d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, h_in, h_out, cur.hp, st));
+  VMM_TRY(linear_fwd(cur.hp.f, w.w4.f, d.R, E2, d.H, cur.g4, d.chain, st));
+  VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps), cur.u, cur.mean4,
+                     cur.rstd4, st));
+  VMM_TRY(linear_fwd(cur.u.f, w.w5.f, d.R, static_cast<int>(d.ZW), E2, cur.g5, d.chain, st));
+  VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps), cur.z, cur.mean5,
+                     cur.rstd5, st));
+  {
+    vmm_gemm_seg s[9];
+    const int ns = make_segs(s, cur.z.f, E1, w.w3.f, E1, E1);
+    VMM_TRY(gemm_bf16(static_cast<int>(d.RM), d.D, ns, s, false, false, pred_out, d.D, p->dec3_b, false, 1, d.chain, st));
+  }
+  VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, cur.z.f, w.w3.f, p->dec3_b, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
+                        sc.part_e, nullptr, nullptr, st));
+  VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, nullptr, nullptr, gamma_out, cur.inv_s, nullptr, nullptr, st));
+  return 0;
+}
+
 int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weights, const void* x, const float* gamma0,
                 const float* prior, const void* workspace, void* scratch, const float* d_h, const float* d_gamma,
                 const float* d_loss, const vmm_em_grads* g, cudaStream_t st) {
@@ -489,6 +549,16 @@ int vmm_em_backward(const vmm_em_config* cfg, const vmm_em_params* params, const
                     const float* d_gamma, const float* d_loss, const vmm_em_grads* grads, void* stream) {
   return vmm::em_backward(cfg, params, weights, x, gamma0, prior, workspace, scratch, d_h, d_gamma, d_loss, grads,
                           static_cast<cudaStream_t>(stream));
+}
+long long vmm_em_step_scratch_bytes(const vmm_em_config* cfg) {
+  if (vmm::check_cfg(cfg) != 0) return VMM_E_INVALID;
+  return vmm::StepScratch(*cfg, nullptr).bytes;
+}
+int vmm_em_step_forward(const vmm_em_config* cfg, const vmm_em_params* params, const void* weights, const void* x,
+                        const float* h_in, const float* pred_in, const float* gamma_in, void* workspace, void* scratch,
+                        float* h_out, float* pred_out, float* gamma_out, void* stream) {
+  return vmm::em_step_forward(cfg, params, weights, x, h_in, pred_in, gamma_in, workspace, scratch, h_out, pred_out,
+                              gamma_out, static_cast<cudaStream_t>(stream));
 }
 const void* vmm_em_workspace_ptr(const vmm_em_config* cfg, const void* workspace, const char* name, int iter) {
   if (vmm::check_cfg(cfg) != 0 || !name || iter < 0 || iter >= cfg->T) return nullptr;

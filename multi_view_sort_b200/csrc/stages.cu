@@ -627,6 +627,31 @@ __global__ void __launch_bounds__(256) act_backward_kernel(int act, long long n,
     grad[i] *= act_grad(act, pre[i]);
 }
 
+__global__ void __launch_bounds__(256) residual_op_kernel(long long rows, int D, int km, int mv,
+                                                          const float* __restrict__ xf,
+                                                          const __nv_bfloat16* __restrict__ xb,
+                                                          const float* __restrict__ pred,
+                                                          const float* __restrict__ gamma, Op out) {
+  const long long n4 = rows * (D / 4);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const long long r = i / (D / 4);
+    const int c = static_cast<int>(i % (D / 4)) * 4;
+    const long long xrow = (r / km) * mv + r % mv;
+    float4 xv;
+    if (xf) {
+      xv = ld4(xf + xrow * D + c);
+    } else {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(xb + xrow * D + c));
+      xv = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+    }
+    const float4 pv = ld4(pred + r * D + c);
+    const float g = gamma[r];
+    store_op4(out, r * D + c, make_float4((xv.x - pv.x) * g, (xv.y - pv.y) * g, (xv.z - pv.z) * g, (xv.w - pv.w) * g));
+  }
+}
+
 int pick_rows_per_block(int rows, int col_blocks) {
   // aim for ~8 blocks per SM in total
   const int target = device_sm_count() * 8;
@@ -765,6 +790,19 @@ int loss_backward(int B, int K, int Mv, int D, int if_gamma_prior, int stop_gamm
               "loss_backward: null argument");
   loss_backward_kernel<<<ceil_div(B * K, 128), 128, 0, stream>>>(B, K, Mv, D, if_gamma_prior, stop_gamma_grad, gamma,
                                                                  prior ? prior : gamma, row_sq, row_pp, g3, dgamma, beta, kappa);
+  VMM_LAUNCHED();
+  return 0;
+}
+
+int residual_op(long long rows, int D, int km, int mv, const void* x, int x_is_bf16, const float* pred,
+                const float* gamma, const Op& out, cudaStream_t stream) {
+  VMM_REQUIRE(rows > 0 && D % 4 == 0 && x && pred && gamma && out.f.n >= 1, "residual_op: bad argument");
+  long long blocks = (rows * (D / 4) + 255) / 256;
+  const long long cap = static_cast<long long>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  residual_op_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      rows, D, km, mv, x_is_bf16 ? nullptr : static_cast<const float*>(x),
+      x_is_bf16 ? static_cast<const __nv_bfloat16*>(x) : nullptr, pred, gamma, out);
   VMM_LAUNCHED();
   return 0;
 }

@@ -78,6 +78,11 @@ int loss_backward(int B, int K, int Mv, int D, int if_gamma_prior, int stop_gamm
                   const float* prior, const float* row_sq, const float* row_pp, const float* g3, float* dgamma,
                   float* beta, float* kappa, cudaStream_t stream);
 
+// Step-level API: operand planes of the responsibility-weighted residual (x - pred) * gamma
+// (train_nem.py:280-284).  x: [B*Mv, D] float or bf16; pred: [rows, D]; gamma: [rows].
+int residual_op(long long rows, int D, int km, int mv, const void* x, int x_is_bf16, const float* pred,
+                const float* gamma, const Op& out, cudaStream_t stream);
+
 // Small dense helpers on fp32 parameters.
 int gemv_rows(int n, int k, const float* W, const float* v, float* out, cudaStream_t stream);            // out[i] = W[i,:].v
 int rank1_update(int n, int k, const float* u, const float* v, float* W, cudaStream_t stream);            // W[i,j] += u[i] v[j]

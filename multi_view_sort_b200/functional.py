@@ -185,7 +185,41 @@ def run_em(module, x: torch.Tensor, iters: int, gamma0: Optional[torch.Tensor] =
 
 
 def em_step(module, x, state):
-    raise NotImplementedError("step-level NEM.forward: use NEM.run_em (fused path)")
+    """NEM.forward(x, (h, pred, gamma)) -> (h', pred', gamma'): one EM iteration from an arbitrary state
+    (train_nem.py:272-294).  Forward only (the reference's validation / export loops run it under
+    no_grad); training goes through run_em, whose backward is hand-written."""
+    h, pred, gamma = state
+    if torch.is_grad_enabled() and (h.requires_grad or pred.requires_grad or gamma.requires_grad
+                                    or any(p.requires_grad for p in em_param_tensors(module))):
+        raise NotImplementedError(
+            "the step-level NEM.forward has no backward in this library: train with NEM.run_em(x) (all "
+            "iterations + loss in one autograd node) or call forward under torch.no_grad()")
+    if not x.is_cuda:
+        raise RuntimeError("multi_view_sort_b200 has no CPU path: x must be a CUDA tensor")
+    B = x.shape[0]
+    K, M, D, H = module.k, module.m, module.input_dim, module.rnn_hidden_size
+    xx = x.reshape(B, M, D)
+    if xx.dtype not in (torch.float32, torch.bfloat16):
+        xx = xx.float()
+    xx = xx.contiguous()
+    dev = xx.device
+    params = [p.detach() for p in em_param_tensors(module)]
+    cfg = make_config(module, B, 1, xx.dtype == torch.bfloat16, False)
+    with torch.cuda.device(dev):
+        weights = _weight_cache(module).get(cfg, params)
+        ws = torch.empty(_bytes(lib().vmm_em_workspace_bytes, cfg), dtype=torch.uint8, device=dev)
+        scratch = torch.empty(_bytes(lib().vmm_em_step_scratch_bytes, cfg), dtype=torch.uint8, device=dev)
+        h_in = h.detach().to(dev, torch.float32).reshape(B * K, H).contiguous()
+        pred_in = pred.detach().to(dev, torch.float32).reshape(B * K * M, D).contiguous()
+        gamma_in = gamma.detach().to(dev, torch.float32).reshape(B * K * M).contiguous()
+        h_out = torch.empty(B * K, H, device=dev)
+        pred_out = torch.empty(B, K, M, D, device=dev)
+        gamma_out = torch.empty(B, K, M, 1, device=dev)
+        pp = _pointers(params)
+        check(lib().vmm_em_step_forward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(xx), ptr(h_in), ptr(pred_in),
+                                        ptr(gamma_in), ptr(ws), ptr(scratch), ptr(h_out), ptr(pred_out), ptr(gamma_out),
+                                        stream_ptr()))
+    return h_out, pred_out, gamma_out
 
 
 # ---- head ---------------------------------------------------------------------------------------

@@ -282,3 +282,27 @@ def test_cfg3_80_views_matches_reference_golden():
             worst[prefix + n] = max(abs(mine[1] - g[1]) / g[1], float(abs(mine[3:] - g[3:]).max() / g[1]))
     bad = {k: v for k, v in worst.items() if not v < (5e-4 if k.endswith("att.0.bias") else 1e-4)}
     assert not bad, bad
+
+
+def test_step_level_forward_matches_oracle_iterations():
+    """The reference's own driving pattern (tools/Trainer.py:304-336): init_state, then T x
+    nem(input, state) under no_grad - every intermediate state against the oracle's."""
+    _, cfg = load_golden("prior0_b5_k2_m12_t3")
+    nem, _ = seeded_models(cfg)
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    pn = params_of(nem, requires_grad=False)
+    with torch.no_grad():
+        ref = O.run_em(pn, x, cfg["K"], cfg["T"], cfg["sigma"], keep_all=True)["hist"]
+    nem = nem.cuda().eval()
+    xc = x.cuda()
+    with torch.no_grad():
+        init = nem.init_state(xc.shape, xc)
+        state = (init[0], init[1], init[2])
+        for t in range(cfg["T"]):
+            state = nem(xc.unsqueeze(1), state)
+            h, pred, gamma = state
+            assert rel_err(h, ref[t][0]) < 1e-4, t
+            assert rel_err(pred, ref[t][1]) < 1e-4, t
+            assert rel_err(gamma, ref[t][2]) < 1e-4, t
+    with pytest.raises(NotImplementedError):
+        nem(xc.unsqueeze(1), (init[0], init[1], init[2]))     # grads enabled: directs the caller to run_em
