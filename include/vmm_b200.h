@@ -161,6 +161,8 @@ typedef struct vmm_em_config {
   int accum_chain;     /* chain_kblocks of every contraction (see vmm_gemm_bf16); 0 = unlimited */
   float sigma;         /* e_sigma (train_nem.py:150)                                            */
   float ln_eps;        /* nn.LayerNorm eps, 1e-5                                                */
+  float dropout_p;     /* train-mode Dropout after enc1/enc2/dec1 (train_nem.py:172,175,181); 0 = eval */
+  unsigned long long dropout_seed; /* masks are a pure function of (seed, stage, iteration, element)    */
 } vmm_em_config;
 
 /* fp32 parameters in the reference's own state_dict layout (torch Linear [out, in]; GRU gate
@@ -237,6 +239,8 @@ typedef struct vmm_head_config {
   int planes, planes_bwd, fwd_fp16, accum_chain;
   int if_sort;          /* 0 unsorted concat, 1 sort by score, 2 sort by responsibility spread    */
   int if_pooling;       /* 1: max over the K latent views instead of concat                       */
+  float dropout_p;      /* train-mode Dropout after the two hidden ReLUs (VGG classifier); 0 = eval */
+  unsigned long long dropout_seed;
 } vmm_head_config;
 
 /* att.0.{weight,bias}, net.0.*, net.3.*, net.6.* of the reference's state_dict (train_nem.py:310,326). */

@@ -182,6 +182,7 @@ int check_cfg(const vmm_em_config* c) {
   VMM_REQUIRE(c->if_gamma_prior >= 0 && c->if_gamma_prior <= 2, "if_gamma_prior must be 0, 1 or 2");
   VMM_REQUIRE(c->sigma > 0.f && c->ln_eps > 0.f, "sigma and ln_eps must be positive");
   VMM_REQUIRE(c->accum_chain >= 0, "accum_chain must be >= 0");
+  VMM_REQUIRE(c->dropout_p >= 0.f && c->dropout_p < 1.f, "dropout_p must be in [0, 1)");
   VMM_REQUIRE(1ll * c->B * c->K * c->M < (1ll << 31) / 2, "too many rows for 32-bit indexing; split the batch");
   return 0;
 }
@@ -208,8 +209,11 @@ int linear_wgrad(const Planes& dy, const Planes& x, long long rows, int n, long 
   return gemm_bf16(n, static_cast<int>(k), ns, s, true, true, dw, k, nullptr, true, 0, chain, st);
 }
 
+// stage ids for the dropout stream
+enum { ST_ENC1 = 1, ST_ENC2 = 2, ST_DEC1 = 3, ST_DEC2 = 4 };
+
 LnDesc ln_desc(long long rows, long long width, const float* C, const float* bias, const float* g, const float* b,
-               float eps) {
+               float eps, const vmm_em_config* c = nullptr, int stage = 0, int iter = 0) {
   LnDesc d;
   memset(&d, 0, sizeof(d));
   d.rows = static_cast<int>(rows);
@@ -220,6 +224,10 @@ LnDesc ln_desc(long long rows, long long width, const float* C, const float* bia
   d.ln_g = g;
   d.ln_b = b;
   d.eps = eps;
+  if (c && c->dropout_p > 0.f && stage != ST_DEC2) {      // dec2 has no Dropout (train_nem.py:183)
+    d.drop_p = c->dropout_p;
+    d.drop_seed = c->dropout_seed + (static_cast<unsigned long long>(stage) << 56) + (static_cast<unsigned long long>(iter) << 40);
+  }
   return d;
 }
 
@@ -284,7 +292,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
     // --- enc1 on the responsibility-weighted residual (train_nem.py:280-284, 226)
     if (t > 0) VMM_TRY(linear_fwd(prev.z.f, w.w13.f, d.RM, E1, E1, cur.g1, d.chain, st));
     {
-      LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps);
+      LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps, c, ST_ENC1, t);
       ln.xw1 = ws.xw1;
       ln.w1b3 = w.w1b3;
       ln.gamma = gam_prev;
@@ -294,7 +302,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
     }
     // --- enc2 (train_nem.py:228-229)
     VMM_TRY(linear_fwd(cur.a.f, w.w2.f, d.R, E2, d.ZW, cur.g2, d.chain, st));
-    VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps), cur.e,
+    VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps, c, ST_ENC2, t), cur.e,
                        cur.mean2, cur.rstd2, st));
     // --- GRU (train_nem.py:232)
     VMM_TRY(linear_fwd(cur.e.f, w.wih.f, d.R, 3 * d.H, E2, cur.gi, d.chain, st));
@@ -304,7 +312,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
                         cur.hp, st));
     // --- dec1, dec2 (train_nem.py:238-240)
     VMM_TRY(linear_fwd(cur.hp.f, w.w4.f, d.R, E2, d.H, cur.g4, d.chain, st));
-    VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps), cur.u,
+    VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps, c, ST_DEC1, t), cur.u,
                        cur.mean4, cur.rstd4, st));
     VMM_TRY(linear_fwd(cur.u.f, w.w5.f, d.R, static_cast<int>(d.ZW), E2, cur.g5, d.chain, st));
     VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps), cur.z,
@@ -453,7 +461,7 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     VMM_TRY(linear_wgrad(sc.dv5, cur.u.b, d.R, static_cast<int>(d.ZW), E2, g->dec2_w, d.chain_b, st));
     // --- dec1
     {
-      LnDesc ln = ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps);
+      LnDesc ln = ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps, c, ST_DEC1, t);
       VMM_TRY(ln_backward_rows(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.du, E2, sc.dv4, sc.c1, sc.c2, nullptr, nullptr,
                                Planes(), st));
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.c1, sc.c2, sc.du, E2, g->dec1_ln_g,
@@ -477,7 +485,7 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     }
     // --- enc2
     {
-      LnDesc ln = ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps);
+      LnDesc ln = ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps, c, ST_ENC2, t);
       VMM_TRY(ln_backward_rows(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.de, E2, sc.dv2, sc.c1, sc.c2, nullptr, nullptr,
                                Planes(), st));
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.c1, sc.c2, sc.de, E2, g->enc2_ln_g,
@@ -487,7 +495,7 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     VMM_TRY(linear_wgrad(sc.dv2, cur.a.b, d.R, E2, d.ZW, g->enc2_w, d.chain_b, st));
     // --- enc1 + residual: dgamma_{t-1}, dXW1, dG1 (-> dz_{t-1} and dW13)
     {
-      LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps);
+      LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps, c, ST_ENC1, t);
       ln.xw1 = ws.xw1;
       ln.w1b3 = w.w1b3;
       ln.gamma = gam_prev;

@@ -346,11 +346,11 @@ int head_forward(const vmm_head_config* c, const vmm_head_params* p, const void*
                                          ws.order, ws.argmax, ws.feat);
   VMM_LAUNCHED();
   VMM_TRY(lin_fwd(ws.feat.f, w.w0.f, d.B, d.W, d.FW, ws.t0, p->b0, d.chain, st));
-  VMM_TRY(act_planes(ACT_RELU, d.B, d.W, ws.t0, d.W, ws.t1, st));
+  VMM_TRY(act_planes(ACT_RELU, d.B, d.W, ws.t0, d.W, ws.t1, c->dropout_p, c->dropout_seed + 1, st));
   VMM_TRY(lin_fwd(ws.t1.f, w.w3.f, d.B, d.W, d.W, ws.t3, p->b3, d.chain, st));
   if (descriptor) VMM_CHECK_CUDA(cudaMemcpyAsync(descriptor, ws.t3, sizeof(float) * d.B * d.W, cudaMemcpyDeviceToDevice, st));
   if (logits) {
-    VMM_TRY(act_planes(ACT_RELU, d.B, d.W, ws.t3, d.W, ws.t3r, st));
+    VMM_TRY(act_planes(ACT_RELU, d.B, d.W, ws.t3, d.W, ws.t3r, c->dropout_p, c->dropout_seed + 2, st));
     VMM_TRY(lin_fwd(ws.t3r.f, w.w6.f, d.B, d.C, d.W, logits, p->b6, d.chain, st));
   }
   return 0;
@@ -372,7 +372,7 @@ int head_backward(const vmm_head_config* c, const vmm_head_params* p, const void
     VMM_TRY(colsum_acc(d.B, d.C, d_logits, d.C, g->b6, st));
     VMM_TRY(lin_wgrad(sc.dl, d.Cp, ws.t3r.b, d.B, d.C, d.W, g->w6, d.chain_b, st));
     VMM_TRY(lin_dgrad(sc.dl, d.Cp, w.w6.b, d.B, d.C, d.W, sc.dt3f, d.chain_b, st));
-    VMM_TRY(act_backward(ACT_RELU, BW, ws.t3, sc.dt3f, st));
+    VMM_TRY(act_backward(ACT_RELU, BW, ws.t3, sc.dt3f, c->dropout_p, c->dropout_seed + 2, st));
     if (d_descriptor) {
       add_kernel<<<blocks_for(BW), 256, 0, st>>>(BW, d_descriptor, sc.dt3f);
       VMM_LAUNCHED();
@@ -384,7 +384,7 @@ int head_backward(const vmm_head_config* c, const vmm_head_params* p, const void
   VMM_TRY(colsum_acc(d.B, d.W, sc.dt3f, d.W, g->b3, st));
   VMM_TRY(lin_wgrad(sc.dt3, d.W, ws.t1.b, d.B, d.W, d.W, g->w3, d.chain_b, st));
   VMM_TRY(lin_dgrad(sc.dt3, d.W, w.w3.b, d.B, d.W, d.W, sc.dt0f, d.chain_b, st));
-  VMM_TRY(act_backward(ACT_RELU, BW, ws.t0, sc.dt0f, st));
+  VMM_TRY(act_backward(ACT_RELU, BW, ws.t0, sc.dt0f, c->dropout_p, c->dropout_seed + 1, st));
   VMM_TRY(split_planes(sc.dt0f, BW, sc.dt0, st));
   VMM_TRY(colsum_acc(d.B, d.W, sc.dt0f, d.W, g->b0, st));
   VMM_TRY(lin_wgrad(sc.dt0, d.W, ws.feat.b, d.B, d.W, d.FW, g->w0, d.chain_b, st));

@@ -187,6 +187,13 @@ __global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int ac
     o.y = act_fwd(act, fmaf((v.y - mean) * rstd, g.y, b.y));
     o.z = act_fwd(act, fmaf((v.z - mean) * rstd, g.z, b.z));
     o.w = act_fwd(act, fmaf((v.w - mean) * rstd, g.w, b.w));
+    if (d.drop_p > 0.f) {
+      const unsigned long long e = static_cast<unsigned long long>(obase + c);
+      o.x *= dropout_scale(d.drop_p, d.drop_seed, e);
+      o.y *= dropout_scale(d.drop_p, d.drop_seed, e + 1);
+      o.z *= dropout_scale(d.drop_p, d.drop_seed, e + 2);
+      o.w *= dropout_scale(d.drop_p, d.drop_seed, e + 3);
+    }
     store_op4(out, obase + c, o);
   };
   if (CACHED) {
@@ -237,7 +244,8 @@ __global__ void __launch_bounds__(LN_THREADS) ln_backward_rows_kernel(
       for (int q = 0; q < 4; ++q) {
         const float xh = (vv[q] - mean) * rstd;
         const float y = fmaf(xh, gg[q], be[q]);
-        const float dxh = oo[q] * act_grad(act, y) * gg[q];
+        const float dxh = oo[q] * dropout_scale(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * d.width + c + q) *
+                          act_grad(act, y) * gg[q];
         s1 += dxh;
         s2 = fmaf(dxh, xh, s2);
       }
@@ -261,7 +269,8 @@ __global__ void __launch_bounds__(LN_THREADS) ln_backward_rows_kernel(
       for (int q = 0; q < 4; ++q) {
         const float xh = (vv[q] - mean) * rstd;
         const float y = fmaf(xh, gg[q], be[q]);
-        const float dxh = oo[q] * act_grad(act, y) * gg[q];
+        const float dxh = oo[q] * dropout_scale(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * d.width + c + q) *
+                          act_grad(act, y) * gg[q];
         dv[q] = rstd * (dxh - c1 - xh * c2);
         if (MODE == LN_ENC1) dgam = fmaf(dv[q], ss[q], dgam);
       }
@@ -316,7 +325,8 @@ __global__ void __launch_bounds__(256) ln_backward_cols_kernel(LnDesc d, int act
     const float mean = mean_in[row], rstd = rstd_in[row];
     const float xh = (v - mean) * rstd;
     const float y = fmaf(xh, g, be);
-    const float dy = d_out[static_cast<long long>(row) * ldd + c] * act_grad(act, y);
+    const float dy = d_out[static_cast<long long>(row) * ldd + c] *
+                     dropout_scale(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * d.width + c) * act_grad(act, y);
     const float dv = rstd * (dy * g - c1_in[row] - xh * c2_in[row]);
     a_g = fmaf(dy, xh, a_g);
     a_b += dy;
@@ -609,7 +619,8 @@ __global__ void __launch_bounds__(256) colsum_acc_kernel(int rows, int width, in
   atomicAdd(out + j, s);
 }
 __global__ void __launch_bounds__(256) act_planes_kernel(int act, long long rows, int width,
-                                                         const float* __restrict__ src, long long ld, Op out) {
+                                                         const float* __restrict__ src, long long ld, Op out, float drop_p,
+                                                         unsigned long long drop_seed) {
   const long long n4 = rows * (width / 4);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -617,14 +628,20 @@ __global__ void __launch_bounds__(256) act_planes_kernel(int act, long long rows
     const int c = static_cast<int>(i % (width / 4)) * 4;
     float4 v = ld4(src + r * ld + c);
     v.x = act_fwd(act, v.x); v.y = act_fwd(act, v.y); v.z = act_fwd(act, v.z); v.w = act_fwd(act, v.w);
+    if (drop_p > 0.f) {
+      const unsigned long long e = static_cast<unsigned long long>(r * width + c);
+      v.x *= dropout_scale(drop_p, drop_seed, e); v.y *= dropout_scale(drop_p, drop_seed, e + 1);
+      v.z *= dropout_scale(drop_p, drop_seed, e + 2); v.w *= dropout_scale(drop_p, drop_seed, e + 3);
+    }
     store_op4(out, r * width + c, v);
   }
 }
 __global__ void __launch_bounds__(256) act_backward_kernel(int act, long long n, const float* __restrict__ pre,
-                                                           float* __restrict__ grad) {
+                                                           float* __restrict__ grad, float drop_p,
+                                                           unsigned long long drop_seed) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    grad[i] *= act_grad(act, pre[i]);
+    grad[i] *= dropout_scale(drop_p, drop_seed, static_cast<unsigned long long>(i)) * act_grad(act, pre[i]);
 }
 
 __global__ void __launch_bounds__(256) residual_op_kernel(long long rows, int D, int km, int mv,
@@ -834,23 +851,25 @@ int colsum_acc(int rows, int width, const float* src, long long ld, float* out, 
   VMM_LAUNCHED();
   return 0;
 }
-int act_planes(int act, long long rows, int width, const float* src, long long ld, const Op& out,
-               cudaStream_t stream) {
+int act_planes(int act, long long rows, int width, const float* src, long long ld, const Op& out, float drop_p,
+               unsigned long long drop_seed, cudaStream_t stream) {
   VMM_REQUIRE(width % 4 == 0 && ld % 4 == 0 && src && out.f.n >= 1, "act_planes: bad argument");
   if (rows <= 0) return 0;
   long long blocks = (rows * (width / 4) + 255) / 256;
   const long long cap = static_cast<long long>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  act_planes_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, rows, width, src, ld, out);
+  VMM_REQUIRE(drop_p <= 0.f || ld == width, "act_planes: dropout needs a dense source");
+  act_planes_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, rows, width, src, ld, out, drop_p, drop_seed);
   VMM_LAUNCHED();
   return 0;
 }
-int act_backward(int act, long long n, const float* pre, float* grad, cudaStream_t stream) {
+int act_backward(int act, long long n, const float* pre, float* grad, float drop_p, unsigned long long drop_seed,
+                 cudaStream_t stream) {
   if (n <= 0) return 0;
   long long blocks = (n + 255) / 256;
   const long long cap = static_cast<long long>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  act_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, n, pre, grad);
+  act_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, n, pre, grad, drop_p, drop_seed);
   VMM_LAUNCHED();
   return 0;
 }

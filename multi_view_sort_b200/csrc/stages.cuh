@@ -30,7 +30,26 @@ struct LnDesc {
   const float* gamma;
   int km, mv;
   float eps;
+  // train-mode Dropout after the activation (train_nem.py:172,175,181): element (row, col) is kept iff
+  // hash(drop_seed, row * width + col) >= drop_p * 2^32; kept values are scaled by 1/(1-p).  The mask is
+  // recomputed, never stored.  drop_p == 0: eval mode.
+  float drop_p;
+  unsigned long long drop_seed;
 };
+
+// Stateless per-element dropout decision shared by forward and backward kernels.
+__host__ __device__ inline unsigned dropout_hash(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<unsigned>(z >> 32);
+}
+__host__ __device__ inline float dropout_scale(float p, unsigned long long seed, unsigned long long idx) {
+  if (p <= 0.f) return 1.f;
+  const unsigned thr = static_cast<unsigned>(static_cast<double>(p) * 4294967296.0);
+  return dropout_hash(seed, idx) >= thr ? 1.f / (1.f - p) : 0.f;
+}
 
 int ln_forward(int mode, int act, const LnDesc& d, const Op& out, float* mean, float* rstd, cudaStream_t stream);
 
@@ -88,8 +107,9 @@ int gemv_rows(int n, int k, const float* W, const float* v, float* out, cudaStre
 int rank1_update(int n, int k, const float* u, const float* v, float* W, cudaStream_t stream);            // W[i,j] += u[i] v[j]
 int gemv_cols_acc(int n, int k, const float* W, const float* u, float* out, cudaStream_t stream);         // out[j] += sum_i u[i] W[i,j]
 int colsum_acc(int rows, int width, const float* src, long long ld, float* out, cudaStream_t stream);     // out[j] += sum_r src[r,j]
-int act_planes(int act, long long rows, int width, const float* src, long long ld, const Op& out,
-               cudaStream_t stream);                                                                     // planes(act(src))
-int act_backward(int act, long long n, const float* pre, float* grad, cudaStream_t stream);              // grad *= act'(pre)
+int act_planes(int act, long long rows, int width, const float* src, long long ld, const Op& out, float drop_p,
+               unsigned long long drop_seed, cudaStream_t stream);                    // planes(dropout(act(src)))
+int act_backward(int act, long long n, const float* pre, float* grad, float drop_p, unsigned long long drop_seed,
+                 cudaStream_t stream);                                                // grad *= mask * act'(pre)
 
 }  // namespace vmm

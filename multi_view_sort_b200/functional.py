@@ -19,7 +19,8 @@ from ._lib import check, lib, ptr, stream_ptr
 class EMConfig(C.Structure):
     _fields_ = [("B", C.c_int), ("K", C.c_int), ("M", C.c_int), ("D", C.c_int), ("H", C.c_int), ("T", C.c_int),
                 ("planes", C.c_int), ("planes_bwd", C.c_int), ("fwd_fp16", C.c_int), ("x_is_bf16", C.c_int), ("if_gamma_prior", C.c_int), ("stop_gamma_grad", C.c_int),
-                ("training", C.c_int), ("accum_chain", C.c_int), ("sigma", C.c_float), ("ln_eps", C.c_float)]
+                ("training", C.c_int), ("accum_chain", C.c_int), ("sigma", C.c_float), ("ln_eps", C.c_float),
+                ("dropout_p", C.c_float), ("dropout_seed", C.c_ulonglong)]
 
 
 EM_PARAM_FIELDS = [
@@ -81,14 +82,29 @@ def precision_planes(precision):
     return PRECISIONS[precision]
 
 
+def dropout_args(module):
+    """(p, seed) of this call: p = 0.5 in train mode (the reference's nn.Dropout(0.5)), 0 in eval mode.  The seed
+    is `module.dropout_seed` when set (tests), else derived from torch's seed and a per-module call counter."""
+    if not module.training:
+        return 0.0, 0
+    p = float(getattr(module, "dropout_p", 0.5))
+    fixed = getattr(module, "dropout_seed", None)
+    if fixed is not None:
+        return p, int(fixed) & 0xFFFFFFFFFF
+    n = module.__dict__.get("_vmm_dropout_calls", 0)
+    module.__dict__["_vmm_dropout_calls"] = n + 1
+    return p, ((torch.initial_seed() * 1000003) ^ (n * 7919 + 12345)) & 0xFFFFFFFFFF
+
+
 def make_config(module, B, T, x_is_bf16, training) -> EMConfig:
     planes, f16, planes_bwd, chain = precision_planes(module.precision)
+    drop_p, drop_seed = dropout_args(module)
     return EMConfig(B=B, K=module.k, M=module.m, D=module.input_dim, H=module.rnn_hidden_size, T=T, planes=planes,
                     planes_bwd=planes_bwd, fwd_fp16=f16,
                     x_is_bf16=int(x_is_bf16), if_gamma_prior=int(module.if_gamma_prior),
                     stop_gamma_grad=int(module.stop_gamma_grad), training=int(training),
                     accum_chain=chain, sigma=float(module.e_sigma),
-                    ln_eps=float(module.enc1[1].eps))
+                    ln_eps=float(module.enc1[1].eps), dropout_p=drop_p, dropout_seed=drop_seed)
 
 
 class _WeightCache:
@@ -226,7 +242,7 @@ def em_step(module, x, state):
 class HeadConfig(C.Structure):
     _fields_ = [("B", C.c_int), ("K", C.c_int), ("H", C.c_int), ("C", C.c_int), ("W", C.c_int), ("M", C.c_int),
                 ("planes", C.c_int), ("planes_bwd", C.c_int), ("fwd_fp16", C.c_int), ("accum_chain", C.c_int),
-                ("if_sort", C.c_int), ("if_pooling", C.c_int)]
+                ("if_sort", C.c_int), ("if_pooling", C.c_int), ("dropout_p", C.c_float), ("dropout_seed", C.c_ulonglong)]
 
 
 HEAD_PARAM_FIELDS = [("att_w", "att.0.weight"), ("att_b", "att.0.bias"), ("w0", "net.0.weight"), ("b0", "net.0.bias"),
@@ -252,9 +268,10 @@ def head_param_tensors(module):
 
 def make_head_config(module, B, M) -> HeadConfig:
     planes, f16, planes_bwd, chain = precision_planes(module.precision)
+    drop_p, drop_seed = dropout_args(module)
     return HeadConfig(B=B, K=module.k, H=module.rnn_hidden_size, C=module.nclasses, W=module.net[3].in_features, M=M,
                       planes=planes, planes_bwd=planes_bwd, fwd_fp16=f16, accum_chain=chain, if_sort=int(module.if_sort),
-                      if_pooling=int(module.if_pooling))
+                      if_pooling=int(module.if_pooling), dropout_p=drop_p, dropout_seed=drop_seed)
 
 
 class _HeadWeightCache:

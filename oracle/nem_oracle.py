@@ -78,20 +78,48 @@ def init_state(B: int, k: int, m: int, input_dim: int, hidden: int, init_type: s
 
 
 # ----------------------------------------------------------------------------
+# train-mode dropout with the CUDA library's stateless mask (NOT torch's Philox stream: bit-parity with
+# nn.Dropout's RNG is not a goal, SURVEY.md 7 hard part 6).  Host restatement of
+# multi_view_sort_b200/csrc/stages.cuh::dropout_hash so the GPU test can check train-mode forward AND
+# backward against the oracle with identical masks.
+# ----------------------------------------------------------------------------
+def dropout_mask(p_drop: float, seed: int, shape, dtype=torch.float32) -> torch.Tensor:
+    n = int(np.prod(shape))
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & ((1 << 64) - 1)) + np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    keep = (z >> np.uint64(32)) >= np.uint64(int(p_drop * 4294967296.0))
+    return torch.from_numpy(keep.astype(np.float64) / (1.0 - p_drop)).to(dtype).reshape(shape)
+
+
+def _stage_seed(seed: int, stage: int, it: int) -> int:
+    return (seed + (stage << 56) + (it << 40)) & ((1 << 64) - 1)
+
+
+# ----------------------------------------------------------------------------
 # one EM iteration (train_nem.py:219-294)
 # ----------------------------------------------------------------------------
-def run_inner_rnn(p: Params, masked: torch.Tensor, h_old: torch.Tensor, b: int, k: int, m: int):
-    """train_nem.py:219-245 in eval mode (Dropout = identity)."""
+def run_inner_rnn(p: Params, masked: torch.Tensor, h_old: torch.Tensor, b: int, k: int, m: int, drop=None):
+    """train_nem.py:219-245.  drop=None: eval mode (Dropout = identity); drop=(p, seed, iteration): the
+    Dropout(0.5) layers of enc1 / enc2 / dec1 (train_nem.py:172,175,181) with the library's masks."""
     x = masked.view(b * k * m, -1)
     a = F.elu(F.layer_norm(F.linear(x, p["enc1.0.weight"], p["enc1.0.bias"]), (ENC1_W,),
                            p["enc1.1.weight"], p["enc1.1.bias"]))
+    if drop:
+        a = a * dropout_mask(drop[0], _stage_seed(drop[1], 1, drop[2]), a.shape, a.dtype)
     a = a.view(b * k, -1)
     e = F.elu(F.layer_norm(F.linear(a, p["enc2.0.weight"], p["enc2.0.bias"]), (ENC2_W,),
                            p["enc2.1.weight"], p["enc2.1.bias"]))
+    if drop:
+        e = e * dropout_mask(drop[0], _stage_seed(drop[1], 2, drop[2]), e.shape, e.dtype)
     h = torch._VF.gru_cell(e, h_old, p["rnn_nem.weight_ih"], p["rnn_nem.weight_hh"],
                            p["rnn_nem.bias_ih"], p["rnn_nem.bias_hh"])
     u = F.relu(F.layer_norm(F.linear(h, p["dec1.0.weight"], p["dec1.0.bias"]), (DEC1_W,),
                             p["dec1.1.weight"], p["dec1.1.bias"]))
+    if drop:
+        u = u * dropout_mask(drop[0], _stage_seed(drop[1], 3, drop[2]), u.shape, u.dtype)
     v = F.layer_norm(F.linear(u, p["dec2.0.weight"], p["dec2.0.bias"]), (DEC3_IN * m,),
                      p["dec2.1.weight"], p["dec2.1.bias"])
     z = v.view(b * k * m, -1)
@@ -114,13 +142,13 @@ def e_step(pred: torch.Tensor, t_data: torch.Tensor, sigma: float):
     return probs / probs.sum(1).unsqueeze(1)
 
 
-def em_iteration(p: Params, x: torch.Tensor, state, sigma: float):
+def em_iteration(p: Params, x: torch.Tensor, state, sigma: float, drop=None):
     """train_nem.py:272-294.  x: (B,1,M,D); state = (h, pred, gamma)."""
     h_old, pred_old, gamma_old = state
     b, k, m = gamma_old.shape[0], gamma_old.shape[1], gamma_old.shape[2]
     delta = x - pred_old
     masked = delta * gamma_old
-    pred, h = run_inner_rnn(p, masked, h_old, b, k, m)
+    pred, h = run_inner_rnn(p, masked, h_old, b, k, m, drop)
     gamma = e_step(pred, x, sigma)
     return h, pred, gamma
 
@@ -166,7 +194,7 @@ def compute_outer_loss(mu, gamma, target, stop_gamma_grad: int, gamma_prior, if_
 # head (train_nem.py:328-380)
 # ----------------------------------------------------------------------------
 def head_forward(p: Params, h: torch.Tensor, gamma: torch.Tensor, k: int, if_sort: int = 1,
-                 if_pooling: int = 0, save_feature: int = 0):
+                 if_pooling: int = 0, save_feature: int = 0, drop=None):
     """train_nem.py:328-380 in eval mode.  h: (B*k, H).  Returns logits (B,C), or the
     4096-d descriptor (output of the 2nd Linear, pre-ReLU) when save_feature=1."""
     scores = torch.sigmoid(F.linear(h, p["att.0.weight"], p["att.0.bias"]))      # (B*k,1)
@@ -184,10 +212,15 @@ def head_forward(p: Params, h: torch.Tensor, gamma: torch.Tensor, k: int, if_sor
     else:
         feat = masked.reshape(masked.shape[0], -1)
     t1 = F.relu(F.linear(feat, p["net.0.weight"], p["net.0.bias"]))
+    if drop:                                          # VGG classifier Dropout after each hidden ReLU
+        t1 = t1 * dropout_mask(drop[0], drop[1] + 1, t1.shape, t1.dtype)
     t3 = F.linear(t1, p["net.3.weight"], p["net.3.bias"])
     if save_feature:
         return t3
-    return F.linear(F.relu(t3), p["net.6.weight"], p["net.6.bias"])
+    t3r = F.relu(t3)
+    if drop:
+        t3r = t3r * dropout_mask(drop[0], drop[1] + 2, t3r.shape, t3r.dtype)
+    return F.linear(t3r, p["net.6.weight"], p["net.6.bias"])
 
 
 # ----------------------------------------------------------------------------
@@ -196,7 +229,7 @@ def head_forward(p: Params, h: torch.Tensor, gamma: torch.Tensor, k: int, if_sor
 def run_em(p: Params, x: torch.Tensor, k: int, iters: int, sigma: float = 0.1,
            init_type: str = "bin_uniform", if_gamma_prior: int = 1, stop_gamma_grad: int = 0,
            gamma0: Optional[torch.Tensor] = None, gamma_prior: Optional[torch.Tensor] = None,
-           keep_all: bool = False):
+           keep_all: bool = False, drop=None):
     """T iterations + the last iteration's outer loss.  x: (B,M,D).
     Returns dict(h, gamma, pred, nem_loss, intra, inter[, hist])."""
     B, M, D = x.shape
@@ -211,8 +244,8 @@ def run_em(p: Params, x: torch.Tensor, k: int, iters: int, sigma: float = 0.1,
     gp = gp.to(dt)
     xin = x.unsqueeze(1)
     hist = []
-    for _ in range(iters):
-        state = em_iteration(p, xin, state, sigma)
+    for it in range(iters):
+        state = em_iteration(p, xin, state, sigma, (drop[0], drop[1], it) if drop else None)
         if keep_all:
             hist.append(state)
     h, pred, gamma = state
@@ -225,10 +258,10 @@ def run_em(p: Params, x: torch.Tensor, k: int, iters: int, sigma: float = 0.1,
 
 def train_step(p_nem: Params, p_head: Params, x: torch.Tensor, labels: Optional[torch.Tensor], k: int,
                iters: int, sigma: float = 0.1, if_gamma_prior: int = 1, stop_gamma_grad: int = 0,
-               if_sort: int = 1, if_pooling: int = 0, init_type: str = "bin_uniform"):
+               if_sort: int = 1, if_pooling: int = 0, init_type: str = "bin_uniform", drop_nem=None, drop_head=None):
     """Trainer.py:160-203: EM loop, head, loss = CE + nem_loss_T."""
-    r = run_em(p_nem, x, k, iters, sigma, init_type, if_gamma_prior, stop_gamma_grad)
-    out = head_forward(p_head, r["h"], r["gamma"], k, if_sort, if_pooling, 0)
+    r = run_em(p_nem, x, k, iters, sigma, init_type, if_gamma_prior, stop_gamma_grad, drop=drop_nem)
+    out = head_forward(p_head, r["h"], r["gamma"], k, if_sort, if_pooling, 0, drop_head)
     r["out"] = out
     if labels is not None:
         r["closs"] = F.cross_entropy(out, labels)

@@ -37,7 +37,7 @@ def _oracle(cfg, nem, x, dtype):
 
 
 def _cuda(cfg, nem, x, precision, xdtype):
-    nem = nem.cuda()
+    nem = nem.cuda().eval()          # parity is defined in eval mode (dropout off) with gradients enabled
     nem.precision = precision
     h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda().to(xdtype), cfg["T"])
     wh, wg = _probe(cfg)
@@ -137,7 +137,7 @@ def test_run_em_bf16_fast_forward():
     z, cfg = load_golden(name)
     nem, _ = seeded_models(cfg)
     x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
-    nem = nem.cuda()
+    nem = nem.cuda().eval()
     nem.precision = "bf16_fast"
     with torch.no_grad():
         h, gamma, nem_loss, _, _ = nem.run_em(x.cuda().bfloat16(), cfg["T"])
@@ -152,7 +152,7 @@ def test_run_em_matches_reference_golden():
     z, cfg = load_golden(name)
     nem, _ = seeded_models(cfg)
     x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
-    nem = nem.cuda()
+    nem = nem.cuda().eval()
     with torch.no_grad():
         h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda(), cfg["T"])
     assert rel_err(h, z["h"]) < 1e-4
@@ -167,7 +167,7 @@ def test_inference_mode_equals_training_forward():
     _, cfg = load_golden("peaky_b6_k4_m12_t4")
     nem, _ = seeded_models(cfg)
     x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
-    nem = nem.cuda()
+    nem = nem.cuda().eval()
     a = nem.run_em(x.cuda(), cfg["T"])
     with torch.no_grad():
         b = nem.run_em(x.cuda(), cfg["T"])
@@ -187,7 +187,7 @@ def test_train_step_fp32_mode_matches_reference_golden(name):
     z, cfg = load_golden(name)
     nem, head = seeded_models(cfg)
     x, y = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
-    nem, head = nem.cuda(), head.cuda()
+    nem, head = nem.cuda().eval(), head.cuda().eval()
     h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda(), cfg["T"])
     logits = head(h, gamma)
     closs = cross_entropy(logits, y.cuda())
@@ -241,7 +241,7 @@ def test_head_options_match_oracle():
         out = O.head_forward(ph, hh, r["gamma"], cfg["K"], if_sort, if_pool, 0)
         w = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
         (out * w).sum().backward()
-        head = head.cuda()
+        head = head.cuda().eval()
         hc = r["h"].cuda().requires_grad_(True)
         outc = head(hc, r["gamma"].cuda())
         (outc * w.cuda()).sum().backward()
@@ -260,7 +260,7 @@ def test_cfg3_80_views_matches_reference_golden():
     z, cfg = load_golden("cfg3_b2_k5_m80_t3")
     nem, head = seeded_models(cfg)
     x, y = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
-    nem, head = nem.cuda(), head.cuda()
+    nem, head = nem.cuda().eval(), head.cuda().eval()
     h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda(), cfg["T"])
     logits = head(h, gamma)
     loss = cross_entropy(logits, y.cuda()) + nem_loss
@@ -306,3 +306,56 @@ def test_step_level_forward_matches_oracle_iterations():
             assert rel_err(gamma, ref[t][2]) < 1e-4, t
     with pytest.raises(NotImplementedError):
         nem(xc.unsqueeze(1), (init[0], init[1], init[2]))     # grads enabled: directs the caller to run_em
+
+
+def test_train_mode_dropout():
+    """Train mode applies the reference's Dropout(0.5) (train_nem.py:172,175,181 and the VGG classifier) with a
+    stateless hashed mask.  Bit-parity with torch's Philox stream is not a goal (SURVEY.md 7, hard part 6);
+    instead the oracle applies the SAME masks (oracle.nem_oracle.dropout_mask restates the hash) and the whole
+    training step - forward and every gradient - must match it: this pins that forward and backward kernels
+    agree on the mask and on the 1/(1-p) scaling.  Also: eval mode is unaffected, a fixed seed is
+    deterministic, another seed differs, and the kept fraction is ~1/2."""
+    from multi_view_sort_b200.functional import cross_entropy
+    _, cfg = load_golden("prior0_b5_k2_m12_t3")
+    nem, head = seeded_models(cfg)
+    x, y = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    seed_n, seed_h = 1234, 777
+    pn, ph = params_of(nem), params_of(head)
+    ref = O.train_step(pn, ph, x, y, cfg["K"], cfg["T"], cfg["sigma"], cfg["if_gamma_prior"], cfg["stop_gamma_grad"],
+                       cfg["if_sort"], cfg["if_pooling"], drop_nem=(0.5, seed_n), drop_head=(0.5, seed_h))
+    ref["loss"].backward()
+    nem, head = nem.cuda(), head.cuda()
+    xc, yc = x.cuda(), y.cuda()
+
+    def step():
+        h, gamma, nem_loss, _, _ = nem.run_em(xc, cfg["T"])
+        logits = head(h, gamma)
+        return h, gamma, logits, cross_entropy(logits, yc) + nem_loss
+
+    close = lambda a, b: abs(a - b) <= 2e-6 * abs(b)       # the CE reduction uses fp32 atomics: order jitter only
+    nem.eval(); head.eval()
+    with torch.no_grad():
+        e1, e2 = step()[3].item(), step()[3].item()
+    assert close(e1, e2)
+    nem.train(); head.train()
+    nem.dropout_seed, head.dropout_seed = seed_n, seed_h
+    h, gamma, logits, loss = step()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - e1) > 1e-3                      # dropout is really on
+    assert rel_err(h, ref["h"]) < 1e-4 and rel_err(logits, ref["out"]) < 1e-4
+    assert abs(loss.item() - ref["loss"].item()) < 1e-4 * abs(ref["loss"].item())
+    for prefix, mod, pp in (("nem.", nem, pn), ("head.", head, ph)):
+        named = dict(mod.named_parameters())
+        for n, p in pp.items():
+            if p.grad is None:
+                continue
+            tol = 5e-4 if n == "att.0.bias" else 1e-4
+            assert rel_err(named[n].grad, p.grad) < tol, (prefix + n, rel_err(named[n].grad, p.grad))
+    with torch.no_grad():
+        t2 = step()[3].item()
+        nem.dropout_seed = 99
+        t3 = step()[3].item()
+    assert close(loss.item(), t2) and not close(t2, t3)
+    from multi_view_sort_b200.csrc_probe import kept_fraction
+    assert abs(kept_fraction(0.5, 1234, 1 << 16) - 0.5) < 0.01
