@@ -73,7 +73,15 @@ VMM_API long long vmm_launch_count(void);
 /* Measurement aid: while enabled, every tensor-core contraction launch is bracketed by CUDA
  * events on its stream; _read() waits for them, returns the summed device time, the executed
  * tensor-core FLOPs (all split passes) and the launch count since the last call, and resets. */
+typedef struct vmm_gemm_record {
+  int M, N;
+  long long k_total; /* sum of the K of all segments (split passes included) */
+  int nseg, chain_kb, chains, splits, epilogue, a_mn, b_mn;
+  float ms;
+} vmm_gemm_record;
 VMM_API int vmm_gemm_profile(int enable);
+/* Copies up to max_records per-launch records (with device times) without resetting; returns the count. */
+VMM_API int vmm_gemm_profile_records(vmm_gemm_record* out, int max_records);
 VMM_API int vmm_gemm_profile_read(double* total_ms, double* executed_flops, long long* launches);
 
 /* ---------------------------------------------------------------------------------------

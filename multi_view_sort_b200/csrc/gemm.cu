@@ -44,6 +44,7 @@ struct GemmProfile {
   bool enabled = false;
   std::vector<cudaEvent_t> ev;     // pairs
   std::vector<double> flops;       // executed tensor-core FLOPs of each launch
+  std::vector<vmm_gemm_record> recs;
   size_t used = 0;
 };
 static GemmProfile g_prof;
@@ -125,6 +126,10 @@ static int launch_one(const GemmParams& p, cudaStream_t stream) {
       double k = 0;
       for (int s = 0; s < p.nseg; ++s) k += static_cast<double>(p.seg_kb[s]) * BK;
       g_prof.flops.push_back(2.0 * p.M * p.N * k);
+      vmm_gemm_record r;
+      r.M = p.M; r.N = p.N; r.k_total = static_cast<long long>(k); r.nseg = p.nseg; r.chain_kb = p.chain_kb;
+      r.chains = p.total_chains; r.splits = p.splits; r.epilogue = EPI; r.a_mn = A_MN; r.b_mn = B_MN; r.ms = 0.f;
+      g_prof.recs.push_back(r);
     }
   }
   if (e0) cudaEventRecord(e0, stream);
@@ -402,7 +407,23 @@ int vmm_gemm_profile(int enable) {
   vmm::g_prof.enabled = enable != 0;
   vmm::g_prof.used = 0;
   vmm::g_prof.flops.clear();
+  vmm::g_prof.recs.clear();
   return 0;
+}
+int vmm_gemm_profile_records(vmm_gemm_record* out, int max_records) {
+  std::lock_guard<std::mutex> lk(vmm::g_prof.mu);
+  const size_t n = vmm::g_prof.used / 2;
+  int w = 0;
+  for (size_t i = 0; i < n && w < max_records; ++i) {
+    float t = 0.f;
+    if (cudaEventSynchronize(vmm::g_prof.ev[2 * i + 1]) != cudaSuccess ||
+        cudaEventElapsedTime(&t, vmm::g_prof.ev[2 * i], vmm::g_prof.ev[2 * i + 1]) != cudaSuccess)
+      return VMM_E_CUDA;
+    out[w] = vmm::g_prof.recs[i];
+    out[w].ms = t;
+    ++w;
+  }
+  return w;
 }
 int vmm_gemm_profile_read(double* total_ms, double* executed_flops, long long* launches) {
   std::lock_guard<std::mutex> lk(vmm::g_prof.mu);
@@ -423,6 +444,7 @@ int vmm_gemm_profile_read(double* total_ms, double* executed_flops, long long* l
   if (launches) *launches = static_cast<long long>(n);
   vmm::g_prof.used = 0;
   vmm::g_prof.flops.clear();
+  vmm::g_prof.recs.clear();
   return 0;
 }
 const char* vmm_last_error(void) { return vmm::g_err; }

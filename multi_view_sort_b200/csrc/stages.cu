@@ -6,6 +6,8 @@
 #include <cuda_fp16.h>
 #include <math.h>
 
+#include <algorithm>
+
 namespace vmm {
 namespace {
 
@@ -188,11 +190,9 @@ __global__ void __launch_bounds__(LN_THREADS) ln_forward_kernel(LnDesc d, int ac
     o.z = act_fwd(act, fmaf((v.z - mean) * rstd, g.z, b.z));
     o.w = act_fwd(act, fmaf((v.w - mean) * rstd, g.w, b.w));
     if (d.drop_p > 0.f) {
-      const unsigned long long e = static_cast<unsigned long long>(obase + c);
-      o.x *= dropout_scale(d.drop_p, d.drop_seed, e);
-      o.y *= dropout_scale(d.drop_p, d.drop_seed, e + 1);
-      o.z *= dropout_scale(d.drop_p, d.drop_seed, e + 2);
-      o.w *= dropout_scale(d.drop_p, d.drop_seed, e + 3);
+      float ds[4];
+      dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(obase + c), ds);
+      o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
     }
     store_op4(out, obase + c, o);
   };
@@ -337,6 +337,302 @@ __global__ void __launch_bounds__(256) ln_backward_cols_kernel(LnDesc d, int act
   atomicAdd(d_ln_b + c, a_b);
   atomicAdd(d_bias + c, a_bias);
   if (MODE == LN_ENC1 && d_w1b3) atomicAdd(d_w1b3 + c, a_w);
+}
+
+
+// ==========================================================================================
+// Width-1024 fast paths (enc1: the [B*K*M, 1024] stage carries most of the streaming traffic).
+// One WARP per row: 8 float4 per lane live in registers, row reductions are warp shuffles (no block
+// barrier), everything a lane needs from the [1024]-wide parameter vectors is L1-resident.
+// ==========================================================================================
+constexpr int W1K = 1024;
+constexpr int W1K_V = W1K / 128;     // float4 per lane
+
+__device__ __forceinline__ float act_grad_fast(int act, float y) {
+  if (act == ACT_ELU) return y > 0.f ? 1.f : __expf(y);
+  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) ln1k_forward_kernel(LnDesc d, int act, Op out, float* __restrict__ mean_out,
+                                                           float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < d.rows; row += gridDim.x * wpb) {
+    float gam = 0.f;
+    long long xrow = 0;
+    if (MODE == LN_ENC1) {
+      gam = __ldg(d.gamma + row);
+      xrow = static_cast<long long>(row / d.km) * d.mv + row % d.mv;
+    }
+    float4 v[W1K_V];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < W1K_V; ++i) {
+      v[i] = ln_value4<MODE>(d, row, xrow, gam, (lane + 32 * i) * 4, nullptr);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum_f(sum) * (1.0f / W1K);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < W1K_V; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      sq += (a * a + b * b) + (e * e + f * f);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum_f(sq) * (1.0f / W1K) + d.eps);
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+    const long long obase = static_cast<long long>(row) * W1K;
+#pragma unroll
+    for (int i = 0; i < W1K_V; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      const float4 g = ld4(d.ln_g + c), b = ld4(d.ln_b + c);
+      float4 o;
+      o.x = act_fwd(act, fmaf((v[i].x - mean) * rstd, g.x, b.x));
+      o.y = act_fwd(act, fmaf((v[i].y - mean) * rstd, g.y, b.y));
+      o.z = act_fwd(act, fmaf((v[i].z - mean) * rstd, g.z, b.z));
+      o.w = act_fwd(act, fmaf((v[i].w - mean) * rstd, g.w, b.w));
+      if (d.drop_p > 0.f) {
+        float ds[4];
+        dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(obase + c), ds);
+        o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
+      }
+      store_op4(out, obase + c, o);
+    }
+  }
+}
+
+// Backward rows, width 1024.  LN_ENC1: a warp owns one feature row (b, m) and walks its K latent rows, so
+// dxw1[b*Mv+m, :] += sum_k gamma*dv is a private read-modify-write.  LN_BIAS: a warp per row.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) ln1k_backward_rows_kernel(
+    LnDesc d, int act, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+    const float* __restrict__ d_out, long long ldd, Planes dvp, float* __restrict__ c1_out, float* __restrict__ c2_out,
+    float* __restrict__ dgamma, float* __restrict__ dxw1, Planes dg1) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int klat = (MODE == LN_ENC1) ? d.km / d.mv : 1;
+  const int groups = d.rows / klat;
+  for (int grp = blockIdx.x * wpb + (threadIdx.x >> 5); grp < groups; grp += gridDim.x * wpb) {
+    float4 acc[W1K_V];
+    if (MODE == LN_ENC1) {
+#pragma unroll
+      for (int i = 0; i < W1K_V; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int kk = 0; kk < klat; ++kk) {
+      int row = grp;
+      long long xrow = 0;
+      float gam = 0.f;
+      if (MODE == LN_ENC1) {
+        const int b = grp / d.mv, m = grp % d.mv;
+        row = (b * klat + kk) * d.mv + m;
+        xrow = grp;
+        gam = __ldg(d.gamma + row);
+      }
+      const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+      const long long rbase = static_cast<long long>(row) * W1K;
+      float4 xh[W1K_V], dx[W1K_V];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < W1K_V; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const float4 v = ln_value4<MODE>(d, row, xrow, gam, c, nullptr);
+        const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c);
+        const float4 go = ld4(d_out + static_cast<long long>(row) * ldd + c);
+        float ds[4] = {1.f, 1.f, 1.f, 1.f};
+        if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(rbase + c), ds);
+        xh[i] = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+        dx[i].x = go.x * ds[0] * act_grad_fast(act, fmaf(xh[i].x, g.x, bb.x)) * g.x;
+        dx[i].y = go.y * ds[1] * act_grad_fast(act, fmaf(xh[i].y, g.y, bb.y)) * g.y;
+        dx[i].z = go.z * ds[2] * act_grad_fast(act, fmaf(xh[i].z, g.z, bb.z)) * g.z;
+        dx[i].w = go.w * ds[3] * act_grad_fast(act, fmaf(xh[i].w, g.w, bb.w)) * g.w;
+        s1 += (dx[i].x + dx[i].y) + (dx[i].z + dx[i].w);
+        s2 += (dx[i].x * xh[i].x + dx[i].y * xh[i].y) + (dx[i].z * xh[i].z + dx[i].w * xh[i].w);
+      }
+      const float c1 = warp_sum_f(s1) * (1.0f / W1K), c2 = warp_sum_f(s2) * (1.0f / W1K);
+      if (lane == 0) {
+        c1_out[row] = c1;
+        c2_out[row] = c2;
+      }
+      float dgam = 0.f;
+#pragma unroll
+      for (int i = 0; i < W1K_V; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        float4 dv;
+        dv.x = rstd * (dx[i].x - c1 - xh[i].x * c2);
+        dv.y = rstd * (dx[i].y - c1 - xh[i].y * c2);
+        dv.z = rstd * (dx[i].z - c1 - xh[i].z * c2);
+        dv.w = rstd * (dx[i].w - c1 - xh[i].w * c2);
+        if (dvp.n) store_planes4(dvp, rbase + c, dv);
+        if (MODE == LN_ENC1) {
+          if (dgamma) {                                  // residual factor s, re-read (L1/L2 resident)
+            float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+            ln_value4<MODE>(d, row, xrow, gam, c, &sv);
+            dgam += (dv.x * sv.x + dv.y * sv.y) + (dv.z * sv.z + dv.w * sv.w);
+          }
+          acc[i].x = fmaf(gam, dv.x, acc[i].x); acc[i].y = fmaf(gam, dv.y, acc[i].y);
+          acc[i].z = fmaf(gam, dv.z, acc[i].z); acc[i].w = fmaf(gam, dv.w, acc[i].w);
+          if (dg1.n) store_planes4(dg1, rbase + c, make_float4(-gam * dv.x, -gam * dv.y, -gam * dv.z, -gam * dv.w));
+        }
+      }
+      if (MODE == LN_ENC1 && dgamma) {
+        dgam = warp_sum_f(dgam);
+        if (lane == 0) dgamma[row] = dgam;
+      }
+    }
+    if (MODE == LN_ENC1 && dxw1) {
+#pragma unroll
+      for (int i = 0; i < W1K_V; ++i) {
+        float4* px = reinterpret_cast<float4*>(dxw1 + static_cast<long long>(grp) * W1K + (lane + 32 * i) * 4);
+        float4 a = *px;
+        a.x += acc[i].x; a.y += acc[i].y; a.z += acc[i].z; a.w += acc[i].w;
+        *px = a;
+      }
+    }
+  }
+}
+
+
+// Backward rows for the wide LN_BIAS stages (4096, 1024*M): one block of width/16 threads per row, four
+// float4 per thread cached in registers between the reduction pass and the output pass.
+__global__ void __launch_bounds__(1024) lnw_backward_rows_kernel(LnDesc d, int act, const float* __restrict__ mean_in,
+                                                                 const float* __restrict__ rstd_in,
+                                                                 const float* __restrict__ d_out, long long ldd,
+                                                                 Planes dvp, float* __restrict__ c1_out,
+                                                                 float* __restrict__ c2_out) {
+  __shared__ float red[32];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+  const long long rbase = static_cast<long long>(row) * d.width;
+  float4 xh[4], dx[4];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (tid + i * blockDim.x) * 4;
+    const float4 v = ln_value4<LN_BIAS>(d, row, 0, 0.f, c, nullptr);
+    const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c);
+    const float4 go = ld4(d_out + static_cast<long long>(row) * ldd + c);
+    float ds[4] = {1.f, 1.f, 1.f, 1.f};
+    if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(rbase + c), ds);
+    xh[i] = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+    dx[i].x = go.x * ds[0] * act_grad_fast(act, fmaf(xh[i].x, g.x, bb.x)) * g.x;
+    dx[i].y = go.y * ds[1] * act_grad_fast(act, fmaf(xh[i].y, g.y, bb.y)) * g.y;
+    dx[i].z = go.z * ds[2] * act_grad_fast(act, fmaf(xh[i].z, g.z, bb.z)) * g.z;
+    dx[i].w = go.w * ds[3] * act_grad_fast(act, fmaf(xh[i].w, g.w, bb.w)) * g.w;
+    s1 += (dx[i].x + dx[i].y) + (dx[i].z + dx[i].w);
+    s2 += (dx[i].x * xh[i].x + dx[i].y * xh[i].y) + (dx[i].z * xh[i].z + dx[i].w * xh[i].w);
+  }
+  const float c1 = block_sum(s1, red) / static_cast<float>(d.width);
+  const float c2 = block_sum(s2, red) / static_cast<float>(d.width);
+  if (tid == 0) {
+    c1_out[row] = c1;
+    c2_out[row] = c2;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (tid + i * blockDim.x) * 4;
+    store_planes4(dvp, rbase + c,
+                  make_float4(rstd * (dx[i].x - c1 - xh[i].x * c2), rstd * (dx[i].y - c1 - xh[i].y * c2),
+                              rstd * (dx[i].z - c1 - xh[i].z * c2), rstd * (dx[i].w - c1 - xh[i].w * c2)));
+  }
+}
+
+// Forward for the same wide stages, same thread mapping (the generic kernel re-reads wide rows three times).
+__global__ void __launch_bounds__(1024) lnw_forward_kernel(LnDesc d, int act, Op out, float* __restrict__ mean_out,
+                                                           float* __restrict__ rstd_out) {
+  __shared__ float red[32];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  float4 v[4];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = ln_value4<LN_BIAS>(d, row, 0, 0.f, (tid + i * blockDim.x) * 4, nullptr);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = block_sum(sum, red) / static_cast<float>(d.width);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+    sq += (a * a + b * b) + (e * e + f * f);
+  }
+  const float rstd = 1.0f / sqrtf(block_sum(sq, red) / static_cast<float>(d.width) + d.eps);
+  if (tid == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  const long long obase = static_cast<long long>(row) * d.width;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (tid + i * blockDim.x) * 4;
+    const float4 g = ld4(d.ln_g + c), b = ld4(d.ln_b + c);
+    float4 o;
+    o.x = act_fwd(act, fmaf((v[i].x - mean) * rstd, g.x, b.x));
+    o.y = act_fwd(act, fmaf((v[i].y - mean) * rstd, g.y, b.y));
+    o.z = act_fwd(act, fmaf((v[i].z - mean) * rstd, g.z, b.z));
+    o.w = act_fwd(act, fmaf((v[i].w - mean) * rstd, g.w, b.w));
+    if (d.drop_p > 0.f) {
+      float ds[4];
+      dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(obase + c), ds);
+      o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
+    }
+    store_op4(out, obase + c, o);
+  }
+}
+
+// Column reductions, any width: each thread owns 4 consecutive columns (one float4 per row),
+// blockIdx.y strides over row chunks, per-row scalars are broadcast loads.
+template <int MODE>
+__global__ void __launch_bounds__(128) ln_backward_cols4_kernel(LnDesc d, int act, const float* __restrict__ mean_in,
+                                                                const float* __restrict__ rstd_in,
+                                                                const float* __restrict__ c1_in,
+                                                                const float* __restrict__ c2_in,
+                                                                const float* __restrict__ d_out, long long ldd,
+                                                                int rows_per_block, float* d_ln_g, float* d_ln_b,
+                                                                float* d_bias, float* d_w1b3) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= d.width) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(d.rows, r0 + rows_per_block);
+  const float4 g = ld4(d.ln_g + c), be = ld4(d.ln_b + c);
+  float4 a_g = make_float4(0.f, 0.f, 0.f, 0.f), a_b = a_g, a_bias = a_g, a_w = a_g;
+  for (int row = r0; row < r1; ++row) {
+    float gam = 0.f;
+    long long xrow = 0;
+    if (MODE == LN_ENC1) {
+      gam = __ldg(d.gamma + row);
+      xrow = static_cast<long long>(row / d.km) * d.mv + row % d.mv;
+    }
+    const float4 v = ln_value4<MODE>(d, row, xrow, gam, c, nullptr);
+    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    const float c1 = __ldg(c1_in + row), c2 = __ldg(c2_in + row);
+    const float4 go = ld4(d_out + static_cast<long long>(row) * ldd + c);
+    float ds[4] = {1.f, 1.f, 1.f, 1.f};
+    if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * d.width + c, ds);
+    const float xh[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
+    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w}, oo[4] = {go.x, go.y, go.z, go.w};
+    float dy[4], dv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      dy[q] = oo[q] * ds[q] * act_grad_fast(act, fmaf(xh[q], gg[q], bb[q]));
+      dv[q] = rstd * (dy[q] * gg[q] - c1 - xh[q] * c2);
+    }
+    a_g.x = fmaf(dy[0], xh[0], a_g.x); a_g.y = fmaf(dy[1], xh[1], a_g.y);
+    a_g.z = fmaf(dy[2], xh[2], a_g.z); a_g.w = fmaf(dy[3], xh[3], a_g.w);
+    a_b.x += dy[0]; a_b.y += dy[1]; a_b.z += dy[2]; a_b.w += dy[3];
+    a_bias.x += dv[0]; a_bias.y += dv[1]; a_bias.z += dv[2]; a_bias.w += dv[3];
+    if (MODE == LN_ENC1) {
+      a_w.x = fmaf(-gam, dv[0], a_w.x); a_w.y = fmaf(-gam, dv[1], a_w.y);
+      a_w.z = fmaf(-gam, dv[2], a_w.z); a_w.w = fmaf(-gam, dv[3], a_w.w);
+    }
+  }
+  atomicAdd(reinterpret_cast<float4*>(d_ln_g + c), a_g);
+  atomicAdd(reinterpret_cast<float4*>(d_ln_b + c), a_b);
+  atomicAdd(reinterpret_cast<float4*>(d_bias + c), a_bias);
+  if (MODE == LN_ENC1 && d_w1b3) atomicAdd(reinterpret_cast<float4*>(d_w1b3 + c), a_w);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -629,9 +925,9 @@ __global__ void __launch_bounds__(256) act_planes_kernel(int act, long long rows
     float4 v = ld4(src + r * ld + c);
     v.x = act_fwd(act, v.x); v.y = act_fwd(act, v.y); v.z = act_fwd(act, v.z); v.w = act_fwd(act, v.w);
     if (drop_p > 0.f) {
-      const unsigned long long e = static_cast<unsigned long long>(r * width + c);
-      v.x *= dropout_scale(drop_p, drop_seed, e); v.y *= dropout_scale(drop_p, drop_seed, e + 1);
-      v.z *= dropout_scale(drop_p, drop_seed, e + 2); v.w *= dropout_scale(drop_p, drop_seed, e + 3);
+      float ds[4];
+      dropout_scale4(drop_p, drop_seed, static_cast<unsigned long long>(r * width + c), ds);
+      v.x *= ds[0]; v.y *= ds[1]; v.z *= ds[2]; v.w *= ds[3];
     }
     store_op4(out, r * width + c, v);
   }
@@ -698,6 +994,18 @@ static int check_ln(const LnDesc& d, int mode) {
 int ln_forward(int mode, int act, const LnDesc& d, const Op& out, float* mean, float* rstd, cudaStream_t stream) {
   VMM_TRY(check_ln(d, mode));
   VMM_REQUIRE(out.f.n >= 1 && out.f.p[0] && mean && rstd, "ln_forward: null output");
+  if (d.width == W1K) {                 // warp-per-row fast path
+    const int blocks = std::min(ceil_div(d.rows, 8), device_sm_count() * 16);
+    if (mode == LN_BIAS) ln1k_forward_kernel<LN_BIAS><<<blocks, 256, 0, stream>>>(d, act, out, mean, rstd);
+    else ln1k_forward_kernel<LN_ENC1><<<blocks, 256, 0, stream>>>(d, act, out, mean, rstd);
+    VMM_LAUNCHED();
+    return 0;
+  }
+  if (mode == LN_BIAS && d.width % 512 == 0 && d.width / 16 <= 1024) {   // block of width/16 threads per row
+    lnw_forward_kernel<<<d.rows, d.width / 16, 0, stream>>>(d, act, out, mean, rstd);
+    VMM_LAUNCHED();
+    return 0;
+  }
   const bool cached = d.width <= LN_THREADS * 4 * LN_CACHE;
   if (mode == LN_BIAS) {
     if (cached) ln_forward_kernel<LN_BIAS, true><<<d.rows, LN_THREADS, 0, stream>>>(d, act, out, mean, rstd);
@@ -716,6 +1024,23 @@ int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, cons
   VMM_TRY(check_ln(d, mode));
   VMM_REQUIRE(mean && rstd && d_out && c1 && c2 && ldd % 4 == 0 && (dv.n > 0 || mode == LN_ENC1),
               "ln_backward_rows: null argument");
+  if (d.width == W1K) {                 // warp-per-row fast path
+    const int groups = mode == LN_ENC1 ? d.rows / d.km * d.mv : d.rows;
+    const int blocks = std::min(ceil_div(groups, 8), device_sm_count() * 16);
+    if (mode == LN_BIAS)
+      ln1k_backward_rows_kernel<LN_BIAS><<<blocks, 256, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2, nullptr,
+                                                                      nullptr, Planes());
+    else
+      ln1k_backward_rows_kernel<LN_ENC1><<<blocks, 256, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2, dgamma, dxw1,
+                                                                      dg1);
+    VMM_LAUNCHED();
+    return 0;
+  }
+  if (mode == LN_BIAS && d.width % 512 == 0 && d.width / 16 <= 1024 && dv.n > 0) {
+    lnw_backward_rows_kernel<<<d.rows, d.width / 16, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2);
+    VMM_LAUNCHED();
+    return 0;
+  }
   if (mode == LN_BIAS) {
     ln_backward_rows_kernel<LN_BIAS><<<d.rows, LN_THREADS, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2, nullptr,
                                                                           nullptr, Planes());
@@ -733,15 +1058,18 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
                      float* d_w1b3, cudaStream_t stream) {
   VMM_TRY(check_ln(d, mode));
   VMM_REQUIRE(mean && rstd && c1 && c2 && d_out && d_ln_g && d_ln_b && d_bias, "ln_backward_cols: null argument");
-  const int col_blocks = ceil_div(d.width, 256);
+  const int col_blocks = ceil_div(d.width / 4, 128);
   const int rpb = pick_rows_per_block(d.rows, col_blocks);
   dim3 grid(col_blocks, ceil_div(d.rows, rpb));
+  VMM_REQUIRE(((reinterpret_cast<uintptr_t>(d_ln_g) | reinterpret_cast<uintptr_t>(d_ln_b) |
+                reinterpret_cast<uintptr_t>(d_bias) | reinterpret_cast<uintptr_t>(d_w1b3)) & 15) == 0,
+              "ln_backward_cols: gradient buffers must be 16-byte aligned");
   if (mode == LN_BIAS)
-    ln_backward_cols_kernel<LN_BIAS><<<grid, 256, 0, stream>>>(d, act, mean, rstd, c1, c2, d_out, ldd, rpb, d_ln_g, d_ln_b,
-                                                                d_bias, nullptr);
+    ln_backward_cols4_kernel<LN_BIAS><<<grid, 128, 0, stream>>>(d, act, mean, rstd, c1, c2, d_out, ldd, rpb, d_ln_g, d_ln_b,
+                                                                 d_bias, nullptr);
   else
-    ln_backward_cols_kernel<LN_ENC1><<<grid, 256, 0, stream>>>(d, act, mean, rstd, c1, c2, d_out, ldd, rpb, d_ln_g, d_ln_b,
-                                                                d_bias, d_w1b3);
+    ln_backward_cols4_kernel<LN_ENC1><<<grid, 128, 0, stream>>>(d, act, mean, rstd, c1, c2, d_out, ldd, rpb, d_ln_g, d_ln_b,
+                                                                 d_bias, d_w1b3);
   VMM_LAUNCHED();
   return 0;
 }

@@ -30,25 +30,37 @@ struct LnDesc {
   const float* gamma;
   int km, mv;
   float eps;
-  // train-mode Dropout after the activation (train_nem.py:172,175,181): element (row, col) is kept iff
-  // hash(drop_seed, row * width + col) >= drop_p * 2^32; kept values are scaled by 1/(1-p).  The mask is
-  // recomputed, never stored.  drop_p == 0: eval mode.
+  // train-mode Dropout after the activation (train_nem.py:172,175,181): see dropout_scale below; kept values
+  // are scaled by 1/(1-p).  The mask is recomputed, never stored.  drop_p == 0: eval mode.
   float drop_p;
   unsigned long long drop_seed;
 };
 
-// Stateless per-element dropout decision shared by forward and backward kernels.
-__host__ __device__ inline unsigned dropout_hash(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return static_cast<unsigned>(z >> 32);
+// Stateless dropout decisions shared by forward and backward kernels: ONE 32-bit hash per group of four
+// consecutive elements (all widths are multiples of 4), one byte per element; an element is kept iff its
+// byte >= round(p * 256) (p is quantised to 1/256; 0.5 is exact).
+__host__ __device__ inline unsigned dropout_bits(unsigned long long seed, unsigned long long group) {
+  unsigned x = static_cast<unsigned>(group) ^ static_cast<unsigned>(seed);
+  const unsigned y = static_cast<unsigned>(group >> 32) ^ static_cast<unsigned>(seed >> 32);
+  x ^= y * 0x9E3779B9u;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
 }
+__host__ __device__ inline unsigned dropout_thr8(float p) { return static_cast<unsigned>(p * 256.f + 0.5f); }
+// scale of element `idx` (its group is idx / 4)
 __host__ __device__ inline float dropout_scale(float p, unsigned long long seed, unsigned long long idx) {
   if (p <= 0.f) return 1.f;
-  const unsigned thr = static_cast<unsigned>(static_cast<double>(p) * 4294967296.0);
-  return dropout_hash(seed, idx) >= thr ? 1.f / (1.f - p) : 0.f;
+  const unsigned bits = dropout_bits(seed, idx >> 2);
+  return ((bits >> (8 * (idx & 3))) & 255u) >= dropout_thr8(p) ? 1.f / (1.f - p) : 0.f;
+}
+// scales of the four elements of group idx / 4 (idx a multiple of 4)
+__host__ __device__ inline void dropout_scale4(float p, unsigned long long seed, unsigned long long idx, float (&s)[4]) {
+  const unsigned bits = dropout_bits(seed, idx >> 2), thr = dropout_thr8(p);
+  const float k = 1.f / (1.f - p);
+  s[0] = (bits & 255u) >= thr ? k : 0.f;
+  s[1] = ((bits >> 8) & 255u) >= thr ? k : 0.f;
+  s[2] = ((bits >> 16) & 255u) >= thr ? k : 0.f;
+  s[3] = (bits >> 24) >= thr ? k : 0.f;
 }
 
 int ln_forward(int mode, int act, const LnDesc& d, const Op& out, float* mean, float* rstd, cudaStream_t stream);

@@ -1,16 +1,23 @@
-"""Host-side re-statement of the library's stateless dropout hash (csrc/stages.cuh::dropout_hash), used by
+"""Host-side re-statement of the library's stateless dropout hash (csrc/stages.cuh::dropout_bits), used by
 tests to check the kept fraction without reading device activations."""
 
 
-def dropout_hash(seed: int, idx: int) -> int:
-    m = (1 << 64) - 1
-    z = (seed + idx * 0x9E3779B97F4A7C15) & m
-    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
-    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
-    z ^= z >> 31
-    return z >> 32
+def dropout_bits(seed: int, group: int) -> int:
+    m = 0xFFFFFFFF
+    x = (group & m) ^ (seed & m)
+    y = ((group >> 32) & m) ^ ((seed >> 32) & m)
+    x ^= (y * 0x9E3779B9) & m
+    x ^= x >> 16
+    x = (x * 0x7feb352d) & m
+    x ^= x >> 15
+    x = (x * 0x846ca68b) & m
+    x ^= x >> 16
+    return x
 
 
 def kept_fraction(p: float, seed: int, n: int) -> float:
-    thr = int(p * 4294967296.0)
-    return sum(dropout_hash(seed, i) >= thr for i in range(n)) / n
+    thr = int(p * 256.0 + 0.5)
+    kept = 0
+    for i in range(n):
+        kept += ((dropout_bits(seed, i >> 2) >> (8 * (i & 3))) & 255) >= thr
+    return kept / n

@@ -84,13 +84,21 @@ def init_state(B: int, k: int, m: int, input_dim: int, hidden: int, init_type: s
 # backward against the oracle with identical masks.
 # ----------------------------------------------------------------------------
 def dropout_mask(p_drop: float, seed: int, shape, dtype=torch.float32) -> torch.Tensor:
+    """multi_view_sort_b200/csrc/stages.cuh::dropout_scale: one 32-bit hash per group of four consecutive
+    elements, one byte per element, kept iff byte >= round(p * 256)."""
     n = int(np.prod(shape))
+    assert n % 4 == 0
+    group = np.arange(n // 4, dtype=np.uint64)
+    seed = seed & ((1 << 64) - 1)
     with np.errstate(over="ignore"):
-        z = np.uint64(seed & ((1 << 64) - 1)) + np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    keep = (z >> np.uint64(32)) >= np.uint64(int(p_drop * 4294967296.0))
+        x = (group & np.uint64(0xFFFFFFFF)).astype(np.uint32) ^ np.uint32(seed & 0xFFFFFFFF)
+        y = (group >> np.uint64(32)).astype(np.uint32) ^ np.uint32(seed >> 32)
+        x = x ^ (y * np.uint32(0x9E3779B9))
+        x = x ^ (x >> np.uint32(16)); x = x * np.uint32(0x7feb352d)
+        x = x ^ (x >> np.uint32(15)); x = x * np.uint32(0x846ca68b)
+        x = x ^ (x >> np.uint32(16))
+    bytes4 = np.stack([(x >> np.uint32(8 * q)) & np.uint32(255) for q in range(4)], axis=1).reshape(-1)
+    keep = bytes4 >= np.uint32(int(p_drop * 256.0 + 0.5))
     return torch.from_numpy(keep.astype(np.float64) / (1.0 - p_drop)).to(dtype).reshape(shape)
 
 
