@@ -1,0 +1,128 @@
+"""Feature store for the VMM path.
+
+Reads the reference's on-disk format - one ``.npy`` per object holding a ``(1, M, D)`` float32 array
+under ``<root>/<class>/fc_features_vggm_pretrained_imagenet/``, label = the directory two levels up
+(`KmeanImgDataset`, train_nem.py:77-141) - and offers a packed shard format for throughput: one
+contiguous ``(N, M, D)`` array (float32 or bfloat16 bit patterns) + labels, memory-mapped, so a
+batch is one slice that can go to pinned memory and the GPU without per-object file opens (at
+~15 k objects/s a B200 consumes ~3 GB/s of fp32 features).
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+CLASSNAMES = {
+    # train_nem.py:81-90
+    "MNet40": ['airplane', 'bathtub', 'bed', 'bench', 'bookshelf', 'bottle', 'bowl', 'car', 'chair', 'cone', 'cup', 'curtain',
+               'desk', 'door', 'dresser', 'flower_pot', 'glass_box', 'guitar', 'keyboard', 'lamp', 'laptop', 'mantel',
+               'monitor', 'night_stand', 'person', 'piano', 'plant', 'radio', 'range_hood', 'sink', 'sofa', 'stairs', 'stool',
+               'table', 'tent', 'toilet', 'tv_stand', 'vase', 'wardrobe', 'xbox'],
+    "MNet10": ['table', 'sofa', 'dresser', 'chair', 'bathtub', 'toilet', 'night_stand', 'monitor', 'desk', 'bed'],
+    "ShapeNet": ['2691156', '2747177', '2773838', '2801938', '2808440', '2818832', '2828884', '2843684', '2871439', '2876657',
+                 '2880940', '2924116', '2933112', '2942699', '2946921', '2954340', '2958343', '2992529', '3001627', '3046257',
+                 '3085013', '3207941', '3211117', '3261776', '3325088', '3337140', '3467517', '3513137', '3593526', '3624134',
+                 '3636649', '3642806', '3691459', '3710193', '3759954', '3761084', '3790512', '3797390', '3928116', '3938244',
+                 '3948459', '3991062', '4004475', '4074963', '4090263', '4099429', '4225987', '4256520', '4330267', '4379243',
+                 '4401088', '4460130', '4468005', '4530566', '4554684'],
+}
+FC_SUBDIR = "fc_features_vggm_pretrained_imagenet"     # train_nem.py:103-104
+CONV_SUBDIR = "features"                                # train_nem.py:106
+
+
+class KmeanImgDataset(torch.utils.data.Dataset):
+    """Drop-in for the reference's dataset (train_nem.py:77-141): same constructor, same
+    ``(class_id, tensor(M, D), path)`` items, same file discovery and shuffle (np.random.permutation)."""
+
+    def __init__(self, root_dir, test_mode=False, num_models=0, num_views=12, shuffle=True, fea_type=None, dataset='MNet40'):
+        self.dataset = dataset
+        if dataset not in CLASSNAMES:
+            print('not supported dataset!')
+        self.classnames = CLASSNAMES.get(dataset, [])
+        self.root_dir = root_dir
+        self.test_mode = test_mode
+        self.num_views = num_views
+        self.filepaths: List[str] = []
+        sub = FC_SUBDIR if fea_type == 'fc' else CONV_SUBDIR
+        for name in self.classnames:
+            self.filepaths.extend(sorted(glob.glob(root_dir + name + '/' + sub + '/*.npy')))
+        if shuffle:
+            idx = np.random.permutation(len(self.filepaths))
+            self.filepaths = [self.filepaths[i] for i in idx]
+
+    def __len__(self):
+        return len(self.filepaths)
+
+    def __getitem__(self, idx):
+        path = self.filepaths[idx]
+        class_id = self.classnames.index(path.split('/')[-3])
+        im = torch.from_numpy(np.load(path)).squeeze(0)
+        return class_id, im, path
+
+
+def _to_bf16_bits(a: np.ndarray) -> np.ndarray:
+    """float32 -> bfloat16 bit patterns (round to nearest even), as uint16."""
+    u = a.astype(np.float32).view(np.uint32)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+def pack_shard(dataset: KmeanImgDataset, out_prefix: str, dtype: str = "float32") -> str:
+    """Packs a per-object .npy dataset into ``<out_prefix>.features.npy`` (N, M, D), ``.labels.npy`` and
+    ``.json`` (paths, dtype).  dtype 'bfloat16' stores bf16 bit patterns (half the bytes: the 'bf16 features'
+    mode of the CUDA path consumes them directly)."""
+    n = len(dataset)
+    assert n > 0, "empty dataset"
+    first = dataset[0][1].numpy()
+    M, D = first.shape
+    store = np.uint16 if dtype == "bfloat16" else np.float32
+    feats = np.lib.format.open_memmap(out_prefix + ".features.npy", mode="w+", dtype=store, shape=(n, M, D))
+    labels = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        cid, im, _ = dataset[i]
+        a = im.numpy().astype(np.float32)
+        assert a.shape == (M, D), f"{dataset.filepaths[i]}: shape {a.shape} != {(M, D)}"
+        feats[i] = _to_bf16_bits(a) if dtype == "bfloat16" else a
+        labels[i] = cid
+    feats.flush()
+    np.save(out_prefix + ".labels.npy", labels)
+    with open(out_prefix + ".json", "w") as f:
+        json.dump({"dtype": dtype, "n": n, "views": M, "dim": D, "dataset": dataset.dataset, "paths": dataset.filepaths}, f)
+    return out_prefix
+
+
+class PackedFeatures:
+    """Memory-mapped packed shard; ``batch(lo, hi)`` returns (labels, features) torch tensors (features float32
+    or bfloat16) backed by pinned memory when ``pin`` and CUDA are available."""
+
+    def __init__(self, prefix: str, pin: bool = True):
+        with open(prefix + ".json") as f:
+            self.meta = json.load(f)
+        self.features = np.load(prefix + ".features.npy", mmap_mode="r")
+        self.labels = np.load(prefix + ".labels.npy")
+        self.paths: Sequence[str] = self.meta["paths"]
+        self.pin = pin and torch.cuda.is_available()
+
+    def __len__(self):
+        return int(self.meta["n"])
+
+    def batch(self, lo: int, hi: int, index: Optional[np.ndarray] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        sel = np.sort(index[lo:hi]) if index is not None else slice(lo, hi)
+        a = np.ascontiguousarray(self.features[sel])
+        t = torch.from_numpy(a)
+        if self.meta["dtype"] == "bfloat16":
+            t = t.view(torch.int16).view(torch.bfloat16)
+        y = torch.from_numpy(np.ascontiguousarray(self.labels[sel]))
+        if self.pin:
+            t, y = t.pin_memory(), y.pin_memory()
+        return y, t
+
+    def iterate(self, batch_size: int, shuffle: bool = False, seed: int = 0):
+        n = len(self)
+        index = np.random.RandomState(seed).permutation(n) if shuffle else None
+        for lo in range(0, n, batch_size):
+            yield self.batch(lo, min(n, lo + batch_size), index)

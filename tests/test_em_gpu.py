@@ -359,3 +359,26 @@ def test_train_mode_dropout():
     assert close(loss.item(), t2) and not close(t2, t3)
     from multi_view_sort_b200.csrc_probe import kept_fraction
     assert abs(kept_fraction(0.5, 1234, 1 << 16) - 0.5) < 0.01
+
+
+@pytest.mark.parametrize("B,K,M,D,H,T,prior_mode", [(1, 2, 12, 256, 128, 2, 1), (3, 6, 12, 512, 256, 1, 2), (2, 1, 12, 256, 128, 2, 1),
+                                                     (5, 5, 12, 264, 136, 2, 1), (7, 3, 4, 128, 64, 3, 0)])
+def test_edge_shapes_match_oracle(B, K, M, D, H, T, prior_mode):
+    """Ragged / minimal shapes: a single object, K = 1 (gamma == 1, train_nem.py:201-202), K = 6 of 12 views,
+    dims that are not multiples of the tile sizes, one iteration, 4 views, all three outer-loss modes."""
+    from multi_view_sort_b200 import NEM
+    torch.manual_seed(10)
+    nem = NEM(view_num=M, k=K, input_dim=D, rnn_hidden_size=H, iter_num=T, init_type="bin_uniform",
+              gamma_prior_loss=prior_mode, e_sigma=0.15).eval()
+    cfg = dict(B=B, K=K, M=M, D=D, H=H, T=T, sigma=0.15, if_gamma_prior=prior_mode, stop_gamma_grad=0, nclasses=40, scale=0.5)
+    x, _ = O.make_inputs(B, M, D, 40, seed=3, scale=0.5)
+    ref, pn = _oracle(cfg, nem, x, torch.float32)
+    res, nem_c = _cuda(cfg, nem, x, "fp32", torch.float32)
+    rows = {k: rel_err(res[k].reshape(-1), ref[k].reshape(-1)) for k in ("h", "gamma", "nem_loss", "intra", "inter")
+            if ref[k].abs().max() > 0}
+    named = dict(nem_c.named_parameters())
+    for n, p in pn.items():
+        if p.grad is not None and p.grad.abs().max() > 0:
+            rows["grad/" + n] = rel_err(named[n].grad, p.grad)
+    bad = {k: v for k, v in rows.items() if not v < 2e-4}
+    assert not bad, bad

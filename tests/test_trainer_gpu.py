@@ -1,0 +1,49 @@
+"""GPU test of the trainer / CLI / descriptor export on a tiny synthetic feature store in the reference's layout."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_features import make_store
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_then_export(tmp_path, monkeypatch):
+    from multi_view_sort_b200 import train_nem as cli
+    train_root = make_store(str(tmp_path / "train"), "MNet10", per_class=4, M=12, D=4096, seed=1)
+    val_root = make_store(str(tmp_path / "val"), "MNet10", per_class=2, M=12, D=4096, seed=2)
+    monkeypatch.chdir(tmp_path)
+    common = ["-name", "run", "-dataset", "MNet10", "-cluster_n", "3", "-iter", "2", "-bs", "8", "-train_path", train_root,
+              "-val_path", val_root, "-precision", "bf16"]
+    cli.main(common + ["-epoch", "2"])
+    assert json.load(open("run/config.json"))["cluster_n"] == 3
+    assert glob.glob("run/NEM/model-*.pth") and glob.glob("run/MV_C_Net/model-*.pth")     # best-accuracy checkpoint
+    scal = [json.loads(l) for l in open("run/scalars.jsonl")] if os.path.exists("run/scalars.jsonl") else None
+    if scal is not None:
+        tags = {s["tag"] for s in scal}
+        assert {"params/lr", "train/train_loss", "train/c_loss", "train/nem_loss", "train/intra_loss", "train/inter_loss",
+                "train/train_overall_acc", "val/val_mean_class_acc", "val/val_overall_acc", "val/val_loss"} <= tags
+        assert all(np.isfinite(s["value"]) for s in scal)
+    assert os.path.exists("3_each_class_acc.npy")
+    # test mode: load the checkpoint and export one 4096-d descriptor per object
+    cli.main(common + ["-train_or_test_mode", "test", "-feature_out", str(tmp_path / "desc")])
+    files = sorted(glob.glob(str(tmp_path / "desc" / "*" / "*" / "*.npy")))
+    assert len(files) == 8
+    d0 = np.load(files[0])
+    assert d0.shape == (1, 4096) and np.isfinite(d0).all()
+    # the exported descriptor equals a direct call on the same object
+    from multi_view_sort_b200.train_nem import build_models, parser
+    args = parser.parse_args(common)
+    nem, head = build_models(args, 10, save_feature=1)
+    nem.load("run", None); head.load("run", None)
+    nem, head = nem.cuda().eval(), head.cuda().eval()
+    rel = os.path.join(*files[0].split("/")[-3:])
+    x = torch.from_numpy(np.load(os.path.join(val_root, rel))).cuda()
+    with torch.no_grad():
+        h, gamma, *_ = nem.run_em(x)
+        d1 = head(h, gamma).cpu().numpy()
+    assert np.abs(d1 - d0).max() <= 2e-3 * np.abs(d0).max()       # bf16 preset, batch 1 vs batch 8 reduction order
