@@ -136,10 +136,9 @@ def _weight_cache(module) -> _WeightCache:
 
 class _EMFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, T, x, gamma0, prior, *params):
+    def forward(ctx, module, T, training, x, gamma0, prior, *params):
         B = x.shape[0]
         dev = x.device
-        training = any(ctx.needs_input_grad[5:])     # False under no_grad or with frozen parameters
         cfg = make_config(module, B, T, x.dtype == torch.bfloat16, training)
         with torch.cuda.device(dev):
             weights = _weight_cache(module).get(cfg, params)
@@ -173,7 +172,7 @@ class _EMFunction(torch.autograd.Function):
             d_loss = d_loss.contiguous().float() if d_loss is not None else torch.zeros(3, device=dev)
             check(lib().vmm_em_backward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(x), ptr(gamma0), ptr(prior), ptr(ws),
                                         ptr(scratch), ptr(d_h), ptr(d_gamma), ptr(d_loss), C.byref(gp), stream_ptr()))
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *grads)
 
 
 def run_em(module, x: torch.Tensor, iters: int, gamma0: Optional[torch.Tensor] = None,
@@ -196,7 +195,9 @@ def run_em(module, x: torch.Tensor, iters: int, gamma0: Optional[torch.Tensor] =
         gamma_prior = gamma0
     gamma_prior = gamma_prior.to(dev, torch.float32).reshape(B, module.k, module.m).contiguous()
     params = em_param_tensors(module)
-    h, gamma, loss = _EMFunction.apply(module, int(iters), x, gamma0, gamma_prior, *params)
+    # keep every iteration's activations only when a backward pass can follow
+    training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    h, gamma, loss = _EMFunction.apply(module, int(iters), training, x, gamma0, gamma_prior, *params)
     return h, gamma, loss[0], loss[1], loss[2]
 
 

@@ -173,6 +173,18 @@ def test_inference_mode_equals_training_forward():
         b = nem.run_em(x.cuda(), cfg["T"])
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+    # and the no_grad path really uses the small workspace (2 iteration slots, not T)
+    import ctypes as C
+    from multi_view_sort_b200.functional import make_config, _bytes
+    from multi_view_sort_b200._lib import lib
+    small = _bytes(lib().vmm_em_workspace_bytes, make_config(nem, cfg["B"], cfg["T"], False, False))
+    big = _bytes(lib().vmm_em_workspace_bytes, make_config(nem, cfg["B"], cfg["T"], False, True))
+    assert small < big
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        nem.run_em(x.cuda(), cfg["T"])
+    assert torch.cuda.max_memory_allocated() - base < big
 
 
 HEAD_CASES = ["cfg1_b8_k3_m12_t10", "peaky_b6_k4_m12_t4", "prior0_b5_k2_m12_t3"]
