@@ -394,3 +394,39 @@ def test_edge_shapes_match_oracle(B, K, M, D, H, T, prior_mode):
             rows["grad/" + n] = rel_err(named[n].grad, p.grad)
     bad = {k: v for k, v in rows.items() if not v < 2e-4}
     assert not bad, bad
+
+
+def test_rand_init_per_object_gamma():
+    """init_type='rand' (the NEM class default, train_nem.py:205-208): per-object random responsibilities that
+    double as the prior - passed explicitly so both sides see the same draw."""
+    from multi_view_sort_b200 import NEM
+    B, K, M, D, H, T = 4, 3, 12, 256, 128, 2
+    torch.manual_seed(10)
+    nem = NEM(view_num=M, k=K, input_dim=D, rnn_hidden_size=H, iter_num=T, init_type="rand", gamma_prior_loss=1, e_sigma=0.15).eval()
+    x, _ = O.make_inputs(B, M, D, 40, seed=10, scale=0.5)
+    g0 = torch.rand(B, K, M, 1, generator=torch.Generator().manual_seed(9))
+    g0 = g0 / g0.sum(1).unsqueeze(1)
+    pn = params_of(nem)
+    r = O.run_em(pn, x, K, T, 0.15, "rand", 1, 0, gamma0=g0, gamma_prior=g0, keep_all=True)
+    # Precondition of a tight gradient comparison: no dec1 pre-activation sits within the forward error of the
+    # ReLU kink (with seed 4 one unit has |y| = 2.6e-7 and ANY two fp32 implementations may disagree on its
+    # derivative, which moves every upstream gradient by ~3e-3 - see DESIGN.md 6).
+    import torch.nn.functional as F
+    with torch.no_grad():
+        margin = min(F.layer_norm(F.linear(h_, pn["dec1.0.weight"], pn["dec1.0.bias"]), (4096,), pn["dec1.1.weight"],
+                                  pn["dec1.1.bias"]).abs().min().item() for h_, _, _ in r["hist"])
+    assert margin > 2e-5, margin
+    wh, wg = torch.randn(B * K, H, generator=torch.Generator().manual_seed(1)) * 0.01, torch.randn(B, K, M, 1, generator=torch.Generator().manual_seed(2))
+    (r["nem_loss"] + (r["h"] * wh).sum() + (r["gamma"] * wg).sum()).backward()
+    nem = nem.cuda()
+    h, gamma, nem_loss, _, _ = nem.run_em(x.cuda(), T, gamma0=g0.cuda(), gamma_prior=g0.cuda())
+    (nem_loss + (h * wh.cuda()).sum() + (gamma * wg.cuda()).sum()).backward()
+    assert rel_err(h, r["h"]) < 1e-4 and rel_err(gamma, r["gamma"]) < 1e-4
+    assert abs(nem_loss.item() - r["nem_loss"].item()) < 1e-4 * abs(r["nem_loss"].item())
+    named = dict(nem.named_parameters())
+    errs = {n: rel_err(named[n].grad, p.grad) for n, p in pn.items() if p.grad is not None}
+    bad = {n: v for n, v in errs.items() if not v < 2e-4}
+    assert not bad, (bad, errs)
+    # and the module's own init_state produces a valid per-object draw
+    st = nem.init_state(x.shape, x)
+    assert st[2].shape == (B, K, M, 1) and torch.allclose(st[2].sum(1), torch.ones(B, M, 1, device=st[2].device), atol=1e-6)
