@@ -430,3 +430,46 @@ def test_rand_init_per_object_gamma():
     # and the module's own init_state produces a valid per-object draw
     st = nem.init_state(x.shape, x)
     assert st[2].shape == (B, K, M, 1) and torch.allclose(st[2].sum(1), torch.ones(B, M, 1, device=st[2].device), atol=1e-6)
+
+
+def test_full_size_properties_configs1():
+    """BASELINE configs[1] at full size (4096 objects x 12 views x 4096-d, K=3, T=10; the oracle needs 511 GB of
+    autograd state there) through size-independent properties: responsibilities sum to one over K, objects are
+    independent (a permuted batch gives permuted outputs; a sub-batch gives the same rows), gradients of a split
+    batch add up to the full-batch gradient, and the outer loss equals the mean of the per-half losses."""
+    from multi_view_sort_b200 import NEM
+    B, K, M, D, H, T = 4096, 3, 12, 4096, 1024, 10
+    torch.manual_seed(10)
+    nem = NEM(view_num=M, k=K, input_dim=D, rnn_hidden_size=H, iter_num=T, init_type="bin_uniform", gamma_prior_loss=1,
+              e_sigma=0.1, precision="bf16").cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.relu(torch.randn(B, M, D, device="cuda", generator=g)).bfloat16()
+    with torch.no_grad():
+        h, gamma, loss, intra, inter = nem.run_em(x)
+        assert torch.isfinite(h).all() and torch.isfinite(gamma).all() and torch.isfinite(loss)
+        assert (gamma.sum(1) - 1).abs().max().item() < 1e-5
+        assert gamma.min().item() > 0
+        perm = torch.randperm(B, device="cuda", generator=g)
+        h2, gamma2, loss2, _, _ = nem.run_em(x[perm])
+        assert torch.equal(gamma2, gamma[perm])                         # bit-identical: no cross-object arithmetic
+        assert torch.equal(h2.view(B, K, H), h.view(B, K, H)[perm])
+        assert abs(loss2.item() - loss.item()) < 1e-5 * abs(loss.item())
+        hs, gs, la, _, _ = nem.run_em(x[:1000])
+        _, _, lb, _, _ = nem.run_em(x[1000:])
+        assert torch.equal(gs, gamma[:1000]) and torch.equal(hs, h[:K * 1000])
+        assert abs((1000 * la.item() + 3096 * lb.item()) / B - loss.item()) < 1e-5 * abs(loss.item())
+    # gradients: full batch == weighted sum of two halves (bf16 gradient planes: compare in relative L2)
+    wh = torch.randn(B * K, H, device="cuda", generator=g) * 1e-3
+    def grads(xs, whs, weight):
+        for p in nem.parameters():
+            p.grad = None
+        hh, gg, ll, _, _ = nem.run_em(xs)
+        ((ll + (hh * whs).sum() / xs.shape[0]) * weight).backward()
+        return {n: p.grad.clone() for n, p in nem.named_parameters() if p.grad is not None}
+    full = grads(x, wh, 1.0)
+    a = grads(x[:2048], wh[:K * 2048], 0.5)
+    b = grads(x[2048:], wh[K * 2048:], 0.5)
+    for n in full:
+        s = a[n] + b[n]
+        rel = ((s - full[n]).norm() / full[n].norm().clamp_min(1e-30)).item()
+        assert rel < 2e-3, (n, rel)
