@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VMM_ABI_VERSION 1
+#define VMM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VMM_API __attribute__((visibility("default")))
@@ -147,6 +147,18 @@ VMM_API int vmm_estep_backward(int rows, int D, int zk, const vmm_planes* z, con
                                const float* alpha, const float* beta, const float* kappa, const vmm_planes* dpred,
                                float* d_b3, void* stream);
 
+/* The same pair with delta = x - pred kept between them instead of recomputed: _save is vmm_estep_forward
+ * that also writes delta [rows, D] (delta_fmt VMM_DELTA_F16: fp16, saturating; VMM_DELTA_F32: float);
+ * _dpred is the streaming backward that reads it (one pass: 2-4 B read + 2 B per plane written per
+ * element instead of a rows x D x zk contraction).  Same outputs as vmm_estep_backward. */
+VMM_API int vmm_estep_forward_save(int rows, int D, int zk, const vmm_planes* z, const vmm_planes* w3, const float* b3,
+                                   const void* x, int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma,
+                                   float* part_e, float* part_sq, float* part_pp, void* delta, int delta_fmt,
+                                   void* stream);
+VMM_API int vmm_estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x, int x_is_bf16,
+                            long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
+                            const float* beta, const float* kappa, const vmm_planes* dpred, float* d_b3, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * The whole EM loop of one batch (replaces the per-batch loop of tools/Trainer.py:160-203:
  * NEM.init_state, T x NEM.forward (train_nem.py:272-294) and compute_outer_loss of the last
@@ -171,7 +183,24 @@ typedef struct vmm_em_config {
   float ln_eps;        /* nn.LayerNorm eps, 1e-5                                                */
   float dropout_p;     /* train-mode Dropout after enc1/enc2/dec1 (train_nem.py:172,175,181); 0 = eval */
   unsigned long long dropout_seed; /* masks are a pure function of (seed, stage, iteration, element)    */
+  /* Per-contraction operand selection of the forward pass, 2 bits each (VMM_FWD_*), contraction i at bits
+   * [2i, 2i+1]: 0 x*W1, 1 z*W13 (enc1 through the fold), 2 enc2, 3 GRU input, 4 GRU hidden, 5 dec1, 6 dec2,
+   * 7 dec3 + E-step, 8 the pred recompute of the E-step backward (save_delta == 0 only).  0 everywhere =
+   * every contraction uses all `planes`. */
+  unsigned fwd_modes;
+  /* 0: the E-step backward recomputes pred = z W3^T (a full dec3 contraction per iteration);
+   * VMM_DELTA_F16 / VMM_DELTA_F32: the forward E-step epilogue also writes delta = x - pred [B*K*M, D] of
+   * every iteration into the workspace (training only) and the backward is a streaming pass over it. */
+  int save_delta;
 } vmm_em_config;
+
+#define VMM_FWD_FULL 0u      /* all planes of both operands                                   */
+#define VMM_FWD_SINGLE 1u    /* leading plane of both operands: one tensor-core pass          */
+#define VMM_FWD_ACT_PAIR 2u  /* all planes of the activation x leading plane of the weight    */
+#define VMM_FWD_W_PAIR 3u    /* leading plane of the activation x all planes of the weight    */
+#define VMM_DELTA_NONE 0
+#define VMM_DELTA_F16 1
+#define VMM_DELTA_F32 2
 
 /* fp32 parameters in the reference's own state_dict layout (torch Linear [out, in]; GRU gate
  * order r, z, n) - train_nem.py:171-185.  after_rnn.* is never used by the reference's

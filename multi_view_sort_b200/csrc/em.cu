@@ -11,6 +11,8 @@
 // never materialised: the only consumer left is the E-step, fused into the dec3 contraction.
 #include <string.h>
 
+#include <cuda_fp16.h>
+
 #include "internal.h"
 #include "stages.cuh"
 
@@ -25,10 +27,12 @@ struct Dims {
   int chain;                          // accumulation chain length in k-blocks (0 = unlimited)
   int f16;                            // forward operands are fp16 pairs
   int chain_b;                        // chain bound of the gradient contractions (single bf16 plane: none needed)
+  unsigned modes;                     // VMM_FWD_* of each forward contraction, 2 bits each
+  int save_delta;                     // VMM_DELTA_*: keep delta = x - pred of every iteration for the backward pass
   long long R, RM, BM, ZW;   // B*K, B*K*M, B*M, 1024*M
   int nblk;
   explicit Dims(const vmm_em_config& c)
-      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16), chain_b(c.planes_bwd >= 2 ? c.accum_chain : 0), R(1ll * c.B * c.K),
+      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16), chain_b(c.planes_bwd >= 2 ? c.accum_chain : 0), modes(c.fwd_modes), save_delta(c.training ? c.save_delta : 0), R(1ll * c.B * c.K),
         RM(1ll * c.B * c.K * c.M), BM(1ll * c.B * c.M), ZW(1ll * E1 * c.M), nblk(2 * ((c.D + 255) / 256)) {}
 };
 
@@ -66,6 +70,7 @@ struct IterBufs {
   float *g5, *mean5, *rstd5;
   Op z;
   float *gamma, *inv_s;
+  void* delta;       // x - pred of this iteration [RM, D] (fp16 or fp32), only with save_delta in training
 };
 
 struct Workspace {
@@ -118,6 +123,9 @@ struct Workspace {
     t.z = b.op(d.RM * E1, d.planes, d.f16, d.pb);
     t.gamma = b.take<float>(d.RM);
     t.inv_s = b.take<float>(d.BM);
+    t.delta = nullptr;
+    if (d.save_delta == VMM_DELTA_F16) t.delta = b.take<__half>(d.RM * d.D);
+    else if (d.save_delta == VMM_DELTA_F32) t.delta = b.take<float>(d.RM * d.D);
     if (o) *o = t;
   }
   IterBufs slot(int iter) const {
@@ -183,16 +191,31 @@ int check_cfg(const vmm_em_config* c) {
   VMM_REQUIRE(c->sigma > 0.f && c->ln_eps > 0.f, "sigma and ln_eps must be positive");
   VMM_REQUIRE(c->accum_chain >= 0, "accum_chain must be >= 0");
   VMM_REQUIRE(c->dropout_p >= 0.f && c->dropout_p < 1.f, "dropout_p must be in [0, 1)");
+  VMM_REQUIRE(c->save_delta >= VMM_DELTA_NONE && c->save_delta <= VMM_DELTA_F32, "save_delta must be 0, 1 or 2");
+  VMM_REQUIRE((c->fwd_modes >> 18) == 0, "fwd_modes has 9 two-bit fields");
   VMM_REQUIRE(1ll * c->B * c->K * c->M < (1ll << 31) / 2, "too many rows for 32-bit indexing; split the batch");
   return 0;
 }
 
+// forward contraction ids (bit positions of vmm_em_config.fwd_modes / 2)
+enum { FC_XW1 = 0, FC_G1 = 1, FC_ENC2 = 2, FC_GI = 3, FC_GH = 4, FC_DEC1 = 5, FC_DEC2 = 6, FC_DEC3 = 7, FC_EBWD = 8 };
+
+inline Planes sel_act(const Dims& d, int fc, const Planes& a) {
+  const unsigned m = (d.modes >> (2 * fc)) & 3u;
+  return (m == VMM_FWD_SINGLE || m == VMM_FWD_W_PAIR) ? a.first(1) : a;
+}
+inline Planes sel_w(const Dims& d, int fc, const Planes& w) {
+  const unsigned m = (d.modes >> (2 * fc)) & 3u;
+  return (m == VMM_FWD_SINGLE || m == VMM_FWD_ACT_PAIR) ? w.first(1) : w;
+}
+
 // y[rows, n] = a[rows, k] * w[n, k]^T        (nn.Linear forward; bias is added by the consumer stage)
-int linear_fwd(const Planes& a, const Planes& w, long long rows, int n, long long k, float* y, int chain,
+int linear_fwd(const Dims& d, int fc, const Planes& a_all, const Planes& w_all, long long rows, int n, long long k, float* y,
                cudaStream_t st) {
+  const Planes a = sel_act(d, fc, a_all), w = sel_w(d, fc, w_all);
   vmm_gemm_seg s[9];
   const int ns = make_segs(s, a, k, w, k, k);
-  return gemm_bf16(static_cast<int>(rows), n, ns, s, false, false, y, n, nullptr, false, 1, chain, st);
+  return gemm_bf16(static_cast<int>(rows), n, ns, s, false, false, y, n, nullptr, false, 1, d.chain, st);
 }
 // dx[rows, k] (+)= dy[rows, n] * w[n, k]     (data gradient; w is read N-major, no transposed copy)
 int linear_dgrad(const Planes& dy, const Planes& w, long long rows, int n, long long k, float* dx, bool accumulate,
@@ -281,7 +304,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
   } else {
     VMM_TRY(split_op(static_cast<const float*>(x), d.BM * d.D, xp, st));
   }
-  VMM_TRY(linear_fwd(xp.f, w.w1.f, d.BM, E1, d.D, ws.xw1, d.chain, st));
+  VMM_TRY(linear_fwd(d, FC_XW1, xp.f, w.w1.f, d.BM, E1, d.D, ws.xw1, st));
   VMM_CHECK_CUDA(cudaMemsetAsync(ws.h0, 0, sizeof(float) * d.R * d.H, st));
 
   for (int t = 0; t < d.T; ++t) {
@@ -290,7 +313,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
     const bool last = (t == d.T - 1);
     const float* gam_prev = t > 0 ? prev.gamma : gamma0;
     // --- enc1 on the responsibility-weighted residual (train_nem.py:280-284, 226)
-    if (t > 0) VMM_TRY(linear_fwd(prev.z.f, w.w13.f, d.RM, E1, E1, cur.g1, d.chain, st));
+    if (t > 0) VMM_TRY(linear_fwd(d, FC_G1, prev.z.f, w.w13.f, d.RM, E1, E1, cur.g1, st));
     {
       LnDesc ln = ln_desc(d.RM, E1, t > 0 ? cur.g1 : nullptr, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps, c, ST_ENC1, t);
       ln.xw1 = ws.xw1;
@@ -301,27 +324,27 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
       VMM_TRY(ln_forward(LN_ENC1, ACT_ELU, ln, cur.a, cur.mean1, cur.rstd1, st));
     }
     // --- enc2 (train_nem.py:228-229)
-    VMM_TRY(linear_fwd(cur.a.f, w.w2.f, d.R, E2, d.ZW, cur.g2, d.chain, st));
+    VMM_TRY(linear_fwd(d, FC_ENC2, cur.a.f, w.w2.f, d.R, E2, d.ZW, cur.g2, st));
     VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps, c, ST_ENC2, t), cur.e,
                        cur.mean2, cur.rstd2, st));
     // --- GRU (train_nem.py:232)
-    VMM_TRY(linear_fwd(cur.e.f, w.wih.f, d.R, 3 * d.H, E2, cur.gi, d.chain, st));
-    if (t > 0) VMM_TRY(linear_fwd(prev.hp.f, w.whh.f, d.R, 3 * d.H, d.H, cur.gh, d.chain, st));
+    VMM_TRY(linear_fwd(d, FC_GI, cur.e.f, w.wih.f, d.R, 3 * d.H, E2, cur.gi, st));
+    if (t > 0) VMM_TRY(linear_fwd(d, FC_GH, prev.hp.f, w.whh.f, d.R, 3 * d.H, d.H, cur.gh, st));
     else VMM_CHECK_CUDA(cudaMemsetAsync(cur.gh, 0, sizeof(float) * d.R * 3 * d.H, st));
     VMM_TRY(gru_forward(static_cast<int>(d.R), d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, t > 0 ? prev.h : ws.h0, cur.h,
                         cur.hp, st));
     // --- dec1, dec2 (train_nem.py:238-240)
-    VMM_TRY(linear_fwd(cur.hp.f, w.w4.f, d.R, E2, d.H, cur.g4, d.chain, st));
+    VMM_TRY(linear_fwd(d, FC_DEC1, cur.hp.f, w.w4.f, d.R, E2, d.H, cur.g4, st));
     VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps, c, ST_DEC1, t), cur.u,
                        cur.mean4, cur.rstd4, st));
-    VMM_TRY(linear_fwd(cur.u.f, w.w5.f, d.R, static_cast<int>(d.ZW), E2, cur.g5, d.chain, st));
+    VMM_TRY(linear_fwd(d, FC_DEC2, cur.u.f, w.w5.f, d.R, static_cast<int>(d.ZW), E2, cur.g5, st));
     VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps), cur.z,
                        cur.mean5, cur.rstd5, st));
     // --- dec3 fused with the E-step (train_nem.py:241-270)
     const bool want_pp = last && c->if_gamma_prior == 0;
-    VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, cur.z.f, w.w3.f, p->dec3_b, x,
+    VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, sel_act(d, FC_DEC3, cur.z.f), sel_w(d, FC_DEC3, w.w3.f), p->dec3_b, x,
                           c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
-                          want_pp ? sc.part_pp : nullptr, st));
+                          want_pp ? sc.part_pp : nullptr, cur.delta, d.save_delta, st));
     VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
                           want_pp ? sc.part_pp : nullptr, cur.gamma, cur.inv_s, ws.row_sq, ws.row_pp, st));
     if (last) {
@@ -368,20 +391,20 @@ int em_step_forward(const vmm_em_config* c, const vmm_em_params* p, const void* 
   const IterBufs cur = ws.slot(0);
   const float eps = c->ln_eps;
   VMM_TRY(residual_op(d.RM, d.D, d.K * d.M, d.M, x, c->x_is_bf16, pred_in, gamma_in, sc.masked, st));
-  VMM_TRY(linear_fwd(sc.masked.f, w.w1.f, d.RM, E1, d.D, cur.g1, d.chain, st));
+  VMM_TRY(linear_fwd(d, FC_XW1, sc.masked.f, w.w1.f, d.RM, E1, d.D, cur.g1, st));
   VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.RM, E1, cur.g1, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps), cur.a, cur.mean1,
                      cur.rstd1, st));
-  VMM_TRY(linear_fwd(cur.a.f, w.w2.f, d.R, E2, d.ZW, cur.g2, d.chain, st));
+  VMM_TRY(linear_fwd(d, FC_ENC2, cur.a.f, w.w2.f, d.R, E2, d.ZW, cur.g2, st));
   VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps), cur.e, cur.mean2,
                      cur.rstd2, st));
-  VMM_TRY(linear_fwd(cur.e.f, w.wih.f, d.R, 3 * d.H, E2, cur.gi, d.chain, st));
+  VMM_TRY(linear_fwd(d, FC_GI, cur.e.f, w.wih.f, d.R, 3 * d.H, E2, cur.gi, st));
   VMM_TRY(split_op(h_in, d.R * d.H, sc.hin, st));
-  VMM_TRY(linear_fwd(sc.hin.f, w.whh.f, d.R, 3 * d.H, d.H, cur.gh, d.chain, st));
+  VMM_TRY(linear_fwd(d, FC_GH, sc.hin.f, w.whh.f, d.R, 3 * d.H, d.H, cur.gh, st));
   VMM_TRY(gru_forward(static_cast<int>(d.R), d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, h_in, h_out, cur.hp, st));
-  VMM_TRY(linear_fwd(cur.hp.f, w.w4.f, d.R, E2, d.H, cur.g4, d.chain, st));
+  VMM_TRY(linear_fwd(d, FC_DEC1, cur.hp.f, w.w4.f, d.R, E2, d.H, cur.g4, st));
   VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps), cur.u, cur.mean4,
                      cur.rstd4, st));
-  VMM_TRY(linear_fwd(cur.u.f, w.w5.f, d.R, static_cast<int>(d.ZW), E2, cur.g5, d.chain, st));
+  VMM_TRY(linear_fwd(d, FC_DEC2, cur.u.f, w.w5.f, d.R, static_cast<int>(d.ZW), E2, cur.g5, st));
   VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps), cur.z, cur.mean5,
                      cur.rstd5, st));
   {
@@ -390,7 +413,7 @@ int em_step_forward(const vmm_em_config* c, const vmm_em_params* p, const void* 
     VMM_TRY(gemm_bf16(static_cast<int>(d.RM), d.D, ns, s, false, false, pred_out, d.D, p->dec3_b, false, 1, d.chain, st));
   }
   VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, cur.z.f, w.w3.f, p->dec3_b, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
-                        sc.part_e, nullptr, nullptr, st));
+                        sc.part_e, nullptr, nullptr, nullptr, VMM_DELTA_NONE, st));
   VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, nullptr, nullptr, gamma_out, cur.inv_s, nullptr, nullptr, st));
   return 0;
 }
@@ -439,8 +462,12 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_CHECK_CUDA(cudaMemsetAsync(sc.beta, 0, sizeof(float) * d.RM, st));
     }
     VMM_TRY(gamma_backward(d.B, d.K, d.M, c->sigma, cur.gamma, cur.inv_s, sc.dgamma, sc.alpha, st));
-    VMM_TRY(estep_backward(static_cast<int>(d.RM), d.D, E1, cur.z.f, w.w3.f, p->dec3_b, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
-                           sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st));
+    if (d.save_delta)
+      VMM_TRY(estep_dpred(static_cast<int>(d.RM), d.D, cur.delta, d.save_delta, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
+                          sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st));
+    else
+      VMM_TRY(estep_backward(static_cast<int>(d.RM), d.D, E1, sel_act(d, FC_EBWD, cur.z.f), sel_w(d, FC_EBWD, w.w3.f), p->dec3_b, x,
+                             c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st));
     // --- dec3: weight gradient; dz = dpred W3 (+ dG1_{t+1} W13, the path through the next residual)
     VMM_TRY(linear_wgrad(sc.dpred, cur.z.b, d.RM, d.D, E1, g->dec3_w, d.chain_b, st));
     {

@@ -274,14 +274,26 @@ static int estep_common(GemmParams& p, int rows, int D, int zk, const Planes& z,
 
 int estep_forward(int rows, int D, int zk, const Planes& z, const Planes& w3, const float* b3, const void* x,
                   int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
-                  float* part_pp, cudaStream_t stream) {
+                  float* part_pp, void* delta, int delta_fmt, cudaStream_t stream) {
   GemmParams p;
   VMM_TRY(estep_common(p, rows, D, zk, z, w3, b3, x, ldx, k_latent, m_views, sigma));
   VMM_REQUIRE(part_e != nullptr, "part_e is null");
   p.part_e = part_e;
   p.part_sq = part_sq;
   p.part_pp = part_pp;
-  if (x_is_bf16) return launch_major<EPI_ESTEP, __nv_bfloat16, 1>(p, false, false, stream);
+  if (!delta) delta_fmt = VMM_DELTA_NONE;
+  VMM_REQUIRE(delta_fmt >= VMM_DELTA_NONE && delta_fmt <= VMM_DELTA_F32, "delta_fmt must be 0, 1 or 2");
+  VMM_REQUIRE((reinterpret_cast<uintptr_t>(delta) & 15) == 0, "delta must be 16-byte aligned");
+  p.delta_out = delta;
+  p.ldo = D;
+  // the kernel's OPL template slot selects the delta output of the forward epilogue: 1 none, 2 fp16, 3 fp32
+  if (x_is_bf16) {
+    if (delta_fmt == VMM_DELTA_F16) return launch_major<EPI_ESTEP, __nv_bfloat16, 2>(p, false, false, stream);
+    if (delta_fmt == VMM_DELTA_F32) return launch_major<EPI_ESTEP, __nv_bfloat16, 3>(p, false, false, stream);
+    return launch_major<EPI_ESTEP, __nv_bfloat16, 1>(p, false, false, stream);
+  }
+  if (delta_fmt == VMM_DELTA_F16) return launch_major<EPI_ESTEP, float, 2>(p, false, false, stream);
+  if (delta_fmt == VMM_DELTA_F32) return launch_major<EPI_ESTEP, float, 3>(p, false, false, stream);
   return launch_major<EPI_ESTEP, float, 1>(p, false, false, stream);
 }
 
@@ -480,7 +492,22 @@ int vmm_estep_forward(int rows, int D, int zk, const vmm_planes* z, const vmm_pl
                       int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
                       float* part_pp, void* stream) {
   return vmm::estep_forward(rows, D, zk, vmm::planes_from_c(z), vmm::planes_from_c(w3), b3, x, x_is_bf16, ldx, k_latent,
-                            m_views, sigma, part_e, part_sq, part_pp, static_cast<cudaStream_t>(stream));
+                            m_views, sigma, part_e, part_sq, part_pp, nullptr, VMM_DELTA_NONE,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int vmm_estep_forward_save(int rows, int D, int zk, const vmm_planes* z, const vmm_planes* w3, const float* b3,
+                           const void* x, int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma,
+                           float* part_e, float* part_sq, float* part_pp, void* delta, int delta_fmt, void* stream) {
+  return vmm::estep_forward(rows, D, zk, vmm::planes_from_c(z), vmm::planes_from_c(w3), b3, x, x_is_bf16, ldx, k_latent,
+                            m_views, sigma, part_e, part_sq, part_pp, delta, delta_fmt, static_cast<cudaStream_t>(stream));
+}
+
+int vmm_estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x, int x_is_bf16, long long ldx,
+                    int k_latent, int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
+                    const vmm_planes* dpred, float* d_b3, void* stream) {
+  return vmm::estep_dpred(rows, D, delta, delta_fmt, x, x_is_bf16, ldx, k_latent, m_views, sigma, alpha, beta, kappa,
+                          vmm::planes_from_c(dpred), d_b3, static_cast<cudaStream_t>(stream));
 }
 
 int vmm_estep_backward(int rows, int D, int zk, const vmm_planes* z, const vmm_planes* w3, const float* b3, const void* x,

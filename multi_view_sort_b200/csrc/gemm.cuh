@@ -22,10 +22,14 @@
 //               staged feature tile x, and reduces exp(-(x-pred)^2 / 2 sigma^2), (x-pred)^2
 //               and pred^2 over the tile's columns into per-(row, n-block) partial sums -
 //               the reference's compute_em_probabilities (train_nem.py:247-263) and the
-//               row sums its outer loss needs (tools/NEM_utilities.py:98-128).
+//               row sums its outer loss needs (tools/NEM_utilities.py:98-128).  In training it can
+//               also write delta = x - pred (fp16 or fp32; template OPL = 2 / 3) so that the
+//               backward pass streams over delta instead of recomputing the contraction.
 //   EPI_EBWD  : backward of the above: recomputes the pred tile and emits
 //               dL/dpred = delta*(alpha_r*E - beta_r) + kappa_r*pred in bf16 operand planes.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "ptx.cuh"
 
 namespace vmm {
@@ -70,6 +74,7 @@ struct alignas(64) GemmParams {
   __nv_bfloat16* out_p[3];   // EBWD output planes [M, ldo]: successive bf16 residuals (hi, mid, lo)
   long long ldo;
   float* colsum;             // EBWD: [N] += column sums of dL/dpred (dec3 bias gradient), nullable
+  void* delta_out;           // ESTEP with OPL 2 (fp16) / 3 (fp32): delta = x - pred, [M, ldo]
 };
 
 template <int BN>
@@ -112,6 +117,10 @@ __device__ __forceinline__ float bf16_bits_to_float(uint32_t hi16) { return __ui
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  __half2 t = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -230,6 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool kFused = (EPI == EPI_ESTEP || EPI == EPI_EBWD);
+  constexpr int kSave = (EPI == EPI_ESTEP) ? OPL - 1 : 0;     // 0: no delta output, 1: fp16, 2: fp32
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
@@ -419,12 +429,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 const float e = exp2f(d * d * p.exp_scale);
                 if constexpr (EPI == EPI_ESTEP) {
                   if (ok) { sum_e += e; sum_sq = fmaf(d, d, sum_sq); sum_pp = fmaf(pred, pred, sum_pp); }
+                  if constexpr (kSave != 0) out[4 * j + q] = ok ? d : 0.f;
                 } else {
                   out[4 * j + q] = ok ? fmaf(d, fmaf(alpha, e, -beta), kappa * pred) : 0.f;
                 }
               }
             }
             __syncwarp();                                            // all lanes have consumed their x row
+            if constexpr (kSave == 1) {
+              // delta as fp16: 64 B per row -> [32 rows][4 x 16 B], swizzled by (row>>1)&3, then coalesced rows
+              uint4* stw = reinterpret_cast<uint4*>(st);
+              uint32_t w16[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) w16[q] = pack_f16x2_sat(out[2 * q], out[2 * q + 1]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                stw[lane * 4 + (q ^ ((lane >> 1) & 3))] = make_uint4(w16[4 * q], w16[4 * q + 1], w16[4 * q + 2], w16[4 * q + 3]);
+              __syncwarp();
+              __half* outp = static_cast<__half*>(p.delta_out);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int r = j * 8 + (lane >> 2), q = lane & 3;
+                const int grow = row0 + r, gcol = col0 + q * 8;
+                if (grow < p.M && gcol < p.N)
+                  *reinterpret_cast<uint4*>(outp + static_cast<long long>(grow) * p.ldo + gcol) = stw[r * 4 + (q ^ ((r >> 1) & 3))];
+              }
+              __syncwarp();
+            } else if constexpr (kSave == 2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                st[st_slot(lane, j)] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+              __syncwarp();
+              float* outp = static_cast<float*>(p.delta_out);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int r = j * 4 + (lane >> 3), c4 = lane & 7;
+                const int grow = row0 + r, gcol = col0 + c4 * 4;
+                if (grow < p.M && gcol < p.N)
+                  *reinterpret_cast<float4*>(outp + static_cast<long long>(grow) * p.ldo + gcol) = st[st_slot(r, c4)];
+              }
+              __syncwarp();
+            }
             if constexpr (EPI == EPI_EBWD) {
               if (p.colsum) {
                 // exact fp32 column sums of this warp's 32x32 block (bias gradient of dec3)

@@ -73,10 +73,14 @@ int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool 
               const float* bias, bool accumulate, int splits, int chain_kb, cudaStream_t stream);
 int estep_forward(int rows, int D, int zk, const Planes& z, const Planes& w3, const float* b3, const void* x,
                   int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
-                  float* part_pp, cudaStream_t stream);
+                  float* part_pp, void* delta, int delta_fmt, cudaStream_t stream);
 int estep_backward(int rows, int D, int zk, const Planes& z, const Planes& w3, const float* b3, const void* x,
                    int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
                    const float* beta, const float* kappa, const Planes& dpred, float* colsum, cudaStream_t stream);
+// Streaming E-step backward from the saved delta = x - pred (stages.cu).
+int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x, int x_is_bf16, long long ldx,
+                int k_latent, int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
+                const Planes& dpred, float* colsum, cudaStream_t stream);
 int split_planes(const float* src, long long n, const Planes& out, cudaStream_t stream);
 int split_op(const float* src, long long n, const Op& out, cudaStream_t stream);   // both operand sets
 int bf16_to_f16(const void* src_bf16, long long n, void* dst_f16, cudaStream_t stream);

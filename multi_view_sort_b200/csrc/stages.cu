@@ -975,6 +975,103 @@ int pick_rows_per_block(int rows, int col_blocks) {
   return rpb;
 }
 
+// ------------------------------------------------------------------------------------------
+// Streaming E-step backward from the saved delta = x - pred (replaces the pred recompute of EPI_EBWD):
+//   dpred[r, d] = delta * (alpha[r] * exp(-delta^2 / (2 sigma^2)) - beta[r]) + kappa[r] * (x - delta)
+// as OPL bf16 residual planes, plus exact fp32 column sums (the dec3 bias gradient).
+// One thread owns 8 consecutive columns of a strip of rows; four rows are in flight per thread.
+// ------------------------------------------------------------------------------------------
+template <typename DT>
+__device__ __forceinline__ void ld_delta8(const DT* p, float (&v)[8]) {
+  if constexpr (sizeof(DT) == 2) {
+    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  } else {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+
+template <typename DT, int OPL>
+__global__ void __launch_bounds__(256) estep_dpred_kernel(int rows, int D, int rows_per_block, const DT* __restrict__ delta,
+                                                          const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                          const float* __restrict__ kappa, const void* __restrict__ x,
+                                                          int x_is_bf16, long long ldx, int km, int mv, float exp_scale,
+                                                          __nv_bfloat16* __restrict__ p0, __nv_bfloat16* __restrict__ p1,
+                                                          __nv_bfloat16* __restrict__ p2, float* __restrict__ colsum) {
+  const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (col >= D) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  __nv_bfloat16* const planes[3] = {p0, p1, p2};
+  for (int rb = r0; rb < r1; rb += 4) {
+    float dv[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (rb + i < r1) ld_delta8<DT>(delta + static_cast<long long>(rb + i) * D + col, dv[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rb + i;
+      if (r >= r1) break;
+      const float a = __ldg(alpha + r), b = __ldg(beta + r);
+      float out[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float d = dv[i][q];
+        out[q] = d * fmaf(a, exp2f(d * d * exp_scale), -b);
+      }
+      if (kappa) {                                                   // if_gamma_prior == 0 only: + kappa * pred
+        const float k = __ldg(kappa + r);
+        const long long xrow = static_cast<long long>(r / km) * mv + r % mv;
+        float xv[8];
+        if (x_is_bf16) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x) + xrow * ldx + col));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            xv[2 * j] = __uint_as_float(w[j] << 16);
+            xv[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+          }
+        } else {
+          const float4 xa = ld4(static_cast<const float*>(x) + xrow * ldx + col);
+          const float4 xb = ld4(static_cast<const float*>(x) + xrow * ldx + col + 4);
+          xv[0] = xa.x; xv[1] = xa.y; xv[2] = xa.z; xv[3] = xa.w; xv[4] = xb.x; xv[5] = xb.y; xv[6] = xb.z; xv[7] = xb.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) out[q] = fmaf(k, xv[q] - dv[i][q], out[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cs[q] += out[q];
+#pragma unroll
+      for (int pl = 0; pl < OPL; ++pl) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 t = __floats2bfloat162_rn(out[2 * j], out[2 * j + 1]);
+          w[j] = *reinterpret_cast<const uint32_t*>(&t);
+          if (pl + 1 < OPL) {
+            out[2 * j] -= __uint_as_float(w[j] << 16);
+            out[2 * j + 1] -= __uint_as_float(w[j] & 0xffff0000u);
+          }
+        }
+        *reinterpret_cast<uint4*>(planes[pl] + static_cast<long long>(r) * D + col) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(colsum + col + q, cs[q]);
+  }
+}
+
+
 }  // namespace
 
 // ---- host wrappers ------------------------------------------------------------------------
@@ -1198,6 +1295,45 @@ int act_backward(int act, long long n, const float* pre, float* grad, float drop
   const long long cap = static_cast<long long>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   act_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(act, n, pre, grad, drop_p, drop_seed);
+  VMM_LAUNCHED();
+  return 0;
+}
+
+int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x, int x_is_bf16, long long ldx,
+                int k_latent, int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
+                const Planes& dpred, float* colsum, cudaStream_t stream) {
+  VMM_REQUIRE(rows > 0 && D > 0 && D % 8 == 0 && delta && alpha && beta, "estep_dpred: bad argument");
+  VMM_REQUIRE(delta_fmt == VMM_DELTA_F16 || delta_fmt == VMM_DELTA_F32, "estep_dpred: delta_fmt must be fp16 or fp32");
+  VMM_REQUIRE(dpred.n >= 1 && dpred.n <= 3 && dpred.fmt == VMM_FMT_BF16, "estep_dpred: dpred must be 1..3 bf16 planes");
+  for (int i = 0; i < dpred.n; ++i)
+    VMM_REQUIRE(dpred.p[i] && (reinterpret_cast<uintptr_t>(dpred.p[i]) & 15) == 0, "dpred planes must be 16-byte aligned");
+  VMM_REQUIRE((reinterpret_cast<uintptr_t>(delta) & 15) == 0, "delta must be 16-byte aligned");
+  VMM_REQUIRE(!kappa || (x && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && k_latent > 0 && m_views > 0),
+              "estep_dpred: the kappa term needs the features");
+  VMM_REQUIRE(sigma > 0.f, "sigma must be positive");
+  const int col_blocks = ceil_div(D, 2048);
+  int strips = (device_sm_count() * 8) / col_blocks;
+  if (strips < 1) strips = 1;
+  int rpb = ceil_div(rows, strips);
+  rpb = (rpb + 3) & ~3;
+  if (rpb < 16) rpb = 16;
+  dim3 grid(col_blocks, ceil_div(rows, rpb));
+  const float exp_scale = -1.4426950408889634f / (2.f * sigma * sigma);
+  const int km = k_latent * m_views;
+#define VMM_DPRED(DT, N)                                                                                            \
+  estep_dpred_kernel<DT, N><<<grid, 256, 0, stream>>>(rows, D, rpb, static_cast<const DT*>(delta), alpha, beta, kappa, x,  \
+                                                      x_is_bf16, ldx, km, m_views, exp_scale, dpred.p[0], dpred.p[1],   \
+                                                      dpred.p[2], colsum)
+  if (delta_fmt == VMM_DELTA_F16) {
+    if (dpred.n == 1) VMM_DPRED(__half, 1);
+    else if (dpred.n == 2) VMM_DPRED(__half, 2);
+    else VMM_DPRED(__half, 3);
+  } else {
+    if (dpred.n == 1) VMM_DPRED(float, 1);
+    else if (dpred.n == 2) VMM_DPRED(float, 2);
+    else VMM_DPRED(float, 3);
+  }
+#undef VMM_DPRED
   VMM_LAUNCHED();
   return 0;
 }

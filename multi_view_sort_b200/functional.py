@@ -20,7 +20,7 @@ class EMConfig(C.Structure):
     _fields_ = [("B", C.c_int), ("K", C.c_int), ("M", C.c_int), ("D", C.c_int), ("H", C.c_int), ("T", C.c_int),
                 ("planes", C.c_int), ("planes_bwd", C.c_int), ("fwd_fp16", C.c_int), ("x_is_bf16", C.c_int), ("if_gamma_prior", C.c_int), ("stop_gamma_grad", C.c_int),
                 ("training", C.c_int), ("accum_chain", C.c_int), ("sigma", C.c_float), ("ln_eps", C.c_float),
-                ("dropout_p", C.c_float), ("dropout_seed", C.c_ulonglong)]
+                ("dropout_p", C.c_float), ("dropout_seed", C.c_ulonglong), ("fwd_modes", C.c_uint), ("save_delta", C.c_int)]
 
 
 EM_PARAM_FIELDS = [
@@ -68,18 +68,39 @@ def _bytes(fn, cfg) -> int:
 # hi/lo pair = 22 mantissa bits in 3 tensor-core passes) and short accumulation chains, while the
 # gradient contractions get by with fewer bits.
 PRECISIONS = {
-    "fp32": (2, 1, 2, 16),          # fp32-class forward, 2 bf16 planes backward        (tolerance 1e-4)
-    "fp32_strict": (2, 1, 3, 4),    # + 3 bf16 planes backward, 256-element chains
-    "bf16": (2, 1, 1, 16),          # "bf16 features" mode: fp32-class forward, bf16 gradients (1e-2)
-    "bf16_fast": (1, 0, 1, 0),      # single-pass bf16 everywhere: inference grade (h ~2e-2)
-    "fp32_bf16planes": (3, 0, 2, 16),   # the same accuracy from 3 bf16 residual planes (6 forward passes)
+    # (forward planes, fp16 pair, backward bf16 planes, chain, fwd_modes, save_delta)
+    "fp32": (2, 1, 2, 16, 0, 2),          # fp32-class forward, 2 bf16 planes backward        (tolerance 1e-4)
+    "fp32_strict": (2, 1, 3, 4, 0, 2),    # + 3 bf16 planes backward, 256-element chains
+    "bf16": (2, 1, 1, 16, 0, 2),          # "bf16 features" mode: fp32-class forward, bf16 gradients (1e-2)
+    "bf16_fast": (1, 0, 1, 0, 0, 1),      # single-pass bf16 everywhere: inference grade (h ~2e-2)
+    "fp32_bf16planes": (3, 0, 2, 16, 0, 2),   # the same accuracy from 3 bf16 residual planes (6 forward passes)
+    # E-step backward by recomputing pred (one more dec3 contraction per iteration) instead of streaming over the
+    # saved fp32 delta = x - pred: numerically identical, 12 % slower, 6 MB/object-iteration less workspace
+    "bf16_recompute": (2, 1, 1, 16, 0, 0),
+    "fp32_recompute": (2, 1, 2, 16, 0, 0),
+    "bf16_delta16": (2, 1, 1, 16, 0, 1),  # fp16 delta: half the delta traffic, gradients ~2e-3 further from the reference
 }
 
 
+# forward contraction ids of vmm_em_config.fwd_modes (2 bits each) and the VMM_FWD_* / VMM_DELTA_* values
+FWD_CONTRACTIONS = ("xw1", "g1", "enc2", "gi", "gh", "dec1", "dec2", "dec3", "ebwd")
+FWD_FULL, FWD_SINGLE, FWD_ACT_PAIR, FWD_W_PAIR = 0, 1, 2, 3
+DELTA_NONE, DELTA_F16, DELTA_F32 = 0, 1, 2
+
+
+def fwd_modes(**kw) -> int:
+    """fwd_modes(enc2=FWD_SINGLE, dec2=FWD_ACT_PAIR, ...) -> the packed bit field."""
+    m = 0
+    for name, v in kw.items():
+        m |= (int(v) & 3) << (2 * FWD_CONTRACTIONS.index(name))
+    return m
+
+
 def precision_planes(precision):
-    if isinstance(precision, (tuple, list)):
-        return tuple(int(v) for v in precision)
-    return PRECISIONS[precision]
+    """-> (forward planes, fp16 pair?, backward bf16 planes, chain, fwd_modes, save_delta); 4-tuples are padded
+    with (0, 0) = every forward contraction at full planes, E-step backward by recompute."""
+    t = tuple(int(v) for v in precision) if isinstance(precision, (tuple, list)) else PRECISIONS[precision]
+    return t + (0, 0)[len(t) - 4:] if len(t) < 6 else t
 
 
 def dropout_args(module):
@@ -97,9 +118,9 @@ def dropout_args(module):
 
 
 def make_config(module, B, T, x_is_bf16, training) -> EMConfig:
-    planes, f16, planes_bwd, chain = precision_planes(module.precision)
+    planes, f16, planes_bwd, chain, modes, save_delta = precision_planes(module.precision)
     drop_p, drop_seed = dropout_args(module)
-    return EMConfig(B=B, K=module.k, M=module.m, D=module.input_dim, H=module.rnn_hidden_size, T=T, planes=planes,
+    return EMConfig(fwd_modes=modes, save_delta=save_delta, B=B, K=module.k, M=module.m, D=module.input_dim, H=module.rnn_hidden_size, T=T, planes=planes,
                     planes_bwd=planes_bwd, fwd_fp16=f16,
                     x_is_bf16=int(x_is_bf16), if_gamma_prior=int(module.if_gamma_prior),
                     stop_gamma_grad=int(module.stop_gamma_grad), training=int(training),
@@ -268,7 +289,7 @@ def head_param_tensors(module):
 
 
 def make_head_config(module, B, M) -> HeadConfig:
-    planes, f16, planes_bwd, chain = precision_planes(module.precision)
+    planes, f16, planes_bwd, chain = precision_planes(module.precision)[:4]
     drop_p, drop_seed = dropout_args(module)
     return HeadConfig(B=B, K=module.k, H=module.rnn_hidden_size, C=module.nclasses, W=module.net[3].in_features, M=M,
                       planes=planes, planes_bwd=planes_bwd, fwd_fp16=f16, accum_chain=chain, if_sort=int(module.if_sort),

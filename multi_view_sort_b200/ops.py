@@ -121,3 +121,31 @@ def estep_backward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, alpha, 
                                    C.c_longlong(x.stride(-2)), int(k_latent), int(m_views), C.c_float(sigma), ptr(alpha),
                                    ptr(beta), ptr(kappa), C.byref(oc), ptr(d_b3), stream_ptr()))
     return outs
+
+
+def estep_forward_save(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, delta_dtype=torch.float16):
+    """estep_forward that also writes delta = x - pred (rows, D) as fp16 (saturating) or fp32.
+    Returns (part_e, part_sq, delta)."""
+    rows, zk = z_planes[0].shape
+    D = w3_planes[0].shape[0]
+    nb = estep_num_blocks(D)
+    dev = z_planes[0].device
+    pe, psq = torch.empty(rows, nb, device=dev), torch.empty(rows, nb, device=dev)
+    delta = torch.empty(rows, D, device=dev, dtype=delta_dtype)
+    zc, wc = planes_c(z_planes), planes_c(w3_planes)
+    check(lib().vmm_estep_forward_save(rows, D, zk, C.byref(zc), C.byref(wc), ptr(b3), ptr(x), int(x.dtype == torch.bfloat16),
+                                       C.c_longlong(x.stride(-2)), int(k_latent), int(m_views), C.c_float(sigma), ptr(pe),
+                                       ptr(psq), None, ptr(delta), 1 if delta_dtype == torch.float16 else 2, stream_ptr()))
+    return pe, psq, delta
+
+
+def estep_dpred(delta, x, k_latent, m_views, sigma, alpha, beta, kappa=None, d_b3=None, out_planes=1):
+    """Streaming E-step backward from the saved delta: same outputs as estep_backward."""
+    rows, D = delta.shape
+    assert delta.dtype in (torch.float16, torch.float32) and delta.is_contiguous()
+    outs = tuple(torch.empty(rows, D, device=delta.device, dtype=torch.bfloat16) for _ in range(out_planes))
+    oc = planes_c(outs)
+    check(lib().vmm_estep_dpred(rows, D, ptr(delta), 1 if delta.dtype == torch.float16 else 2, ptr(x),
+                                int(x.dtype == torch.bfloat16), C.c_longlong(x.stride(-2)), int(k_latent), int(m_views),
+                                C.c_float(sigma), ptr(alpha), ptr(beta), ptr(kappa), C.byref(oc), ptr(d_b3), stream_ptr()))
+    return outs

@@ -153,6 +153,42 @@ def test_estep_fused_forward_backward(B, K, Mv, D, zk, planes, xdt):
     assert _relmax(d_b3 - 0.5, dref.reshape(rows, D).sum(0)) < tol
 
 
+@pytest.mark.parametrize("ddt,out_planes,xdt,use_kappa", [(torch.float16, 1, torch.bfloat16, False), (torch.float32, 2, torch.float32, True),
+                                                          (torch.float32, 3, torch.float32, False), (torch.float16, 2, torch.float32, True)])
+@pytest.mark.parametrize("B,K,Mv,D,zk", [(3, 3, 12, 512, 256), (16, 3, 12, 4096, 1024), (2, 5, 80, 1000, 1024)])
+def test_estep_saved_delta_backward(B, K, Mv, D, zk, ddt, out_planes, xdt, use_kappa):
+    """The forward epilogue's saved delta = x - pred and the streaming backward over it reproduce the
+    recompute path (vmm_estep_backward): bit-identical planes with fp32 delta, fp16-rounding close with fp16."""
+    from multi_view_sort_b200 import ops
+    sigma = 0.25
+    rows = B * K * Mv
+    z = _rand((rows, zk), 30)
+    w3 = _rand((D, zk), 31, 1.0 / 32)
+    b3 = _rand((D,), 32, 0.1)
+    x = torch.relu(_rand((B * Mv, D), 33)).to(xdt)
+    zp, wp = ops.split_planes(z, 2, True), ops.split_planes(w3, 2, True)
+    pe0, psq0, _ = ops.estep_forward(zp, wp, b3, x, K, Mv, sigma, want_sq=True)
+    pe, psq, delta = ops.estep_forward_save(zp, wp, b3, x, K, Mv, sigma, delta_dtype=ddt)
+    torch.cuda.synchronize()
+    assert torch.equal(pe, pe0) and torch.equal(psq, psq0)          # saving delta does not change the E-step sums
+    zq = zp[0].double() + zp[1].double() / 2048
+    wq = wp[0].double() + wp[1].double() / 2048
+    pred, d, e = _estep_ref(zq, wq, b3, x.float(), K, Mv, sigma)
+    assert _relmax(delta.double().view(-1), d.reshape(-1)) < (1e-3 if ddt == torch.float16 else 2e-6)
+    alpha, beta = _rand((rows,), 34), _rand((rows,), 35, 0.1)
+    kappa = _rand((rows,), 36, 0.05) if use_kappa else None
+    db_a = torch.zeros(D, device="cuda")
+    db_b = torch.zeros(D, device="cuda")
+    want = ops.estep_backward(zp, wp, b3, x, K, Mv, sigma, alpha, beta, kappa, d_b3=db_a, out_planes=out_planes)
+    got = ops.estep_dpred(delta, x, K, Mv, sigma, alpha, beta, kappa, d_b3=db_b, out_planes=out_planes)
+    torch.cuda.synchronize()
+    w_sum, g_sum = sum(t.double() for t in want), sum(t.double() for t in got)
+    # fp16 delta: one bf16 ulp of the largest entry when the output is a single plane
+    tol = (8e-3 if out_planes == 1 else 3e-3) if ddt == torch.float16 else {2: 3e-5, 3: 2e-6}[out_planes]
+    assert _relmax(g_sum.view(-1), w_sum.view(-1)) < tol
+    assert _relmax(db_b, db_a) < (2e-3 if ddt == torch.float16 else 1e-5)
+
+
 def test_gemm_fp16_pair_planes():
     """fp16 hi/lo' pair (lo' = lo * 2^11) with the accumulator rescale (tcgen05.mma scale_input_d = 11):
     3 passes give ~22 mantissa bits.  (kind::f16 rejects mixed bf16 x fp16 operands - illegal
