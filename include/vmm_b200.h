@@ -114,6 +114,11 @@ VMM_API int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int 
                   float* C, long long ldc, const float* bias, int accumulate, int splits, int chain_kblocks,
                   void* stream);
 
+/* Execution shape of the contraction kernels: 0 = library's choice (CTA pairs - cluster of 2, tcgen05
+ * cta_group::2, 256 x 256 tile per pair - whenever M > 128), 1 = always one CTA per tile, 2 = always pairs.
+ * Process-wide; for tests and A/B timing. */
+VMM_API int vmm_gemm_force_ncta(int ncta);
+
 /* Same contract computed by a plain one-thread-per-output CUDA kernel (no tensor cores):
  * the on-device cross-check used by the GPU tests.  Not used by the product path. */
 VMM_API int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,

@@ -528,10 +528,16 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       ln.gamma = gam_prev;
       ln.km = d.K * d.M;
       ln.mv = d.M;
-      VMM_TRY(ln_backward_rows(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, Planes(), sc.c1, sc.c2,
-                               t > 0 ? sc.dgamma : nullptr, sc.dxw1, t > 0 ? sc.dg1 : Planes(), st));
-      VMM_TRY(ln_backward_cols(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.c1, sc.c2, sc.da, E1, g->enc1_ln_g,
-                               g->enc1_ln_b, g->enc1_b, t > 0 ? sc.dw1b3 : nullptr, st));
+      if (enc1_backward_fused_ok(E1, d.K)) {
+        VMM_TRY(enc1_backward_fused(ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, t > 0 ? sc.dgamma : nullptr, sc.dxw1,
+                                    t > 0 ? sc.dg1 : Planes(), g->enc1_ln_g, g->enc1_ln_b, g->enc1_b,
+                                    t > 0 ? sc.dw1b3 : nullptr, st));
+      } else {
+        VMM_TRY(ln_backward_rows(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, Planes(), sc.c1, sc.c2,
+                                 t > 0 ? sc.dgamma : nullptr, sc.dxw1, t > 0 ? sc.dg1 : Planes(), st));
+        VMM_TRY(ln_backward_cols(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.c1, sc.c2, sc.da, E1, g->enc1_ln_g,
+                                 g->enc1_ln_b, g->enc1_b, t > 0 ? sc.dw1b3 : nullptr, st));
+      }
     }
     if (t > 0) VMM_TRY(linear_wgrad(sc.dg1, prev.z.b, d.RM, E1, E1, sc.dw13, d.chain_b, st));
   }

@@ -1,5 +1,7 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map construction, tile/split planning, launch,
 // and the extern "C" entry points vmm_gemm_bf16 / vmm_estep_forward / vmm_estep_backward.
+#include <string.h>
+
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -94,10 +96,13 @@ static int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long inner, long
 }
 
 // ---- launch -------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int EPI, typename XT, int OPL>
+// NCTA = 2: CTA pairs (cluster of 2, tcgen05 cta_group::2), one pair per 256 x 256 output tile.
+static std::atomic<int> g_force_ncta{0};   // 0 = choose (pairs whenever M > 128); 1 / 2 = forced (tests, A/B timing)
+
+template <int BN, bool A_MN, bool B_MN, int EPI, typename XT, int OPL, int NCTA>
 static int launch_one(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, XT, OPL>;
+  using Cfg = GemmCfg<BN, NCTA>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, XT, OPL, NCTA>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -107,8 +112,10 @@ static int launch_one(const GemmParams& p, cudaStream_t stream) {
     set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
     return VMM_E_CUDA;
   }
-  const int total_work = p.num_m_blk * p.num_n_blk * p.splits;
-  const int grid = total_work < device_sm_count() ? total_work : device_sm_count();
+  const int units = ceil_div(p.num_m_blk, NCTA);
+  const int total_work = units * p.num_n_blk * p.splits;
+  const int workers = device_sm_count() / NCTA;
+  const int grid = (total_work < workers ? total_work : workers) * NCTA;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.enabled) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
@@ -133,21 +140,52 @@ static int launch_one(const GemmParams& p, cudaStream_t stream) {
     }
   }
   if (e0) cudaEventRecord(e0, stream);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  if constexpr (NCTA == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VMM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  }
   if (e1) cudaEventRecord(e1, stream);
   VMM_LAUNCHED();
   return 0;
 }
 
+static int pick_ncta(const GemmParams& p) {
+  const int f = g_force_ncta.load(std::memory_order_relaxed);
+  if (f == 1 || f == 2) return f;
+  return p.num_m_blk >= 2 ? 2 : 1;
+}
+
 template <int EPI, typename XT, int OPL>
 static int launch_major(const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t s) {
+  const bool pair = pick_ncta(p) == 2;
   if constexpr (EPI == EPI_ESTEP || EPI == EPI_EBWD) {
-    return launch_one<256, false, false, EPI, XT, OPL>(p, s);
+    if (pair) return launch_one<256, false, false, EPI, XT, OPL, 2>(p, s);
+    return launch_one<256, false, false, EPI, XT, OPL, 1>(p, s);
   } else {
-    if (!a_mn && !b_mn) return launch_one<256, false, false, EPI, XT, OPL>(p, s);
-    if (!a_mn && b_mn) return launch_one<256, false, true, EPI, XT, OPL>(p, s);
-    if (a_mn && !b_mn) return launch_one<256, true, false, EPI, XT, OPL>(p, s);
-    return launch_one<256, true, true, EPI, XT, OPL>(p, s);
+    if (pair) {
+      if (!a_mn && !b_mn) return launch_one<256, false, false, EPI, XT, OPL, 2>(p, s);
+      if (!a_mn && b_mn) return launch_one<256, false, true, EPI, XT, OPL, 2>(p, s);
+      if (a_mn && !b_mn) return launch_one<256, true, false, EPI, XT, OPL, 2>(p, s);
+      return launch_one<256, true, true, EPI, XT, OPL, 2>(p, s);
+    }
+    if (!a_mn && !b_mn) return launch_one<256, false, false, EPI, XT, OPL, 1>(p, s);
+    if (!a_mn && b_mn) return launch_one<256, false, true, EPI, XT, OPL, 1>(p, s);
+    if (a_mn && !b_mn) return launch_one<256, true, false, EPI, XT, OPL, 1>(p, s);
+    return launch_one<256, true, true, EPI, XT, OPL, 1>(p, s);
   }
 }
 
@@ -162,13 +200,14 @@ static int fill_common(GemmParams& p, int M, int N, int nseg, const vmm_gemm_seg
   p.nseg = nseg;
   p.num_m_blk = ceil_div(M, BM);
   p.num_n_blk = ceil_div(N, BN);
+  const int ncta = pick_ncta(p);
   int nkb_max = 0;
   for (int s = 0; s < nseg; ++s) {
     const vmm_gemm_seg& g = segs[s];
     VMM_REQUIRE(g.k > 0 && g.a && g.b, "segment %d is empty", s);
     if (!a_mn) VMM_TRY(make_tmap_bf16(&p.tma_a[s], g.a, g.k, M, g.lda, BK, BM));
     else       VMM_TRY(make_tmap_bf16(&p.tma_a[s], g.a, M, g.k, g.lda, 64, BK));
-    if (!b_mn) VMM_TRY(make_tmap_bf16(&p.tma_b[s], g.b, g.k, N, g.ldb, BK, BN));
+    if (!b_mn) VMM_TRY(make_tmap_bf16(&p.tma_b[s], g.b, g.k, N, g.ldb, BK, BN / ncta));   // a pair's CTAs load half the tile each
     else       VMM_TRY(make_tmap_bf16(&p.tma_b[s], g.b, N, g.k, g.ldb, 64, BK));
     p.seg_kb[s] = ceil_div(g.k, BK);
     p.seg_flags[s] = g.flags;
@@ -182,8 +221,8 @@ static int fill_common(GemmParams& p, int M, int N, int nseg, const vmm_gemm_seg
     if (splits_req > 0) {
       want = splits_req;
     } else {
-      const int tiles = p.num_m_blk * p.num_n_blk;
-      const int sms = device_sm_count();
+      const int tiles = ceil_div(p.num_m_blk, ncta) * p.num_n_blk;
+      const int sms = device_sm_count() / ncta;          // workers: CTAs, or CTA pairs
       if (tiles < sms) want = sms / tiles;               // fill the machine when output tiles are few
       const int max_by_k = nkb_max / 8 > 0 ? nkb_max / 8 : 1;   // keep >= 8 k-blocks per split
       if (want > max_by_k) want = max_by_k;
@@ -413,6 +452,11 @@ extern "C" {
 
 int vmm_version(void) { return VMM_ABI_VERSION; }
 long long vmm_launch_count(void) { return vmm::g_launches.load(); }
+
+int vmm_gemm_force_ncta(int ncta) {
+  vmm::g_force_ncta.store(ncta == 1 || ncta == 2 ? ncta : 0);
+  return 0;
+}
 
 int vmm_gemm_profile(int enable) {
   std::lock_guard<std::mutex> lk(vmm::g_prof.mu);

@@ -8,6 +8,12 @@
 // the segments are the cross terms A_i B_j with i + j below the split order) and how two
 // contractions that land in the same output are fused into one launch.
 //
+// NCTA = 2 (the default for M > 128): CTAs run as pairs (cluster of 2, tcgen05 cta_group::2).  A pair owns a
+// 256 x BN tile: each CTA loads its own 128 rows of A and HALF of the B tile, the leader CTA issues M = 256 MMAs
+// that read both CTAs' shared memory, and each CTA drains its own 128 accumulator rows from its own TMEM.
+// Per-SM L2->smem traffic drops from 48 KB to 32 KB per 64-wide k-block; the single-CTA kernel ran AT the
+// chip's L2 throughput cap (measured: 1.13 PFLOP/s x 48 KB per 128x256x64 block = 12.9 TB/s).
+//
 // One CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
 // (one elected lane), warps 2..9 = epilogue (two warps per 32-lane TMEM group, each taking half
 // of the tile's columns).
@@ -77,12 +83,13 @@ struct alignas(64) GemmParams {
   void* delta_out;           // ESTEP with OPL 2 (fp16) / 3 (fp32): delta = x - pred, [M, ldo]
 };
 
-template <int BN>
+template <int BN, int NCTA = 1>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int A_BYTES = BM * BK * 2;              // this CTA's 128 rows of A
+  static constexpr int B_ROWS = BN / NCTA;                 // N rows of the B tile held by this CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB, or 32 KB per CTA of a pair
+  static constexpr int STAGES = (196608 / STAGE_BYTES);    // 4, or 6 for a pair
   static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256: power of two
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + BAR_BYTES;
@@ -97,16 +104,19 @@ struct WorkItem {
   int m_blk, n_blk, c0, c1;
 };
 
-__device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work) {
+// `ncta` consecutive m-blocks form one scheduling unit (the two CTAs of a pair take one each).
+__device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work, int ncta, int rank) {
   WorkItem w;
   const int tile = work / p.splits;
   const int split = work - tile * p.splits;
-  const int per_group = GROUP_M * p.num_n_blk;
+  const int units = (p.num_m_blk + ncta - 1) / ncta;
+  const int group_m = GROUP_M / ncta;
+  const int per_group = group_m * p.num_n_blk;
   const int group = tile / per_group;
-  const int first_m = group * GROUP_M;
-  const int gsize = min(p.num_m_blk - first_m, GROUP_M);
+  const int first_m = group * group_m;
+  const int gsize = min(units - first_m, group_m);
   const int in_group = tile - group * per_group;
-  w.m_blk = first_m + in_group % gsize;
+  w.m_blk = (first_m + in_group % gsize) * ncta + rank;
   w.n_blk = in_group / gsize;
   w.c0 = static_cast<int>((static_cast<long long>(p.total_chains) * split) / p.splits);
   w.c1 = static_cast<int>((static_cast<long long>(p.total_chains) * (split + 1)) / p.splits);
@@ -234,9 +244,9 @@ __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint3
   __syncwarp();
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, typename XT, int OPL>
+template <int BN, bool A_MN, bool B_MN, int EPI, typename XT, int OPL, int NCTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, NCTA>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool kFused = (EPI == EPI_ESTEP || EPI == EPI_EBWD);
   constexpr int kSave = (EPI == EPI_ESTEP) ? OPL - 1 : 0;     // 0: no delta output, 1: fp16, 2: fp32
@@ -251,7 +261,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_work = p.num_m_blk * p.num_n_blk * p.splits;
+  const int rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;          // 0 = leader of the pair
+  const int worker = NCTA == 2 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int nworkers = NCTA == 2 ? static_cast<int>(cluster_count_x()) : static_cast<int>(gridDim.x);
+  const int total_work = ((p.num_m_blk + NCTA - 1) / NCTA) * p.num_n_blk * p.splits;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -264,16 +277,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS);
+      mbar_init(&tempty_bar[a], EPI_WARPS * NCTA);        // the leader's barrier collects both CTAs' epilogue warps
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (NCTA == 2) {
+      tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();            // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -282,29 +301,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        const WorkItem w = decode_work(p, work);
+      // pair: completion bytes of BOTH CTAs are counted on the leader's barrier
+      const uint32_t full0 = NCTA == 2 ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;
+      auto load = [&](void* dst, const CUtensorMap* m, int st, int c0, int c1) {
+        if constexpr (NCTA == 2) tma_load_2d_pair(dst, m, full0 + 8u * st, c0, c1);
+        else tma_load_2d(dst, m, &full_bar[st], c0, c1);
+      };
+      for (int work = worker; work < total_work; work += nworkers) {
+        const WorkItem w = decode_work(p, work, NCTA, rank);
+        const int n0 = w.n_blk * BN + rank * Cfg::B_ROWS;       // first N row of this CTA's part of the B tile
         for (int ch = w.c0; ch < w.c1; ++ch)
         for (int seg = 0; seg < p.nseg; ++seg) {
         const int k_lo = ch * p.chain_kb, k_hi = min(k_lo + p.chain_kb, p.seg_kb[seg]);
         for (int kb = k_lo; kb < k_hi; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * NCTA);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &p.tma_a[seg], &full_bar[stage], kb * BK, w.m_blk * BM);
+            load(sa, &p.tma_a[seg], stage, kb * BK, w.m_blk * BM);
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c)
-              tma_load_2d(sa + c * (64 * BK * 2), &p.tma_a[seg], &full_bar[stage], w.m_blk * BM + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) load(sa + c * (64 * BK * 2), &p.tma_a[seg], stage, w.m_blk * BM + c * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &p.tma_b[seg], &full_bar[stage], kb * BK, w.n_blk * BN);
+            load(sb, &p.tma_b[seg], stage, kb * BK, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sb + c * (64 * BK * 2), &p.tma_b[seg], &full_bar[stage], w.n_blk * BN + c * 64, kb * BK);
+            for (int c = 0; c < Cfg::B_ROWS / 64; ++c) load(sb + c * (64 * BK * 2), &p.tma_b[seg], stage, n0 + c * 64, kb * BK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -312,13 +336,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (the leader CTA of a pair) =====================
+    if (rank == 0) {
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-      const WorkItem w = decode_work(p, work);
+    for (int work = worker; work < total_work; work += nworkers) {
+      const WorkItem w = decode_work(p, work, NCTA, rank);
       for (int ch = w.c0; ch < w.c1; ++ch) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
@@ -327,7 +352,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       for (int seg = 0; seg < p.nseg; ++seg) {
       const int k_lo = ch * p.chain_kb, k_hi = min(k_lo + p.chain_kb, p.seg_kb[seg]);
       const unsigned fl = p.seg_flags[seg];
-      const uint32_t idesc = umma_idesc_16b(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, fl & 1u, (fl >> 1) & 1u);
+      const uint32_t idesc = umma_idesc_16b(BM * NCTA, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, fl & 1u, (fl >> 1) & 1u);
       bool rescale = (fl & 4u) != 0;                     // fold the scaled low-order terms accumulated so far
       for (int kb = k_lo; kb < k_hi; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -344,10 +369,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                                         : umma_smem_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_base + k * 2048, 64 * BK * 2, 1024)
                                         : umma_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            if (rescale && !first && k == 0) umma_f16_ss_rescale11(tmem_d, adesc, bdesc, idesc);
-            else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
+            if constexpr (NCTA == 2) {
+              if (rescale && !first && k == 0) umma_f16_ss_rescale11_pair(tmem_d, adesc, bdesc, idesc);
+              else umma_bf16_ss_pair(tmem_d, adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
+            } else {
+              if (rescale && !first && k == 0) umma_f16_ss_rescale11(tmem_d, adesc, bdesc, idesc);
+              else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (!first || k > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (NCTA == 2) umma_commit_pair(&empty_bar[stage]);     // frees the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);
         }
         first = false;
         rescale = false;
@@ -355,11 +386,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       }
-      if (lane == 0) umma_commit(&tfull_bar[acc]);       // arrives once every MMA of this chain has completed
+      if (lane == 0) {                                   // arrives once every MMA of this chain has completed
+        if constexpr (NCTA == 2) umma_commit_pair(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
+      }
       __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
       }
+    }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -373,8 +408,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     float4* st = reinterpret_cast<float4*>(epi_smem + ew * EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-      const WorkItem w = decode_work(p, work);
+    const uint32_t tempty0 = NCTA == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;   // the leader's barriers
+    for (int work = worker; work < total_work; work += nworkers) {
+      const WorkItem w = decode_work(p, work, NCTA, rank);
       const int row0 = w.m_blk * BM + lane_grp * 32;                 // first row of this warp
       const int nbase = w.n_blk * BN + col_half * (BN / 2);
       for (int ch = w.c0; ch < w.c1; ++ch) {
@@ -526,7 +562,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (NCTA == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
       }
@@ -535,9 +574,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();            // neither CTA frees TMEM / exits while its peer still reads it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (NCTA == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

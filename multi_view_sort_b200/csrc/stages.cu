@@ -496,6 +496,124 @@ __global__ void __launch_bounds__(256, 2) ln1k_backward_rows_kernel(
 }
 
 
+// ------------------------------------------------------------------------------------------
+// enc1 backward, width 1024, rows AND columns in one pass (replaces ln1k_backward_rows_kernel<LN_ENC1> +
+// ln_backward_cols4_kernel<LN_ENC1>, which read G1 and the incoming gradient twice).  A block owns feature rows
+// (b, m) in a grid-stride loop and processes the NR = K latent rows that share one together: thread t owns columns
+// 4t..4t+3 of every row, so dxw1 and the four column reductions (dLN gamma/beta, d bias, d w1b3) are
+// thread-private accumulators, and the 2*NR row reductions of a group share one block barrier.
+// ------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
+    LnDesc d, int act, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+    const float* __restrict__ d_out, long long ldd, float* __restrict__ dgamma, float* __restrict__ dxw1, Planes dg1,
+    float* __restrict__ d_ln_g, float* __restrict__ d_ln_b, float* __restrict__ d_bias, float* __restrict__ d_w1b3) {
+  __shared__ float red[2][8][2 * NR];
+  __shared__ float red2[2][8][NR];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = tid * 4;
+  const int groups = d.rows / NR;
+  const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c), bias = ld4(d.bias + c);
+  const float4 w1b3 = d.C ? ld4(d.w1b3 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a_g = make_float4(0.f, 0.f, 0.f, 0.f), a_b = a_g, a_bias = a_g, a_w = a_g;
+  int par = 0;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x, par ^= 1) {
+    const int b = grp / d.mv, m = grp - b * d.mv;
+    const float4 xw = ld4(d.xw1 + static_cast<long long>(grp) * W1K + c);
+    float4 sv[NR], dy[NR];
+    float gam[NR], mean[NR], rstd[NR], part[2 * NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int row = (b * NR + k) * d.mv + m;
+      gam[k] = __ldg(d.gamma + row);
+      mean[k] = __ldg(mean_in + row);
+      rstd[k] = __ldg(rstd_in + row);
+      sv[k] = xw;
+      if (d.C) {
+        const float4 g1 = ld4(d.C + static_cast<long long>(row) * d.ldc + c);
+        sv[k] = make_float4(xw.x - g1.x - w1b3.x, xw.y - g1.y - w1b3.y, xw.z - g1.z - w1b3.z, xw.w - g1.w - w1b3.w);
+      }
+      dy[k] = ld4(d_out + static_cast<long long>(row) * ldd + c);
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int row = (b * NR + k) * d.mv + m;
+      float ds[4] = {1.f, 1.f, 1.f, 1.f};
+      if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * W1K + c, ds);
+      const float xh0 = (fmaf(gam[k], sv[k].x, bias.x) - mean[k]) * rstd[k], xh1 = (fmaf(gam[k], sv[k].y, bias.y) - mean[k]) * rstd[k];
+      const float xh2 = (fmaf(gam[k], sv[k].z, bias.z) - mean[k]) * rstd[k], xh3 = (fmaf(gam[k], sv[k].w, bias.w) - mean[k]) * rstd[k];
+      dy[k].x *= ds[0] * act_grad_fast(act, fmaf(xh0, g.x, bb.x));
+      dy[k].y *= ds[1] * act_grad_fast(act, fmaf(xh1, g.y, bb.y));
+      dy[k].z *= ds[2] * act_grad_fast(act, fmaf(xh2, g.z, bb.z));
+      dy[k].w *= ds[3] * act_grad_fast(act, fmaf(xh3, g.w, bb.w));
+      const float dx0 = dy[k].x * g.x, dx1 = dy[k].y * g.y, dx2 = dy[k].z * g.z, dx3 = dy[k].w * g.w;
+      part[2 * k] = warp_sum_f((dx0 + dx1) + (dx2 + dx3));
+      part[2 * k + 1] = warp_sum_f((dx0 * xh0 + dx1 * xh1) + (dx2 * xh2 + dx3 * xh3));
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 2 * NR; ++j) red[par][warp][j] = part[j];
+    }
+    __syncthreads();
+    float4 accx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dgam[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        c1 += red[par][w][2 * k];
+        c2 += red[par][w][2 * k + 1];
+      }
+      c1 *= (1.0f / W1K);
+      c2 *= (1.0f / W1K);
+      const int row = (b * NR + k) * d.mv + m;
+      const float xh[4] = {(fmaf(gam[k], sv[k].x, bias.x) - mean[k]) * rstd[k], (fmaf(gam[k], sv[k].y, bias.y) - mean[k]) * rstd[k],
+                           (fmaf(gam[k], sv[k].z, bias.z) - mean[k]) * rstd[k], (fmaf(gam[k], sv[k].w, bias.w) - mean[k]) * rstd[k]};
+      float4 dv;
+      dv.x = rstd[k] * (dy[k].x * g.x - c1 - xh[0] * c2);
+      dv.y = rstd[k] * (dy[k].y * g.y - c1 - xh[1] * c2);
+      dv.z = rstd[k] * (dy[k].z * g.z - c1 - xh[2] * c2);
+      dv.w = rstd[k] * (dy[k].w * g.w - c1 - xh[3] * c2);
+      dgam[k] = (dv.x * sv[k].x + dv.y * sv[k].y) + (dv.z * sv[k].z + dv.w * sv[k].w);
+      accx.x = fmaf(gam[k], dv.x, accx.x); accx.y = fmaf(gam[k], dv.y, accx.y);
+      accx.z = fmaf(gam[k], dv.z, accx.z); accx.w = fmaf(gam[k], dv.w, accx.w);
+      const float4 ng = make_float4(-gam[k] * dv.x, -gam[k] * dv.y, -gam[k] * dv.z, -gam[k] * dv.w);
+      if (dg1.n) store_planes4(dg1, static_cast<long long>(row) * W1K + c, ng);
+      a_g.x = fmaf(dy[k].x, xh[0], a_g.x); a_g.y = fmaf(dy[k].y, xh[1], a_g.y);
+      a_g.z = fmaf(dy[k].z, xh[2], a_g.z); a_g.w = fmaf(dy[k].w, xh[3], a_g.w);
+      a_b.x += dy[k].x; a_b.y += dy[k].y; a_b.z += dy[k].z; a_b.w += dy[k].w;
+      a_bias.x += dv.x; a_bias.y += dv.y; a_bias.z += dv.z; a_bias.w += dv.w;
+      a_w.x += ng.x; a_w.y += ng.y; a_w.z += ng.z; a_w.w += ng.w;
+    }
+    if (dxw1) {
+      float4* px = reinterpret_cast<float4*>(dxw1 + static_cast<long long>(grp) * W1K + c);
+      float4 a = *px;
+      a.x += accx.x; a.y += accx.y; a.z += accx.z; a.w += accx.w;
+      *px = a;
+    }
+    if (dgamma) {
+#pragma unroll
+      for (int k = 0; k < NR; ++k) {
+        const float t = warp_sum_f(dgam[k]);
+        if (lane == 0) red2[par][warp][k] = t;
+      }
+      __syncthreads();
+      if (tid < NR) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red2[par][w][tid];
+        dgamma[(b * NR + tid) * d.mv + m] = t;
+      }
+    }
+  }
+  atomicAdd(reinterpret_cast<float4*>(d_ln_g + c), a_g);
+  atomicAdd(reinterpret_cast<float4*>(d_ln_b + c), a_b);
+  atomicAdd(reinterpret_cast<float4*>(d_bias + c), a_bias);
+  if (d_w1b3) atomicAdd(reinterpret_cast<float4*>(d_w1b3 + c), a_w);
+}
+
+
 // Backward rows for the wide LN_BIAS stages (4096, 1024*M): one block of width/16 threads per row, four
 // float4 per thread cached in registers between the reduction pass and the output pass.
 __global__ void __launch_bounds__(1024) lnw_backward_rows_kernel(LnDesc d, int act, const float* __restrict__ mean_in,
@@ -1167,6 +1285,34 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
   else
     ln_backward_cols4_kernel<LN_ENC1><<<grid, 128, 0, stream>>>(d, act, mean, rstd, c1, c2, d_out, ldd, rpb, d_ln_g, d_ln_b,
                                                                  d_bias, d_w1b3);
+  VMM_LAUNCHED();
+  return 0;
+}
+
+int enc1_backward_fused(int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out, long long ldd,
+                        float* dgamma, float* dxw1, const Planes& dg1, float* d_ln_g, float* d_ln_b, float* d_bias,
+                        float* d_w1b3, cudaStream_t stream) {
+  VMM_TRY(check_ln(d, LN_ENC1));
+  const int K = d.km / d.mv;
+  VMM_REQUIRE(enc1_backward_fused_ok(d.width, K), "enc1_backward_fused: needs width 1024 and 1 <= K <= 6");
+  VMM_REQUIRE(mean && rstd && d_out && ldd % 4 == 0 && d_ln_g && d_ln_b && d_bias, "enc1_backward_fused: null argument");
+  VMM_REQUIRE(((reinterpret_cast<uintptr_t>(d_ln_g) | reinterpret_cast<uintptr_t>(d_ln_b) |
+                reinterpret_cast<uintptr_t>(d_bias) | reinterpret_cast<uintptr_t>(d_w1b3)) & 15) == 0,
+              "enc1_backward_fused: gradient buffers must be 16-byte aligned");
+  const int groups = d.rows / K;
+  const int blocks = std::min(groups, device_sm_count() * 2);
+#define VMM_ENC1B(NR)                                                                                                  \
+  enc1_backward_fused_kernel<NR><<<blocks, 256, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dgamma, dxw1, dg1, d_ln_g, \
+                                                             d_ln_b, d_bias, d_w1b3)
+  switch (K) {
+    case 1: VMM_ENC1B(1); break;
+    case 2: VMM_ENC1B(2); break;
+    case 3: VMM_ENC1B(3); break;
+    case 4: VMM_ENC1B(4); break;
+    case 5: VMM_ENC1B(5); break;
+    default: VMM_ENC1B(6); break;
+  }
+#undef VMM_ENC1B
   VMM_LAUNCHED();
   return 0;
 }

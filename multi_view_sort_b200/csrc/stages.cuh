@@ -81,6 +81,12 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
                      const float* c2, const float* d_out, long long ldd, float* d_ln_g, float* d_ln_b, float* d_bias,
                      float* d_w1b3, cudaStream_t stream);
 
+// enc1 (LN_ENC1, width 1024, K <= 6): ln_backward_rows + ln_backward_cols in ONE pass over G1 and d_out.
+inline bool enc1_backward_fused_ok(int width, int k_latent) { return width == 1024 && k_latent >= 1 && k_latent <= 6; }
+int enc1_backward_fused(int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out, long long ldd,
+                        float* dgamma, float* dxw1, const Planes& dg1, float* d_ln_g, float* d_ln_b, float* d_bias,
+                        float* d_w1b3, cudaStream_t stream);
+
 // GRUCell gate math (train_nem.py:177,232; torch.nn.GRUCell, gate order r,z,n).
 // gi = e Wih^T, gh = h Whh^T are the raw contraction outputs [rows, 3H] (biases added here).
 int gru_forward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,

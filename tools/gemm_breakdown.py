@@ -12,6 +12,7 @@ class Rec(C.Structure):
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+if len(sys.argv) > 3: lib().vmm_gemm_force_ncta(int(sys.argv[3]))   # 1 = single CTAs, 2 = CTA pairs
 dev = torch.device("cuda")
 nem, head = bench.build_models(prec, dev)
 x = torch.relu(torch.randn(B, 12, 4096, device=dev)).to(torch.bfloat16 if prec.startswith("bf16") else torch.float32)
