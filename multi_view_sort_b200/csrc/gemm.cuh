@@ -129,6 +129,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ float ex2_approx(float x) {          // one MUFU; flushes results below 2^-126 to zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
   __half2 t = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
   return *reinterpret_cast<uint32_t*>(&t);
@@ -145,22 +150,33 @@ struct XRegs {
   uint4 v[sizeof(XT) == 4 ? 8 : 4];
 };
 
+// Feature-row pointers of the rows a lane fetches (constant over the chunks of one tile; the integer
+// divisions of the row map are paid once per tile, not once per chunk).
 template <typename XT>
-__device__ __forceinline__ void x_fetch(const GemmParams& p, XRegs<XT>& xr, int row0, int col0, int lane) {
+struct XRows {
+  const XT* p[sizeof(XT) == 4 ? 8 : 4];
+};
+template <typename XT>
+__device__ __forceinline__ void x_rows(const GemmParams& p, XRows<XT>& xr, int row0, int lane) {
   constexpr int NI = sizeof(XT) == 4 ? 8 : 4;
-  constexpr int RPI = 32 / NI;             // rows covered per instruction: 4 (fp32) or 8 (bf16)
-  constexpr int LPR = 32 / RPI;            // lanes per row: 8 or 4
-  constexpr int EPL = 16 / sizeof(XT);     // elements per lane: 4 or 8
+  constexpr int RPI = 32 / NI, LPR = 32 / RPI, EPL = 16 / sizeof(XT);
   const XT* x = static_cast<const XT*>(p.x);
 #pragma unroll
   for (int j = 0; j < NI; ++j) {
-    const int r = j * RPI + lane / LPR, cc = (lane % LPR) * EPL;
-    const int grow = row0 + r, gcol = col0 + cc;
+    const int grow = row0 + j * RPI + lane / LPR;
+    xr.p[j] = nullptr;
+    if (grow < p.M) xr.p[j] = x + (static_cast<long long>(grow / p.km) * p.mv + grow % p.mv) * p.ldx + (lane % LPR) * EPL;
+  }
+}
+template <typename XT>
+__device__ __forceinline__ void x_fetch(const GemmParams& p, XRegs<XT>& xr, const XRows<XT>& rows, int col0, int lane) {
+  constexpr int NI = sizeof(XT) == 4 ? 8 : 4;
+  constexpr int RPI = 32 / NI, LPR = 32 / RPI, EPL = 16 / sizeof(XT);
+  const bool col_ok = col0 + (lane % LPR) * EPL < p.N;
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (grow < p.M && gcol < p.N) {
-      const long long xrow = static_cast<long long>(grow / p.km) * p.mv + grow % p.mv;
-      v = __ldg(reinterpret_cast<const uint4*>(x + xrow * p.ldx + gcol));
-    }
+    if (rows.p[j] && col_ok) v = __ldg(reinterpret_cast<const uint4*>(rows.p[j] + col0));
     xr.v[j] = v;
   }
 }
@@ -428,7 +444,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         }
       }
       XRegs<XT> xr;
-      if constexpr (kFused) x_fetch<XT>(p, xr, row0, nbase, lane);   // overlaps the wait for the MMAs
+      XRows<XT> xrows;
+      float4 mybias = make_float4(0.f, 0.f, 0.f, 0.f);               // b3 of this warp's 128 columns, 4 per lane
+      if constexpr (kFused) {
+        x_rows<XT>(p, xrows, row0, lane);
+        x_fetch<XT>(p, xr, xrows, nbase, lane);                      // overlaps the wait for the MMAs
+        if (nbase + lane * 4 < p.N) mybias = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + lane * 4));
+      }
+      const bool want_sq = kFused && (EPI == EPI_ESTEP) && p.part_sq != nullptr;   // last iteration only
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -447,28 +470,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0);
           } else {
             x_stage<XT>(xr, st, lane);
-            if (c + 1 < NCH) x_fetch<XT>(p, xr, row0, col0 + 32, lane);
+            if (c + 1 < NCH) x_fetch<XT>(p, xr, xrows, col0 + 32, lane);
             __syncwarp();
             float out[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 xv = st[st_slot(lane, j)];
-              const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (col0 + j * 4 < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
-              const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+              if (col0 + j * 4 < p.N) {                              // warp-uniform; N is a multiple of 4
+                const float4 xv = st[st_slot(lane, j)];
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                const int src = c * 8 + j;                           // lane holding this float4 of the bias
+                const float bs[4] = {__shfl_sync(0xffffffffu, mybias.x, src), __shfl_sync(0xffffffffu, mybias.y, src),
+                                     __shfl_sync(0xffffffffu, mybias.z, src), __shfl_sync(0xffffffffu, mybias.w, src)};
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const bool ok = (col0 + j * 4 + q) < p.N;
-                const float pred = __uint_as_float(v[4 * j + q]) + bs[q];
-                const float d = xs[q] - pred;
-                const float e = exp2f(d * d * p.exp_scale);
-                if constexpr (EPI == EPI_ESTEP) {
-                  if (ok) { sum_e += e; sum_sq = fmaf(d, d, sum_sq); sum_pp = fmaf(pred, pred, sum_pp); }
-                  if constexpr (kSave != 0) out[4 * j + q] = ok ? d : 0.f;
-                } else {
-                  out[4 * j + q] = ok ? fmaf(d, fmaf(alpha, e, -beta), kappa * pred) : 0.f;
+                for (int q = 0; q < 4; ++q) {
+                  const float pred = __uint_as_float(v[4 * j + q]) + bs[q];
+                  const float d = xs[q] - pred;
+                  const float dd = d * d;
+                  const float e = ex2_approx(dd * p.exp_scale);
+                  if constexpr (EPI == EPI_ESTEP) {
+                    sum_e += e;
+                    if (want_sq) { sum_sq += dd; sum_pp = fmaf(pred, pred, sum_pp); }
+                    if constexpr (kSave != 0) out[4 * j + q] = d;
+                  } else {
+                    out[4 * j + q] = fmaf(d, fmaf(alpha, e, -beta), kappa * pred);
+                  }
                 }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) out[4 * j + q] = 0.f;
               }
             }
             __syncwarp();                                            // all lanes have consumed their x row

@@ -77,6 +77,7 @@ PRECISIONS = {
     # E-step backward by recomputing pred (one more dec3 contraction per iteration) instead of streaming over the
     # saved fp32 delta = x - pred: numerically identical, 12 % slower, 6 MB/object-iteration less workspace
     "bf16_recompute": (2, 1, 1, 16, 0, 0),
+    "bf16_pair_dec3": (2, 1, 1, 16, 0, 2),   # "bf16" without the sigma rule: dec3 always on the fp16 pair
     "fp32_recompute": (2, 1, 2, 16, 0, 0),
     "bf16_delta16": (2, 1, 1, 16, 0, 1),  # fp16 delta: half the delta traffic, gradients ~2e-3 further from the reference
 }
@@ -103,6 +104,24 @@ def precision_planes(precision):
     return t + (0, 0)[len(t) - 4:] if len(t) < 6 else t
 
 
+# dec3 feeds ONLY the E-step (sum_d exp(-(x - pred)^2 / 2 sigma^2)) and the loss: its rounding errors average over
+# the D feature columns instead of entering the recurrent state, so it is the one forward contraction that
+# tolerates a single fp16 pass - as long as the E-step's gain 1/sigma^2 is moderate.  Measured with exact
+# gradient contractions (tools/mode_sweep.py fp32): single-pass dec3 adds 5e-5 (cfg1) / 2e-4 (prior0) of gradient
+# error at sigma = 0.1 and 2e-1 at sigma = 0.02, i.e. ~2e-4 * (0.1 / sigma)^4.  The bf16-features preset (bar 1e-2)
+# therefore runs dec3 in one pass when sigma >= DEC3_SINGLE_MIN_SIGMA (contribution <= 1e-3) and keeps the fp16
+# pair below it; every other forward contraction needs the pair (single pass: 5e-2 .. 1e-1 gradient error).
+DEC3_SINGLE_MIN_SIGMA = 0.07
+
+
+def resolve_precision(module):
+    """precision_planes(module.precision) with the sigma rule of the "bf16" preset applied."""
+    t = precision_planes(module.precision)
+    if module.precision == "bf16" and float(module.e_sigma) >= DEC3_SINGLE_MIN_SIGMA:
+        t = t[:4] + (t[4] | fwd_modes(dec3=FWD_SINGLE), t[5])
+    return t
+
+
 def dropout_args(module):
     """(p, seed) of this call: p = 0.5 in train mode (the reference's nn.Dropout(0.5)), 0 in eval mode.  The seed
     is `module.dropout_seed` when set (tests), else derived from torch's seed and a per-module call counter."""
@@ -118,7 +137,7 @@ def dropout_args(module):
 
 
 def make_config(module, B, T, x_is_bf16, training) -> EMConfig:
-    planes, f16, planes_bwd, chain, modes, save_delta = precision_planes(module.precision)
+    planes, f16, planes_bwd, chain, modes, save_delta = resolve_precision(module)
     drop_p, drop_seed = dropout_args(module)
     return EMConfig(fwd_modes=modes, save_delta=save_delta, B=B, K=module.k, M=module.m, D=module.input_dim, H=module.rnn_hidden_size, T=T, planes=planes,
                     planes_bwd=planes_bwd, fwd_fp16=f16,
