@@ -126,3 +126,42 @@ class PackedFeatures:
         index = np.random.RandomState(seed).permutation(n) if shuffle else None
         for lo in range(0, n, batch_size):
             yield self.batch(lo, min(n, lo + batch_size), index)
+
+
+class DevicePrefetcher:
+    """Double-buffered host->device feeder for the training / export loops: while step i computes, batch i+1 is
+    copied on a side stream (pinned source -> truly asynchronous), so the copy (403 MB of bf16 features per 4096
+    objects, ~8 ms over PCIe 5) leaves the critical path.  Items are tuples; tensors are moved, anything else
+    (the reference's file paths) is passed through."""
+
+    def __init__(self, loader, device=None):
+        self.loader = loader
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _load(self, it):
+        try:
+            item = next(it)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(self.stream):
+            out = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in item)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return out, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        nxt = self._load(it)
+        while nxt is not None:
+            cur, ev = nxt
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(ev)
+            for t in cur:
+                if torch.is_tensor(t):
+                    t.record_stream(main)          # the side stream's allocator must not reuse it while the step runs
+            nxt = self._load(it)                    # next batch's copy overlaps this step
+            yield cur

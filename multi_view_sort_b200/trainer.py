@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from .dist import GradBucket
+from .features import DevicePrefetcher
 from .nem_utilities import clip_gradient
 
 
@@ -91,7 +92,7 @@ class ModelNetTrainer(object):
             lr = self.optimizer.state_dict()['param_groups'][0]['lr']
             if self.writer:
                 self.writer.add_scalar('params/lr', lr, epoch)
-            for i, i_data in enumerate(self.train_loader):
+            for i, i_data in enumerate(DevicePrefetcher(self.train_loader)):     # batch i+1 is copied while step i runs
                 start = time.time()
                 in_data = i_data[1]
                 if in_data.dim() != 3:
