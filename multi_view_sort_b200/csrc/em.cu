@@ -209,6 +209,21 @@ inline Planes sel_w(const Dims& d, int fc, const Planes& w) {
   return (m == VMM_FWD_SINGLE || m == VMM_FWD_ACT_PAIR) ? w.first(1) : w;
 }
 
+// The operand planes a streaming stage has to WRITE for activation `o`: in training everything (forward planes +
+// the bf16 set of the gradient contractions); in forward-only runs no gradient set, and only the leading forward
+// plane when every contraction that reads the activation runs single-pass.
+inline Op fwd_out(const Dims& d, bool training, const Op& o, int fc_a, int fc_b = -1) {
+  if (training) return o;
+  Op r = o;
+  r.b = Planes();
+  auto single = [&](int fc) {
+    const unsigned m = (d.modes >> (2 * fc)) & 3u;
+    return m == VMM_FWD_SINGLE || m == VMM_FWD_W_PAIR;
+  };
+  if (single(fc_a) && (fc_b < 0 || single(fc_b))) r.f = o.f.first(1);
+  return r;
+}
+
 // y[rows, n] = a[rows, k] * w[n, k]^T        (nn.Linear forward; bias is added by the consumer stage)
 int linear_fwd(const Dims& d, int fc, const Planes& a_all, const Planes& w_all, long long rows, int n, long long k, float* y,
                cudaStream_t st) {
@@ -292,6 +307,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
   Workspace ws(*c, workspace);
   Scratch sc(*c, scratch);
   const float eps = c->ln_eps;
+  const bool tr = c->training != 0;
 
   // operand planes of the features and W1 x (once per batch)
   Op xp = ws.x;
@@ -321,25 +337,25 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
       ln.gamma = gam_prev;
       ln.km = d.K * d.M;
       ln.mv = d.M;
-      VMM_TRY(ln_forward(LN_ENC1, ACT_ELU, ln, cur.a, cur.mean1, cur.rstd1, st));
+      VMM_TRY(ln_forward(LN_ENC1, ACT_ELU, ln, fwd_out(d, tr, cur.a, FC_ENC2), cur.mean1, cur.rstd1, st));
     }
     // --- enc2 (train_nem.py:228-229)
     VMM_TRY(linear_fwd(d, FC_ENC2, cur.a.f, w.w2.f, d.R, E2, d.ZW, cur.g2, st));
-    VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps, c, ST_ENC2, t), cur.e,
-                       cur.mean2, cur.rstd2, st));
+    VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps, c, ST_ENC2, t),
+                       fwd_out(d, tr, cur.e, FC_GI), cur.mean2, cur.rstd2, st));
     // --- GRU (train_nem.py:232)
     VMM_TRY(linear_fwd(d, FC_GI, cur.e.f, w.wih.f, d.R, 3 * d.H, E2, cur.gi, st));
     if (t > 0) VMM_TRY(linear_fwd(d, FC_GH, prev.hp.f, w.whh.f, d.R, 3 * d.H, d.H, cur.gh, st));
     else VMM_CHECK_CUDA(cudaMemsetAsync(cur.gh, 0, sizeof(float) * d.R * 3 * d.H, st));
     VMM_TRY(gru_forward(static_cast<int>(d.R), d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, t > 0 ? prev.h : ws.h0, cur.h,
-                        cur.hp, st));
+                        fwd_out(d, tr, cur.hp, FC_GH, FC_DEC1), st));
     // --- dec1, dec2 (train_nem.py:238-240)
     VMM_TRY(linear_fwd(d, FC_DEC1, cur.hp.f, w.w4.f, d.R, E2, d.H, cur.g4, st));
-    VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps, c, ST_DEC1, t), cur.u,
-                       cur.mean4, cur.rstd4, st));
+    VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps, c, ST_DEC1, t),
+                       fwd_out(d, tr, cur.u, FC_DEC2), cur.mean4, cur.rstd4, st));
     VMM_TRY(linear_fwd(d, FC_DEC2, cur.u.f, w.w5.f, d.R, static_cast<int>(d.ZW), E2, cur.g5, st));
-    VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps), cur.z,
-                       cur.mean5, cur.rstd5, st));
+    VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps),
+                       fwd_out(d, tr, cur.z, FC_DEC3, FC_G1), cur.mean5, cur.rstd5, st));
     // --- dec3 fused with the E-step (train_nem.py:241-270)
     const bool want_pp = last && c->if_gamma_prior == 0;
     VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, sel_act(d, FC_DEC3, cur.z.f), sel_w(d, FC_DEC3, w.w3.f), p->dec3_b, x,

@@ -146,6 +146,35 @@ def test_run_em_bf16_fast_forward():
     assert abs(nem_loss.item() - float(z["nem_loss"])) < 1e-3 * abs(float(z["nem_loss"]))
 
 
+@pytest.mark.parametrize("name", ["cfg1_b8_k3_m12_t10", "prior0_b5_k2_m12_t3", "peaky_b6_k4_m12_t4"])
+def test_bf16_inference_single_pass(name):
+    """Forward-only calls of the bf16-features preset run every contraction in ONE fp16 pass when sigma >= 0.07
+    (fp16 pair otherwise - the 'peaky' case): descriptors h_T, responsibilities and the 4096-d head descriptor within
+    north_star's 1e-2 of the oracle on the same bf16-rounded features, identical argmax class predictions."""
+    from multi_view_sort_b200.functional import resolve_precision, fwd_modes, FWD_CONTRACTIONS, FWD_SINGLE
+    _, cfg = load_golden(name)
+    nem, head = seeded_models(cfg)
+    x, y = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    xb = x.bfloat16()
+    pn, ph = params_of(nem), params_of(head)
+    with torch.no_grad():
+        r = O.run_em(pn, xb.float(), cfg["K"], cfg["T"], cfg["sigma"], "bin_uniform", cfg["if_gamma_prior"], cfg["stop_gamma_grad"])
+        ref_logits = O.head_forward(ph, r["h"], r["gamma"], cfg["K"], cfg["if_sort"], cfg["if_pooling"])
+    nem, head = nem.cuda().eval(), head.cuda().eval()
+    nem.precision = head.precision = "bf16"
+    all_single = fwd_modes(**{n: FWD_SINGLE for n in FWD_CONTRACTIONS})
+    assert (resolve_precision(nem, training=False)[4] == all_single) == (cfg["sigma"] >= 0.07)
+    with torch.no_grad():
+        h, gamma, nem_loss, _, _ = nem.run_em(xb.cuda(), cfg["T"])
+        logits = head(h, gamma)
+    tol = 4e-2 if name.startswith("peaky") else 1e-2            # see test_train_step_fp32_mode_matches_reference_golden
+    assert rel_err(h, r["h"]) < 1e-2
+    assert rel_err(gamma.reshape(r["gamma"].shape), r["gamma"]) < 1e-2
+    assert abs(nem_loss.item() - r["nem_loss"].item()) < 1e-2 * abs(r["nem_loss"].item())
+    assert rel_err(logits, ref_logits) < tol
+    assert (logits.argmax(1).cpu() == ref_logits.argmax(1)).all(), "argmax class predictions differ"
+
+
 def test_run_em_matches_reference_golden():
     """CUDA fp32-mode forward against the frozen outputs of the UNMODIFIED reference."""
     name = "cfg1_b8_k3_m12_t10"
