@@ -77,7 +77,9 @@ PRECISIONS = {
     # E-step backward by recomputing pred (one more dec3 contraction per iteration) instead of streaming over the
     # saved fp32 delta = x - pred: numerically identical, 12 % slower, 6 MB/object-iteration less workspace
     "bf16_recompute": (2, 1, 1, 16, 0, 0),
-    "bf16_pair_dec3": (2, 1, 1, 16, 0, 2),   # "bf16" without the sigma rule: dec3 always on the fp16 pair
+    "bf16_pair_dec3": (2, 1, 1, 16, 0, 2),
+    "bf16_chain32": (2, 1, 1, 32, 1 << 14, 2),   # timing probes of the accumulation-chain bound (dec3 single-pass)
+    "bf16_chain0": (2, 1, 1, 0, 1 << 14, 2),   # "bf16" without the sigma rule: dec3 always on the fp16 pair
     "fp32_recompute": (2, 1, 2, 16, 0, 0),
     "bf16_delta16": (2, 1, 1, 16, 0, 1),  # fp16 delta: half the delta traffic, gradients ~2e-3 further from the reference
 }

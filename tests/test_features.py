@@ -74,3 +74,23 @@ def test_cli_flags_match_reference():
         for k, v in ref_opts.items():
             assert k in opts, f"reference flag {k} missing"
             assert opts[k] == v, (k, opts[k], v)
+
+
+def test_precision_rules_of_the_bf16_preset():
+    """Host logic of functional.resolve_precision: the sigma rule picks single-pass dec3 for training and
+    all-single-pass contractions for forward-only calls iff sigma >= 0.07; other presets are never touched."""
+    from types import SimpleNamespace as NS
+    from multi_view_sort_b200.functional import (DEC3_SINGLE_MIN_SIGMA, FWD_CONTRACTIONS, FWD_SINGLE, PRECISIONS, fwd_modes,
+                                                 precision_planes, resolve_precision)
+    assert precision_planes((1, 0, 1, 0)) == (1, 0, 1, 0, 0, 0)
+    assert precision_planes("fp32") == PRECISIONS["fp32"]
+    dec3 = fwd_modes(dec3=FWD_SINGLE)
+    every = fwd_modes(**{n: FWD_SINGLE for n in FWD_CONTRACTIONS})
+    assert dec3 == 1 << 14 and every == 0x15555
+    hi, lo = NS(precision="bf16", e_sigma=0.1), NS(precision="bf16", e_sigma=0.02)
+    assert resolve_precision(hi, True)[4] == dec3 and resolve_precision(hi, False)[4] == every
+    assert resolve_precision(lo, True)[4] == 0 and resolve_precision(lo, False)[4] == 0
+    assert resolve_precision(NS(precision="bf16", e_sigma=DEC3_SINGLE_MIN_SIGMA), True)[4] == dec3
+    for name in ("fp32", "fp32_strict", "bf16_fast"):
+        m = NS(precision=name, e_sigma=0.1)
+        assert resolve_precision(m, True) == resolve_precision(m, False) == precision_planes(name)

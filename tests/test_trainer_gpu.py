@@ -47,3 +47,18 @@ def test_train_then_export(tmp_path, monkeypatch):
         h, gamma, *_ = nem.run_em(x)
         d1 = head(h, gamma).cpu().numpy()
     assert np.abs(d1 - d0).max() <= 2e-3 * np.abs(d0).max()       # bf16 preset, batch 1 vs batch 8 reduction order
+
+
+def test_device_prefetcher_order_and_values():
+    """DevicePrefetcher yields the loader's batches in order, on the device, bit-identical, passing non-tensors through."""
+    from multi_view_sort_b200.features import DevicePrefetcher
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randint(0, 10, (4,), generator=g), torch.randn(4, 12, 64, generator=g).pin_memory(), [f"p{i}"] * 4)
+               for i in range(5)]
+    seen = 0
+    for i, (y, x, paths) in enumerate(DevicePrefetcher(batches)):
+        assert x.is_cuda and y.is_cuda and paths == batches[i][2]
+        x = x * 1.0                                  # consume on the compute stream
+        assert torch.equal(x.cpu(), batches[i][1]) and torch.equal(y.cpu(), batches[i][0])
+        seen += 1
+    assert seen == 5 and len(DevicePrefetcher(batches)) == 5
