@@ -12,10 +12,11 @@
  *     several host threads, one stream per call;
  *   - all work is enqueued on `stream`; nothing synchronises the device.
  *
- * "Operand planes": matrices consumed by the tensor cores are bf16.  One plane is plain bf16;
- * with n planes every operand is stored as n successive bf16 residuals and every contraction
- * sums the cross terms A_i * B_j with i + j < n (3 passes for n = 2, 6 for n = 3) with fp32
- * accumulation in TMEM.  n = 3 reproduces the reference's fp32 arithmetic.
+ * "Operand planes": matrices consumed by the tensor cores are 16-bit.  VMM_FMT_BF16: one plane is plain
+ * bf16; with n planes every operand is stored as n successive bf16 residuals and every contraction sums
+ * the cross terms A_i * B_j with i + j < n (3 passes for n = 2, 6 for n = 3) with fp32 accumulation in
+ * TMEM; n = 3 reproduces the reference's fp32 arithmetic.  VMM_FMT_F16PAIR: an fp16 hi/lo pair gives the
+ * same accuracy in 3 passes (see below) and is what the forward pass of the fp32 / bf16 presets uses.
  */
 #ifndef VMM_B200_H_
 #define VMM_B200_H_

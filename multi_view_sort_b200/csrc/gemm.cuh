@@ -267,7 +267,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   constexpr bool kFused = (EPI == EPI_ESTEP || EPI == EPI_EBWD);
   constexpr int kSave = (EPI == EPI_ESTEP) ? OPL - 1 : 0;     // 0: no delta output, 1: fp16, 2: fp32
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array - NOT through an integer
+  // round trip, which makes the compiler lose the address space and emit generic LD/ST for all staging traffic
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;

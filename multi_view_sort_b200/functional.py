@@ -61,27 +61,28 @@ def _bytes(fn, cfg) -> int:
     return int(n)
 
 
-# precision name -> (forward operand planes, forward planes are fp16 pairs, bf16 planes of the gradient
-# contractions, accumulation-chain bound in 64-wide K blocks).  Measured on B200 against the reference
-# (tests/test_em_gpu.py, tools/precision_sweep.py): the E-step amplifies forward errors by 1/sigma^2 and
-# dec1's ReLU turns them into gradient flips, so the forward pass needs fp32-class operands (an fp16
-# hi/lo pair = 22 mantissa bits in 3 tensor-core passes) and short accumulation chains, while the
-# gradient contractions get by with fewer bits.
+# precision name -> (forward operand planes, forward planes are fp16 pairs, bf16 planes of the gradient contractions,
+# accumulation-chain bound in 64-wide K blocks, per-contraction forward modes, delta storage).  Measured on B200
+# against the reference (tests/test_em_gpu.py, tools/precision_sweep.py, tools/mode_sweep.py): the E-step amplifies
+# forward errors by 1/sigma^2 and dec1's ReLU turns them into gradient flips, so a forward pass that a backward pass
+# follows needs fp32-class operands (an fp16 hi/lo pair = 22 mantissa bits in 3 tensor-core passes) and short
+# accumulation chains, while the gradient contractions get by with fewer bits.  resolve_precision() below applies
+# the sigma rule of the "bf16" preset on top of this table.
 PRECISIONS = {
-    # (forward planes, fp16 pair, backward bf16 planes, chain, fwd_modes, save_delta)
     "fp32": (2, 1, 2, 16, 0, 2),          # fp32-class forward, 2 bf16 planes backward        (tolerance 1e-4)
     "fp32_strict": (2, 1, 3, 4, 0, 2),    # + 3 bf16 planes backward, 256-element chains
     "bf16": (2, 1, 1, 16, 0, 2),          # "bf16 features" mode: fp32-class forward, bf16 gradients (1e-2)
     "bf16_fast": (1, 0, 1, 0, 0, 1),      # single-pass bf16 everywhere: inference grade (h ~2e-2)
     "fp32_bf16planes": (3, 0, 2, 16, 0, 2),   # the same accuracy from 3 bf16 residual planes (6 forward passes)
+    # ---- A/B variants (tools/) ----
     # E-step backward by recomputing pred (one more dec3 contraction per iteration) instead of streaming over the
-    # saved fp32 delta = x - pred: numerically identical, 12 % slower, 6 MB/object-iteration less workspace
+    # saved fp32 delta = x - pred: numerically identical, 12 % slower, 0.59 MB/object-iteration less workspace
     "bf16_recompute": (2, 1, 1, 16, 0, 0),
-    "bf16_pair_dec3": (2, 1, 1, 16, 0, 2),
-    "bf16_chain32": (2, 1, 1, 32, 1 << 14, 2),   # timing probes of the accumulation-chain bound (dec3 single-pass)
-    "bf16_chain0": (2, 1, 1, 0, 1 << 14, 2),   # "bf16" without the sigma rule: dec3 always on the fp16 pair
     "fp32_recompute": (2, 1, 2, 16, 0, 0),
-    "bf16_delta16": (2, 1, 1, 16, 0, 1),  # fp16 delta: half the delta traffic, gradients ~2e-3 further from the reference
+    "bf16_delta16": (2, 1, 1, 16, 0, 1),         # fp16 delta: half the delta traffic, gradients ~2e-3 further off
+    "bf16_pair_dec3": (2, 1, 1, 16, 0, 2),       # "bf16" without the sigma rule: dec3 always on the fp16 pair
+    "bf16_chain32": (2, 1, 1, 32, 1 << 14, 2),   # timing probes of the chain bound (dec3 single-pass): -1 % / -2.4 %
+    "bf16_chain0": (2, 1, 1, 0, 1 << 14, 2),     #   of the step time, but chain 64 / 0 fail the sigma = 0.02 case
 }
 
 
