@@ -158,15 +158,22 @@ def make_config(module, B, T, x_is_bf16, training) -> EMConfig:
 
 
 class _WeightCache:
-    """bf16 operand planes of the weights (+ the W1*W3 fold), rebuilt only when a parameter changed."""
+    """Operand planes of the weights (+ the W1*W3 fold).  Forward-only calls reuse them while no parameter changed
+    (data pointer + autograd version).  Training calls ALWAYS rebuild them, and a backward pass marks them stale:
+    fused optimizers (torch.optim.Adam(fused=True), the multi-tensor CUDA kernels) update parameters in place
+    WITHOUT bumping the version counter (measured), so a version-keyed cache would keep serving the planes of the
+    previous step.  Rebuilding costs ~0.35 ms per step (1.3 GB of streaming) at configs[1]."""
 
     def __init__(self):
         self.key = None
         self.buf = None
 
-    def get(self, cfg: EMConfig, params):
+    def invalidate(self):
+        self.key = None
+
+    def get(self, cfg: EMConfig, params, force=False):
         key = (cfg.planes, cfg.planes_bwd, cfg.fwd_fp16, cfg.accum_chain, cfg.M, cfg.D, cfg.H) + tuple((p.data_ptr(), p._version) for p in params)
-        if key != self.key:
+        if force or key != self.key:
             nbytes = _bytes(lib().vmm_em_weights_bytes, cfg)
             if self.buf is None or self.buf.numel() < nbytes or self.buf.device != params[0].device:
                 self.buf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
@@ -191,7 +198,7 @@ class _EMFunction(torch.autograd.Function):
         dev = x.device
         cfg = make_config(module, B, T, x.dtype == torch.bfloat16, training)
         with torch.cuda.device(dev):
-            weights = _weight_cache(module).get(cfg, params)
+            weights = _weight_cache(module).get(cfg, params, force=bool(training))
             ws = torch.empty(_bytes(lib().vmm_em_workspace_bytes, cfg), dtype=torch.uint8, device=dev)
             scratch = torch.empty(_bytes(lib().vmm_em_scratch_bytes, cfg), dtype=torch.uint8, device=dev)
             h = torch.empty(B * cfg.K, cfg.H, device=dev)
@@ -222,6 +229,7 @@ class _EMFunction(torch.autograd.Function):
             d_loss = d_loss.contiguous().float() if d_loss is not None else torch.zeros(3, device=dev)
             check(lib().vmm_em_backward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(x), ptr(gamma0), ptr(prior), ptr(ws),
                                         ptr(scratch), ptr(d_h), ptr(d_gamma), ptr(d_loss), C.byref(gp), stream_ptr()))
+        _weight_cache(ctx.module).invalidate()          # an optimizer step follows: the planes are stale from here on
         return (None, None, None, None, None, None, *grads)
 
 
@@ -326,12 +334,17 @@ def make_head_config(module, B, M) -> HeadConfig:
 
 
 class _HeadWeightCache:
+    """Same policy as _WeightCache: rebuilt on every call that can be followed by a backward pass."""
+
     def __init__(self):
         self.key, self.buf = None, None
 
-    def get(self, cfg, params):
+    def invalidate(self):
+        self.key = None
+
+    def get(self, cfg, params, force=False):
         key = (cfg.planes, cfg.planes_bwd, cfg.fwd_fp16, cfg.K, cfg.H, cfg.C, cfg.W, cfg.if_pooling) + tuple((p.data_ptr(), p._version) for p in params)
-        if key != self.key:
+        if force or key != self.key:
             nbytes = _bytes(lib().vmm_head_weights_bytes, cfg)
             if self.buf is None or self.buf.numel() < nbytes or self.buf.device != params[0].device:
                 self.buf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
@@ -343,21 +356,21 @@ class _HeadWeightCache:
 
 class _HeadFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, want_descriptor, h, gamma, *params):
+    def forward(ctx, module, want_descriptor, can_backward, h, gamma, *params):
         B = h.shape[0] // module.k
         dev = h.device
         M = gamma.shape[2] if gamma is not None else 1
         cfg = make_head_config(module, B, M)
         with torch.cuda.device(dev):
             wc = module.__dict__.setdefault("_vmm_weight_cache", _HeadWeightCache())
-            weights = wc.get(cfg, params)
+            weights = wc.get(cfg, params, force=can_backward)
             ws = torch.empty(_bytes(lib().vmm_head_workspace_bytes, cfg), dtype=torch.uint8, device=dev)
             out = torch.empty(B, cfg.W if want_descriptor else cfg.C, device=dev)
             pp = _head_pointers(params)
             check(lib().vmm_head_forward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(h), ptr(gamma), ptr(ws),
                                          None if want_descriptor else ptr(out), ptr(out) if want_descriptor else None,
                                          stream_ptr()))
-        ctx.cfg, ctx.want_descriptor = cfg, want_descriptor
+        ctx.cfg, ctx.want_descriptor, ctx.module = cfg, want_descriptor, module
         ctx.save_for_backward(h, ws, weights, *params)
         return out
 
@@ -375,7 +388,8 @@ class _HeadFunction(torch.autograd.Function):
             check(lib().vmm_head_backward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(h), ptr(ws), ptr(scratch),
                                           None if ctx.want_descriptor else ptr(d_out),
                                           ptr(d_out) if ctx.want_descriptor else None, C.byref(gp), ptr(d_h), stream_ptr()))
-        return (None, None, d_h, None, *grads)
+        ctx.module.__dict__["_vmm_weight_cache"].invalidate()
+        return (None, None, None, d_h, None, *grads)
 
 
 def head_forward(module, h, gamma):
@@ -387,7 +401,10 @@ def head_forward(module, h, gamma):
     if gamma is not None:
         B = h.shape[0] // module.k
         g = gamma.detach().to(h.device, torch.float32).reshape(B, module.k, -1).contiguous()
-    return _HeadFunction.apply(module, bool(module.save_fea), h, g, *head_param_tensors(module))
+    params = head_param_tensors(module)
+    # grad mode is off inside Function.forward: decide here whether a backward pass (and an optimizer step) can follow
+    can_backward = torch.is_grad_enabled() and (h.requires_grad or any(p.requires_grad for p in params))
+    return _HeadFunction.apply(module, bool(module.save_fea), can_backward, h, g, *params)
 
 
 class _CrossEntropyFunction(torch.autograd.Function):

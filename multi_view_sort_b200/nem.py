@@ -95,6 +95,15 @@ class NEM(Model):
         return h, pred, gamma, gamma_prior
 
     # -- compute ---------------------------------------------------------------------------
+    def invalidate_weights(self):
+        """Drop the cached operand planes of the weights.  Needed only after changing parameter VALUES in a way
+        autograd cannot see AND without a backward pass through this module in between (e.g. a fused optimizer
+        stepping on externally computed gradients, or writes through .data): training calls always rebuild the
+        planes and every backward pass marks them stale (functional._WeightCache)."""
+        wc = self.__dict__.get("_vmm_weight_cache")
+        if wc is not None:
+            wc.invalidate()
+
     def run_em(self, x, iters=None, gamma0=None, gamma_prior=None, labels=None):
         """Fused path: all `iters` EM iterations and the last iteration's outer loss in one
         autograd node.  x: (B, M, D) on the GPU (fp32, or bf16 when precision='bf16').
@@ -144,6 +153,15 @@ class Multi_View_Net(Model):
         # keys net.0 / net.3 / net.6 as in the reference (VGG classifier indices)
         self.net = nn.Sequential(first, nn.ReLU(True), nn.Dropout(), mid, nn.ReLU(True), nn.Dropout(), last)
         self.att = nn.Sequential(nn.Linear(rnn_hidden_size, 1), nn.Sigmoid())
+
+    def invalidate_weights(self):
+        """Drop the cached operand planes of the weights.  Needed only after changing parameter VALUES in a way
+        autograd cannot see AND without a backward pass through this module in between (e.g. a fused optimizer
+        stepping on externally computed gradients, or writes through .data): training calls always rebuild the
+        planes and every backward pass marks them stale (functional._WeightCache)."""
+        wc = self.__dict__.get("_vmm_weight_cache")
+        if wc is not None:
+            wc.invalidate()
 
     def forward(self, input, gamma):
         """input: (B*K, H) last hidden state, gamma: (B,K,M,1) -> logits (B, nclasses), or

@@ -62,3 +62,36 @@ def test_device_prefetcher_order_and_values():
         assert torch.equal(x.cpu(), batches[i][1]) and torch.equal(y.cpu(), batches[i][0])
         seen += 1
     assert seen == 5 and len(DevicePrefetcher(batches)) == 5
+
+
+def test_training_updates_the_prepared_weights_and_learns():
+    """The operand planes of the weights are cached per parameter version: after every optimizer step (fused Adam
+    updates in place) they must be rebuilt, and a few steps on one fixed batch must reduce the loss."""
+    from multi_view_sort_b200 import NEM, Multi_View_Net
+    from multi_view_sort_b200.functional import cross_entropy
+    torch.manual_seed(0)
+    nem = NEM(nclasses=10, view_num=12, k=3, input_dim=256, rnn_hidden_size=1024, iter_num=2, init_type="bin_uniform",
+              gamma_prior_loss=1, e_sigma=0.1, precision="bf16").cuda().eval()
+    head = Multi_View_Net(None, "vggm", nclasses=10, k=3, rnn_hidden_size=1024, precision="bf16").cuda().eval()
+    opt = torch.optim.Adam(list(nem.parameters()) + list(head.parameters()), lr=2e-4, fused=True)
+    g = torch.Generator().manual_seed(1)
+    x = torch.relu(torch.randn(16, 12, 256, generator=g)).cuda().bfloat16()
+    y = torch.randint(0, 10, (16,), generator=g).cuda()
+    def eval_out():
+        with torch.no_grad():
+            h, gamma, *_ = nem.run_em(x, 2)
+            return h.clone(), head(h, gamma).clone()
+    losses, prev = [], eval_out()
+    for step in range(12):
+        opt.zero_grad(set_to_none=True)
+        h, gamma, nem_loss, _, _ = nem.run_em(x, 2)
+        closs = cross_entropy(head(h, gamma), y)
+        (closs + nem_loss).backward()
+        opt.step()
+        losses.append(closs.item())
+        if step < 3:                                  # a forward-only call right after the step sees the NEW weights
+            cur = eval_out()
+            assert not torch.equal(cur[0], prev[0]) and not torch.equal(cur[1], prev[1]), "stale weight planes"
+            prev = cur
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < 0.7 * losses[0], losses
