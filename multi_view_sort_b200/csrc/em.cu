@@ -505,10 +505,15 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     // --- dec1
     {
       LnDesc ln = ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps, c, ST_DEC1, t);
-      VMM_TRY(ln_backward_rows(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.du, E2, sc.dv4, sc.c1, sc.c2, nullptr, nullptr,
-                               Planes(), st));
-      VMM_TRY(ln_backward_cols(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.c1, sc.c2, sc.du, E2, g->dec1_ln_g,
-                               g->dec1_ln_b, g->dec1_b, nullptr, st));
+      if (lnw_backward_fused_ok(E2)) {
+        VMM_TRY(lnw_backward_fused(ACT_RELU, ln, cur.mean4, cur.rstd4, sc.du, E2, sc.dv4, g->dec1_ln_g, g->dec1_ln_b,
+                                   g->dec1_b, st));
+      } else {
+        VMM_TRY(ln_backward_rows(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.du, E2, sc.dv4, sc.c1, sc.c2, nullptr, nullptr,
+                                 Planes(), st));
+        VMM_TRY(ln_backward_cols(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.c1, sc.c2, sc.du, E2, g->dec1_ln_g,
+                                 g->dec1_ln_b, g->dec1_b, nullptr, st));
+      }
     }
     VMM_TRY(linear_dgrad(sc.dv4, w.w4.b, d.R, E2, d.H, dh, true, d.chain_b, st));          // dh += dG4 W4
     VMM_TRY(linear_wgrad(sc.dv4, cur.hp.b, d.R, E2, d.H, g->dec1_w, d.chain_b, st));
@@ -529,10 +534,15 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     // --- enc2
     {
       LnDesc ln = ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps, c, ST_ENC2, t);
-      VMM_TRY(ln_backward_rows(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.de, E2, sc.dv2, sc.c1, sc.c2, nullptr, nullptr,
-                               Planes(), st));
-      VMM_TRY(ln_backward_cols(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.c1, sc.c2, sc.de, E2, g->enc2_ln_g,
-                               g->enc2_ln_b, g->enc2_b, nullptr, st));
+      if (lnw_backward_fused_ok(E2)) {
+        VMM_TRY(lnw_backward_fused(ACT_ELU, ln, cur.mean2, cur.rstd2, sc.de, E2, sc.dv2, g->enc2_ln_g, g->enc2_ln_b,
+                                   g->enc2_b, st));
+      } else {
+        VMM_TRY(ln_backward_rows(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.de, E2, sc.dv2, sc.c1, sc.c2, nullptr, nullptr,
+                                 Planes(), st));
+        VMM_TRY(ln_backward_cols(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.c1, sc.c2, sc.de, E2, g->enc2_ln_g,
+                                 g->enc2_ln_b, g->enc2_b, nullptr, st));
+      }
     }
     VMM_TRY(linear_dgrad(sc.dv2, w.w2.b, d.R, E2, d.ZW, sc.da, false, d.chain_b, st));
     VMM_TRY(linear_wgrad(sc.dv2, cur.a.b, d.R, E2, d.ZW, g->enc2_w, d.chain_b, st));

@@ -614,6 +614,106 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
 }
 
 
+// ------------------------------------------------------------------------------------------
+// LN_BIAS stages of width 4096 (enc2, dec1): LayerNorm+activation backward, rows AND columns in one pass (replaces
+// lnw_backward_rows_kernel + ln_backward_cols4_kernel, which each read C and the incoming gradient).  One block
+// of 1024 threads per SM walks rows in a grid-stride loop; thread t owns columns 4t..4t+3 of every row, so the
+// three column reductions are thread-private accumulators; the next row is prefetched into registers before the
+// two row reductions of the current one (one barrier per row, double-buffered partials).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1) lnw4k_backward_fused_kernel(
+    LnDesc d, int act, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+    const float* __restrict__ d_out, long long ldd, Planes dvp, float* __restrict__ d_ln_g, float* __restrict__ d_ln_b,
+    float* __restrict__ d_bias) {
+  // 512 threads x 2 float4 (columns 4t..4t+3 and 2048+4t..): two rows are prefetched into registers ahead of the
+  // one being reduced, i.e. 64 KB in flight per SM - what Little's law asks for at ~6 TB/s and ~1.5 us of latency.
+  __shared__ float2 red[2][16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x;
+  float4 g[2], bb[2], bias[2], a_g[2], a_b[2], a_bias[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid * 4 + i * 2048;
+    g[i] = ld4(d.ln_g + c); bb[i] = ld4(d.ln_b + c); bias[i] = ld4(d.bias + c);
+    a_g[i] = make_float4(0.f, 0.f, 0.f, 0.f); a_b[i] = a_g[i]; a_bias[i] = a_g[i];
+  }
+  struct RowRegs { float4 v[2], go[2]; float mean, rstd; };
+  auto fetch = [&](int row, RowRegs& r) {
+    if (row < d.rows) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = tid * 4 + i * 2048;
+        r.v[i] = ld4(d.C + static_cast<long long>(row) * d.ldc + c);
+        r.go[i] = ld4(d_out + static_cast<long long>(row) * ldd + c);
+      }
+      r.mean = __ldg(mean_in + row);
+      r.rstd = __ldg(rstd_in + row);
+    }
+  };
+  RowRegs r0, r1, r2;
+  int row = blockIdx.x;
+  fetch(row, r0);
+  fetch(row + G, r1);
+  for (int par = 0; row < d.rows; row += G, par ^= 1) {
+    fetch(row + 2 * G, r2);
+    const float mean = r0.mean, rstd = r0.rstd;
+    float xh[2][4], dy[2][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = tid * 4 + i * 2048;
+      float ds[4] = {1.f, 1.f, 1.f, 1.f};
+      if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * d.width + c, ds);
+      const float vv[4] = {r0.v[i].x + bias[i].x, r0.v[i].y + bias[i].y, r0.v[i].z + bias[i].z, r0.v[i].w + bias[i].w};
+      const float gg[4] = {g[i].x, g[i].y, g[i].z, g[i].w}, be[4] = {bb[i].x, bb[i].y, bb[i].z, bb[i].w};
+      const float oo[4] = {r0.go[i].x, r0.go[i].y, r0.go[i].z, r0.go[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        xh[i][q] = (vv[q] - mean) * rstd;
+        dy[i][q] = oo[q] * ds[q] * act_grad_fast(act, fmaf(xh[i][q], gg[q], be[q]));
+        const float dx = dy[i][q] * gg[q];
+        s1 += dx;
+        s2 = fmaf(dx, xh[i][q], s2);
+      }
+    }
+    s1 = warp_sum_f(s1);
+    s2 = warp_sum_f(s2);
+    if (lane == 0) red[par][warp] = make_float2(s1, s2);
+    __syncthreads();
+    const float2 pr = red[par][lane & 15];
+    float c1 = pr.x, c2 = pr.y;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    c1 *= (1.0f / 4096.f);
+    c2 *= (1.0f / 4096.f);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = tid * 4 + i * 2048;
+      const float gg[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
+      float dv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dv[q] = rstd * (dy[i][q] * gg[q] - c1 - xh[i][q] * c2);
+      store_planes4(dvp, static_cast<long long>(row) * d.width + c, make_float4(dv[0], dv[1], dv[2], dv[3]));
+      a_g[i].x = fmaf(dy[i][0], xh[i][0], a_g[i].x); a_g[i].y = fmaf(dy[i][1], xh[i][1], a_g[i].y);
+      a_g[i].z = fmaf(dy[i][2], xh[i][2], a_g[i].z); a_g[i].w = fmaf(dy[i][3], xh[i][3], a_g[i].w);
+      a_b[i].x += dy[i][0]; a_b[i].y += dy[i][1]; a_b[i].z += dy[i][2]; a_b[i].w += dy[i][3];
+      a_bias[i].x += dv[0]; a_bias[i].y += dv[1]; a_bias[i].z += dv[2]; a_bias[i].w += dv[3];
+    }
+    r0 = r1;
+    r1 = r2;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid * 4 + i * 2048;
+    atomicAdd(reinterpret_cast<float4*>(d_ln_g + c), a_g[i]);
+    atomicAdd(reinterpret_cast<float4*>(d_ln_b + c), a_b[i]);
+    atomicAdd(reinterpret_cast<float4*>(d_bias + c), a_bias[i]);
+  }
+}
+
 // Backward rows for the wide LN_BIAS stages (4096, 1024*M): one block of width/16 threads per row, four
 // float4 per thread cached in registers between the reduction pass and the output pass.
 __global__ void __launch_bounds__(1024) lnw_backward_rows_kernel(LnDesc d, int act, const float* __restrict__ mean_in,
@@ -1285,6 +1385,19 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
   else
     ln_backward_cols4_kernel<LN_ENC1><<<grid, 128, 0, stream>>>(d, act, mean, rstd, c1, c2, d_out, ldd, rpb, d_ln_g, d_ln_b,
                                                                  d_bias, d_w1b3);
+  VMM_LAUNCHED();
+  return 0;
+}
+
+int lnw_backward_fused(int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out, long long ldd,
+                       const Planes& dv, float* d_ln_g, float* d_ln_b, float* d_bias, cudaStream_t stream) {
+  VMM_TRY(check_ln(d, LN_BIAS));
+  VMM_REQUIRE(lnw_backward_fused_ok(d.width) && dv.n > 0, "lnw_backward_fused: needs width 4096 and output planes");
+  VMM_REQUIRE(mean && rstd && d_out && ldd % 4 == 0 && d_ln_g && d_ln_b && d_bias, "lnw_backward_fused: null argument");
+  VMM_REQUIRE(((reinterpret_cast<uintptr_t>(d_ln_g) | reinterpret_cast<uintptr_t>(d_ln_b) |
+                reinterpret_cast<uintptr_t>(d_bias)) & 15) == 0, "lnw_backward_fused: gradient buffers must be 16-byte aligned");
+  const int blocks = std::min(d.rows, device_sm_count());
+  lnw4k_backward_fused_kernel<<<blocks, 512, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, d_ln_g, d_ln_b, d_bias);
   VMM_LAUNCHED();
   return 0;
 }

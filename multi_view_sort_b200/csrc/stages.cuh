@@ -81,6 +81,11 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
                      const float* c2, const float* d_out, long long ldd, float* d_ln_g, float* d_ln_b, float* d_bias,
                      float* d_w1b3, cudaStream_t stream);
 
+// LN_BIAS stages of width 4096 (enc2, dec1): ln_backward_rows + ln_backward_cols in ONE pass over C and d_out.
+inline bool lnw_backward_fused_ok(int width) { return width == 4096; }
+int lnw_backward_fused(int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out, long long ldd,
+                       const Planes& dv, float* d_ln_g, float* d_ln_b, float* d_bias, cudaStream_t stream);
+
 // enc1 (LN_ENC1, width 1024, K <= 6): ln_backward_rows + ln_backward_cols in ONE pass over G1 and d_out.
 inline bool enc1_backward_fused_ok(int width, int k_latent) { return width == 1024 && k_latent >= 1 && k_latent <= 6; }
 int enc1_backward_fused(int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out, long long ldd,
