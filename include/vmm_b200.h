@@ -204,6 +204,9 @@ typedef struct vmm_em_config {
 #define VMM_FWD_SINGLE 1u    /* leading plane of both operands: one tensor-core pass          */
 #define VMM_FWD_ACT_PAIR 2u  /* all planes of the activation x leading plane of the weight    */
 #define VMM_FWD_W_PAIR 3u    /* leading plane of the activation x all planes of the weight    */
+/* A/B bits of fwd_modes (planes_bwd >= 2 only): leading plane only in the weight- / data-gradient contractions */
+#define VMM_BWD_WGRAD_SINGLE (1u << 18)
+#define VMM_BWD_DGRAD_SINGLE (1u << 19)
 #define VMM_DELTA_NONE 0
 #define VMM_DELTA_F16 1
 #define VMM_DELTA_F32 2

@@ -192,10 +192,15 @@ int check_cfg(const vmm_em_config* c) {
   VMM_REQUIRE(c->accum_chain >= 0, "accum_chain must be >= 0");
   VMM_REQUIRE(c->dropout_p >= 0.f && c->dropout_p < 1.f, "dropout_p must be in [0, 1)");
   VMM_REQUIRE(c->save_delta >= VMM_DELTA_NONE && c->save_delta <= VMM_DELTA_F32, "save_delta must be 0, 1 or 2");
-  VMM_REQUIRE((c->fwd_modes >> 18) == 0, "fwd_modes has 9 two-bit fields");
+  VMM_REQUIRE((c->fwd_modes >> 20) == 0, "fwd_modes has 9 two-bit fields and 2 gradient-contraction bits");
   VMM_REQUIRE(1ll * c->B * c->K * c->M < (1ll << 31) / 2, "too many rows for 32-bit indexing; split the batch");
   return 0;
 }
+
+// A/B bits 18, 19 of vmm_em_config.fwd_modes: with planes_bwd >= 2, run only the weight-gradient (18) or only the
+// data-gradient (19) contractions on the leading plane - separates the two error sources of single-plane gradients
+// (tools/mode_sweep.py).  Set per call by em_backward (thread-local: the library has no other per-call state).
+static thread_local unsigned g_bwd_bits = 0;
 
 // forward contraction ids (bit positions of vmm_em_config.fwd_modes / 2)
 enum { FC_XW1 = 0, FC_G1 = 1, FC_ENC2 = 2, FC_GI = 3, FC_GH = 4, FC_DEC1 = 5, FC_DEC2 = 6, FC_DEC3 = 7, FC_EBWD = 8 };
@@ -233,15 +238,19 @@ int linear_fwd(const Dims& d, int fc, const Planes& a_all, const Planes& w_all, 
   return gemm_bf16(static_cast<int>(rows), n, ns, s, false, false, y, n, nullptr, false, 1, d.chain, st);
 }
 // dx[rows, k] (+)= dy[rows, n] * w[n, k]     (data gradient; w is read N-major, no transposed copy)
-int linear_dgrad(const Planes& dy, const Planes& w, long long rows, int n, long long k, float* dx, bool accumulate,
+int linear_dgrad(const Planes& dy_all, const Planes& w_all, long long rows, int n, long long k, float* dx, bool accumulate,
                  int chain, cudaStream_t st) {
+  const Planes dy = g_bwd_bits & VMM_BWD_DGRAD_SINGLE ? dy_all.first(1) : dy_all;
+  const Planes w = g_bwd_bits & VMM_BWD_DGRAD_SINGLE ? w_all.first(1) : w_all;
   vmm_gemm_seg s[9];
   const int ns = make_segs(s, dy, n, w, k, n);
   return gemm_bf16(static_cast<int>(rows), static_cast<int>(k), ns, s, false, true, dx, k, nullptr, accumulate, 1, chain, st);
 }
 // dw[n, k] += dy[rows, n]^T * x[rows, k]     (weight gradient; both operands read MN-major, split-K)
-int linear_wgrad(const Planes& dy, const Planes& x, long long rows, int n, long long k, float* dw, int chain,
+int linear_wgrad(const Planes& dy_all, const Planes& x_all, long long rows, int n, long long k, float* dw, int chain,
                  cudaStream_t st) {
+  const Planes dy = g_bwd_bits & VMM_BWD_WGRAD_SINGLE ? dy_all.first(1) : dy_all;
+  const Planes x = g_bwd_bits & VMM_BWD_WGRAD_SINGLE ? x_all.first(1) : x_all;
   vmm_gemm_seg s[9];
   const int ns = make_segs(s, dy, n, x, k, rows);
   return gemm_bf16(n, static_cast<int>(k), ns, s, true, true, dw, k, nullptr, true, 0, chain, st);
@@ -446,6 +455,7 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
   Scratch sc(*c, scratch);
   const float eps = c->ln_eps;
   const int R = static_cast<int>(d.R);
+  g_bwd_bits = c->fwd_modes & (VMM_BWD_WGRAD_SINGLE | VMM_BWD_DGRAD_SINGLE);
 
   Op xp = ws.x;
   if (c->x_is_bf16) {
@@ -488,8 +498,9 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     VMM_TRY(linear_wgrad(sc.dpred, cur.z.b, d.RM, d.D, E1, g->dec3_w, d.chain_b, st));
     {
       vmm_gemm_seg s[18];
-      int ns = make_segs(s, sc.dpred, d.D, w.w3.b, E1, d.D);
-      if (!last) ns += make_segs(s + ns, sc.dg1, E1, w.w13.b, E1, E1);
+      const bool one = (g_bwd_bits & VMM_BWD_DGRAD_SINGLE) != 0;
+      int ns = make_segs(s, one ? sc.dpred.first(1) : sc.dpred, d.D, one ? w.w3.b.first(1) : w.w3.b, E1, d.D);
+      if (!last) ns += make_segs(s + ns, one ? sc.dg1.first(1) : sc.dg1, E1, one ? w.w13.b.first(1) : w.w13.b, E1, E1);
       VMM_TRY(gemm_bf16(static_cast<int>(d.RM), E1, ns, s, false, true, sc.dz, E1, nullptr, false, 1, d.chain_b, st));
     }
     // --- dec2: LayerNorm(1024*M) backward, dgrad, wgrad

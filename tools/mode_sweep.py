@@ -26,11 +26,13 @@ if len(sys.argv) > 2:
         if "+d" in spec:
             spec, dd = spec.split("+d")
             delta = int(dd)
-        kw = {}
+        kw, extra = {}, 0
         for item in filter(None, spec.split(",")):
             n, m = item.split(":")
-            kw[n] = MODE[m]
-        combos.append((sys.argv[2:][len(combos)], fwd_modes(**kw), delta))
+            if n == "wgrad": extra |= 1 << 18          # weight-gradient contractions on the leading plane only
+            elif n == "dgrad": extra |= 1 << 19        # data-gradient contractions on the leading plane only
+            else: kw[n] = MODE[m]
+        combos.append((sys.argv[2:][len(combos)], fwd_modes(**kw) | extra, delta))
 else:
     combos.append(("base", 0, 0))
     combos.append(("delta_f16", 0, 1))
