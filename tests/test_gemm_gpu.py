@@ -222,3 +222,24 @@ def test_gemm_fp16_pair_planes():
     assert errs["f16x1"] < 2e-3
     assert errs["f16pair_check_kernel"] < 2e-6, "reference semantics of the fp16 pair are wrong"
     assert errs["f16pair_chain4"] < 2e-6 and errs["mn_f16pair"] < 2e-6 and errs["f16x1_f16pair"] < 2e-6
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 512, 1024), (384, 768, 136), (3000, 1024, 1024), (1024, 40, 4096)])
+def test_cta_pair_kernel_is_bit_identical_to_single_cta(M, N, K, a_mn, b_mn):
+    """The CTA-pair execution shape (cluster of 2, tcgen05 cta_group::2, the default for M > 128) accumulates every
+    output element over the same K order as the single-CTA kernel: results are bit-identical, including odd numbers
+    of 128-row blocks (the pair's second CTA runs on an all-out-of-bounds tile) and chained accumulation."""
+    from multi_view_sort_b200 import ops
+    from multi_view_sort_b200._lib import lib
+    A = _rand((K, M) if a_mn else (M, K), 51).bfloat16()
+    B = _rand((K, N) if b_mn else (N, K), 52).bfloat16()
+    outs = []
+    try:
+        for ncta in (1, 2):
+            lib().vmm_gemm_force_ncta(ncta)
+            outs.append((ops.gemm([(A, B)], a_mn, b_mn), ops.gemm([(A, B), (A, B)], a_mn, b_mn, chain=4)))
+    finally:
+        lib().vmm_gemm_force_ncta(0)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
