@@ -115,6 +115,13 @@ VMM_API int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int 
                   float* C, long long ldc, const float* bias, int accumulate, int splits, int chain_kblocks,
                   void* stream);
 
+/* Same contraction with output row m multiplied by row_scale[m] (float[M], device) before it is stored / accumulated:
+ * un-scales an A operand whose rows were scaled by powers of two to fit fp16 (the data-gradient contractions of the
+ * "fp16 gradient" mode: dy rows are stored as fp16(dy * s_m), row_scale = 1 / s_m).  A must not be MN-major. */
+VMM_API int vmm_gemm_rowscaled(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,
+                               float* C, long long ldc, const float* row_scale, int accumulate, int splits,
+                               int chain_kblocks, void* stream);
+
 /* Execution shape of the contraction kernels: 0 = library's choice (CTA pairs - cluster of 2, tcgen05
  * cta_group::2, 256 x 256 tile per pair - whenever M > 128), 1 = always one CTA per tile, 2 = always pairs.
  * Process-wide; for tests and A/B timing. */
@@ -198,6 +205,12 @@ typedef struct vmm_em_config {
    * VMM_DELTA_F16 / VMM_DELTA_F32: the forward E-step epilogue also writes delta = x - pred [B*K*M, D] of
    * every iteration into the workspace (training only) and the backward is a streaming pass over it. */
   int save_delta;
+  /* 1 (needs fwd_fp16; training): every data-gradient contraction of the BPTT chain (dpred*W3, dG1*W13, dv5*W5, dv4*W4,
+   * dgi*Wih, dgh*Whh, dv2*W2) reads a row-scaled fp16 copy of the gradient (exact row maxima, or for dpred the bound
+   * 0.607 sigma |alpha| + max|delta| |beta|) and the fp16 hi plane of the weight instead of single bf16 planes: 11
+   * mantissa bits instead of 8 where rounding errors accumulate, at the same number of tensor-core passes.  The
+   * weight-gradient contractions (reductions over rows) keep bf16 operands. */
+  int dgrad_fp16;
 } vmm_em_config;
 
 #define VMM_FWD_FULL 0u      /* all planes of both operands                                   */

@@ -29,10 +29,11 @@ struct Dims {
   int chain_b;                        // chain bound of the gradient contractions (single bf16 plane: none needed)
   unsigned modes;                     // VMM_FWD_* of each forward contraction, 2 bits each
   int save_delta;                     // VMM_DELTA_*: keep delta = x - pred of every iteration for the backward pass
+  int dgh;                            // row-scaled fp16 operands in the LayerNorm-fed data-gradient contractions
   long long R, RM, BM, ZW;   // B*K, B*K*M, B*M, 1024*M
   int nblk;
   explicit Dims(const vmm_em_config& c)
-      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16), chain_b(c.planes_bwd >= 2 ? c.accum_chain : 0), modes(c.fwd_modes), save_delta(c.training ? c.save_delta : 0), R(1ll * c.B * c.K),
+      : B(c.B), K(c.K), M(c.M), D(c.D), H(c.H), T(c.T), planes(c.planes), pb(c.planes_bwd), chain(c.accum_chain), f16(c.fwd_fp16), chain_b(c.planes_bwd >= 2 ? c.accum_chain : 0), modes(c.fwd_modes), save_delta(c.training ? c.save_delta : 0), dgh(c.training && c.dgrad_fp16 && c.fwd_fp16 && enc1_backward_fused_ok(1024, c.K) ? 1 : 0), R(1ll * c.B * c.K),
         RM(1ll * c.B * c.K * c.M), BM(1ll * c.B * c.M), ZW(1ll * E1 * c.M), nblk(2 * ((c.D + 255) / 256)) {}
 };
 
@@ -71,6 +72,7 @@ struct IterBufs {
   Op z;
   float *gamma, *inv_s;
   void* delta;       // x - pred of this iteration [RM, D] (fp16 or fp32), only with save_delta in training
+  float* dmax;       // max_d |x - pred| per row [RM], only with dgrad_fp16 in training
 };
 
 struct Workspace {
@@ -126,6 +128,7 @@ struct Workspace {
     t.delta = nullptr;
     if (d.save_delta == VMM_DELTA_F16) t.delta = b.take<__half>(d.RM * d.D);
     else if (d.save_delta == VMM_DELTA_F32) t.delta = b.take<float>(d.RM * d.D);
+    t.dmax = (d.dgh && d.save_delta) ? b.take<float>(d.RM) : nullptr;
     if (o) *o = t;
   }
   IterBufs slot(int iter) const {
@@ -138,11 +141,12 @@ struct Workspace {
 };
 
 struct Scratch {
-  float *part_e, *part_sq, *part_pp;
+  float *part_e, *part_sq, *part_pp, *part_dmax;
   // backward
   float *dh, *dh_prev, *dgamma, *alpha, *beta, *kappa, *c1, *c2;
   Planes dpred, dv5, dv4, dgi, dgh, dv2, dg1, dxw1p, dw13p;
   float *dz, *du, *de, *da, *dxw1, *dw13, *dw1b3;
+  RowF16 dv5h, dv4h, dv2h, dg1h, dgih, dghh, dpredh;     // row-scaled fp16 copies (dgrad_fp16)
   long long bytes;
   Scratch(const vmm_em_config& c, void* base) {
     Dims d(c);
@@ -150,6 +154,7 @@ struct Scratch {
     part_e = b.take<float>(d.RM * d.nblk);
     part_sq = b.take<float>(d.RM * d.nblk);
     part_pp = b.take<float>(d.RM * d.nblk);
+    part_dmax = d.dgh ? b.take<float>(d.RM * d.nblk) : nullptr;
     if (c.training) {
       dh = b.take<float>(d.R * d.H);
       dh_prev = b.take<float>(d.R * d.H);
@@ -175,6 +180,19 @@ struct Scratch {
       dw13 = b.take<float>(1ll * E1 * E1);
       dw13p = b.planes(1ll * E1 * E1, d.pb);
       dw1b3 = b.take<float>(E1);
+      if (d.dgh) {
+        dv5h.p = b.take<__half>(d.R * d.ZW); dv5h.inv_scale = b.take<float>(d.R);
+        dv4h.p = b.take<__half>(d.R * E2);   dv4h.inv_scale = b.take<float>(d.R);
+        dv2h.p = b.take<__half>(d.R * E2);   dv2h.inv_scale = b.take<float>(d.R);
+        dg1h.p = b.take<__half>(d.RM * E1);  dg1h.inv_scale = b.take<float>(d.RM);
+        if (d.save_delta) {
+          dpredh.p = b.take<__half>(d.RM * d.D); dpredh.inv_scale = b.take<float>(d.RM);
+        }
+        if (d.H <= 1024) {
+          dgih.p = b.take<__half>(d.R * 3 * d.H); dgih.inv_scale = b.take<float>(d.R);
+          dghh.p = b.take<__half>(d.R * 3 * d.H); dghh.inv_scale = b.take<float>(d.R);
+        }
+      }
     }
     bytes = b.off + 256;
   }
@@ -192,6 +210,7 @@ int check_cfg(const vmm_em_config* c) {
   VMM_REQUIRE(c->accum_chain >= 0, "accum_chain must be >= 0");
   VMM_REQUIRE(c->dropout_p >= 0.f && c->dropout_p < 1.f, "dropout_p must be in [0, 1)");
   VMM_REQUIRE(c->save_delta >= VMM_DELTA_NONE && c->save_delta <= VMM_DELTA_F32, "save_delta must be 0, 1 or 2");
+  VMM_REQUIRE(!c->dgrad_fp16 || c->fwd_fp16, "dgrad_fp16 needs fwd_fp16 (the fp16 hi planes of the weights)");
   VMM_REQUIRE((c->fwd_modes >> 20) == 0, "fwd_modes has 9 two-bit fields and 2 gradient-contraction bits");
   VMM_REQUIRE(1ll * c->B * c->K * c->M < (1ll << 31) / 2, "too many rows for 32-bit indexing; split the batch");
   return 0;
@@ -245,6 +264,19 @@ int linear_dgrad(const Planes& dy_all, const Planes& w_all, long long rows, int 
   vmm_gemm_seg s[9];
   const int ns = make_segs(s, dy, n, w, k, n);
   return gemm_bf16(static_cast<int>(rows), static_cast<int>(k), ns, s, false, true, dx, k, nullptr, accumulate, 1, chain, st);
+}
+// dx (+)= diag(inv_scale) * (dyh[rows, n] * w_hi[n, k]) : the same with a row-scaled fp16 gradient and the fp16 hi
+// plane of the weight (one tensor-core pass, 11 mantissa bits on both sides)
+int linear_dgrad_h(const RowF16& dyh, const Planes& w_f, long long rows, int n, long long k, float* dx, bool accumulate,
+                   cudaStream_t st) {
+  Planes a;
+  a.n = 1;
+  a.fmt = VMM_FMT_F16PAIR;
+  a.p[0] = reinterpret_cast<__nv_bfloat16*>(dyh.p);
+  vmm_gemm_seg s[9];
+  const int ns = make_segs(s, a, n, w_f.first(1), k, n);
+  return gemm_bf16(static_cast<int>(rows), static_cast<int>(k), ns, s, false, true, dx, k, nullptr, accumulate, 1, 0, st,
+                   dyh.inv_scale);
 }
 // dw[n, k] += dy[rows, n]^T * x[rows, k]     (weight gradient; both operands read MN-major, split-K)
 int linear_wgrad(const Planes& dy_all, const Planes& x_all, long long rows, int n, long long k, float* dw, int chain,
@@ -369,7 +401,8 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
     const bool want_pp = last && c->if_gamma_prior == 0;
     VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, sel_act(d, FC_DEC3, cur.z.f), sel_w(d, FC_DEC3, w.w3.f), p->dec3_b, x,
                           c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
-                          want_pp ? sc.part_pp : nullptr, cur.delta, d.save_delta, st));
+                          want_pp ? sc.part_pp : nullptr, cur.delta, d.save_delta, st, cur.dmax ? sc.part_dmax : nullptr));
+    if (cur.dmax) VMM_TRY(row_max_partials(static_cast<int>(d.RM), d.nblk, sc.part_dmax, cur.dmax, st));
     VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
                           want_pp ? sc.part_pp : nullptr, cur.gamma, cur.inv_s, ws.row_sq, ws.row_pp, st));
     if (last) {
@@ -479,6 +512,7 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     const bool last = (t == d.T - 1);
     const float* gam_prev = t > 0 ? prev.gamma : gamma0;
     const float* kappa = nullptr;
+    bool dv5_h = false;
     // --- loss and E-step: per-row scalars of dL/dpred
     if (last) {
       VMM_TRY(loss_backward(d.B, d.K, d.M, d.D, c->if_gamma_prior, c->stop_gamma_grad, cur.gamma, prior, ws.row_sq, ws.row_pp,
@@ -488,9 +522,11 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       VMM_CHECK_CUDA(cudaMemsetAsync(sc.beta, 0, sizeof(float) * d.RM, st));
     }
     VMM_TRY(gamma_backward(d.B, d.K, d.M, c->sigma, cur.gamma, cur.inv_s, sc.dgamma, sc.alpha, st));
+    const bool dpred_h = d.dgh && d.save_delta && !kappa && sc.dpredh.p && cur.dmax;
     if (d.save_delta)
       VMM_TRY(estep_dpred(static_cast<int>(d.RM), d.D, cur.delta, d.save_delta, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
-                          sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st));
+                          sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st, dpred_h ? sc.dpredh.p : nullptr,
+                          dpred_h ? sc.dpredh.inv_scale : nullptr, dpred_h ? cur.dmax : nullptr));
     else
       VMM_TRY(estep_backward(static_cast<int>(d.RM), d.D, E1, sel_act(d, FC_EBWD, cur.z.f), sel_w(d, FC_EBWD, w.w3.f), p->dec3_b, x,
                              c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st));
@@ -500,25 +536,30 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       vmm_gemm_seg s[18];
       const bool one = (g_bwd_bits & VMM_BWD_DGRAD_SINGLE) != 0;
       int ns = make_segs(s, one ? sc.dpred.first(1) : sc.dpred, d.D, one ? w.w3.b.first(1) : w.w3.b, E1, d.D);
-      if (!last) ns += make_segs(s + ns, one ? sc.dg1.first(1) : sc.dg1, E1, one ? w.w13.b.first(1) : w.w13.b, E1, E1);
-      VMM_TRY(gemm_bf16(static_cast<int>(d.RM), E1, ns, s, false, true, sc.dz, E1, nullptr, false, 1, d.chain_b, st));
+      if (!last && !d.dgh) ns += make_segs(s + ns, one ? sc.dg1.first(1) : sc.dg1, E1, one ? w.w13.b.first(1) : w.w13.b, E1, E1);
+      if (dpred_h) VMM_TRY(linear_dgrad_h(sc.dpredh, w.w3.f, d.RM, d.D, E1, sc.dz, false, st));
+      else VMM_TRY(gemm_bf16(static_cast<int>(d.RM), E1, ns, s, false, true, sc.dz, E1, nullptr, false, 1, d.chain_b, st));
+      if (!last && d.dgh) VMM_TRY(linear_dgrad_h(sc.dg1h, w.w13.f, d.RM, E1, E1, sc.dz, true, st));   // own row scales: own launch
     }
     // --- dec2: LayerNorm(1024*M) backward, dgrad, wgrad
     {
       LnDesc ln = ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps);
+      const bool wide = d.dgh && d.ZW != E1 && d.ZW % 512 == 0 && d.ZW / 16 <= 1024;    // the kernel that can write dv5h
+      dv5_h = wide;
       VMM_TRY(ln_backward_rows(LN_BIAS, ACT_NONE, ln, cur.mean5, cur.rstd5, sc.dz, d.ZW, sc.dv5, sc.c1, sc.c2, nullptr, nullptr,
-                               Planes(), st));
+                               Planes(), st, wide ? sc.dv5h : RowF16()));
       VMM_TRY(ln_backward_cols(LN_BIAS, ACT_NONE, ln, cur.mean5, cur.rstd5, sc.c1, sc.c2, sc.dz, d.ZW, g->dec2_ln_g,
                                g->dec2_ln_b, g->dec2_b, nullptr, st));
     }
-    VMM_TRY(linear_dgrad(sc.dv5, w.w5.b, d.R, static_cast<int>(d.ZW), E2, sc.du, false, d.chain_b, st));
+    if (dv5_h) VMM_TRY(linear_dgrad_h(sc.dv5h, w.w5.f, d.R, static_cast<int>(d.ZW), E2, sc.du, false, st));
+    else VMM_TRY(linear_dgrad(sc.dv5, w.w5.b, d.R, static_cast<int>(d.ZW), E2, sc.du, false, d.chain_b, st));
     VMM_TRY(linear_wgrad(sc.dv5, cur.u.b, d.R, static_cast<int>(d.ZW), E2, g->dec2_w, d.chain_b, st));
     // --- dec1
     {
       LnDesc ln = ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps, c, ST_DEC1, t);
       if (lnw_backward_fused_ok(E2)) {
         VMM_TRY(lnw_backward_fused(ACT_RELU, ln, cur.mean4, cur.rstd4, sc.du, E2, sc.dv4, g->dec1_ln_g, g->dec1_ln_b,
-                                   g->dec1_b, st));
+                                   g->dec1_b, st, d.dgh ? sc.dv4h : RowF16()));
       } else {
         VMM_TRY(ln_backward_rows(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.du, E2, sc.dv4, sc.c1, sc.c2, nullptr, nullptr,
                                  Planes(), st));
@@ -526,15 +567,19 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
                                  g->dec1_ln_b, g->dec1_b, nullptr, st));
       }
     }
-    VMM_TRY(linear_dgrad(sc.dv4, w.w4.b, d.R, E2, d.H, dh, true, d.chain_b, st));          // dh += dG4 W4
+    if (d.dgh && lnw_backward_fused_ok(E2)) VMM_TRY(linear_dgrad_h(sc.dv4h, w.w4.f, d.R, E2, d.H, dh, true, st));
+    else VMM_TRY(linear_dgrad(sc.dv4, w.w4.b, d.R, E2, d.H, dh, true, d.chain_b, st));          // dh += dG4 W4
     VMM_TRY(linear_wgrad(sc.dv4, cur.hp.b, d.R, E2, d.H, g->dec1_w, d.chain_b, st));
     // --- GRU
+    const bool gru_h = d.dgh && sc.dgih.p != nullptr;
     VMM_TRY(gru_backward(R, d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, t > 0 ? prev.h : ws.h0, dh, sc.dgi, sc.dgh,
-                         dh_prev, g->gru_b_ih, g->gru_b_hh, st));
-    VMM_TRY(linear_dgrad(sc.dgi, w.wih.b, d.R, 3 * d.H, E2, sc.de, false, d.chain_b, st));
+                         dh_prev, g->gru_b_ih, g->gru_b_hh, st, gru_h ? sc.dgih : RowF16(), gru_h ? sc.dghh : RowF16()));
+    if (gru_h) VMM_TRY(linear_dgrad_h(sc.dgih, w.wih.f, d.R, 3 * d.H, E2, sc.de, false, st));
+    else VMM_TRY(linear_dgrad(sc.dgi, w.wih.b, d.R, 3 * d.H, E2, sc.de, false, d.chain_b, st));
     VMM_TRY(linear_wgrad(sc.dgi, cur.e.b, d.R, 3 * d.H, E2, g->gru_w_ih, d.chain_b, st));
     if (t > 0) {
-      VMM_TRY(linear_dgrad(sc.dgh, w.whh.b, d.R, 3 * d.H, d.H, dh_prev, true, d.chain_b, st));   // dh_{t-1} += dgh Whh
+      if (gru_h) VMM_TRY(linear_dgrad_h(sc.dghh, w.whh.f, d.R, 3 * d.H, d.H, dh_prev, true, st));
+      else VMM_TRY(linear_dgrad(sc.dgh, w.whh.b, d.R, 3 * d.H, d.H, dh_prev, true, d.chain_b, st));   // dh_{t-1} += dgh Whh
       VMM_TRY(linear_wgrad(sc.dgh, prev.hp.b, d.R, 3 * d.H, d.H, g->gru_w_hh, d.chain_b, st));
     }
     {
@@ -547,7 +592,7 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       LnDesc ln = ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps, c, ST_ENC2, t);
       if (lnw_backward_fused_ok(E2)) {
         VMM_TRY(lnw_backward_fused(ACT_ELU, ln, cur.mean2, cur.rstd2, sc.de, E2, sc.dv2, g->enc2_ln_g, g->enc2_ln_b,
-                                   g->enc2_b, st));
+                                   g->enc2_b, st, d.dgh ? sc.dv2h : RowF16()));
       } else {
         VMM_TRY(ln_backward_rows(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.de, E2, sc.dv2, sc.c1, sc.c2, nullptr, nullptr,
                                  Planes(), st));
@@ -555,7 +600,8 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
                                  g->enc2_ln_b, g->enc2_b, nullptr, st));
       }
     }
-    VMM_TRY(linear_dgrad(sc.dv2, w.w2.b, d.R, E2, d.ZW, sc.da, false, d.chain_b, st));
+    if (d.dgh && lnw_backward_fused_ok(E2)) VMM_TRY(linear_dgrad_h(sc.dv2h, w.w2.f, d.R, E2, d.ZW, sc.da, false, st));
+    else VMM_TRY(linear_dgrad(sc.dv2, w.w2.b, d.R, E2, d.ZW, sc.da, false, d.chain_b, st));
     VMM_TRY(linear_wgrad(sc.dv2, cur.a.b, d.R, E2, d.ZW, g->enc2_w, d.chain_b, st));
     // --- enc1 + residual: dgamma_{t-1}, dXW1, dG1 (-> dz_{t-1} and dW13)
     {
@@ -568,7 +614,7 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       if (enc1_backward_fused_ok(E1, d.K)) {
         VMM_TRY(enc1_backward_fused(ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, t > 0 ? sc.dgamma : nullptr, sc.dxw1,
                                     t > 0 ? sc.dg1 : Planes(), g->enc1_ln_g, g->enc1_ln_b, g->enc1_b,
-                                    t > 0 ? sc.dw1b3 : nullptr, st));
+                                    t > 0 ? sc.dw1b3 : nullptr, st, (t > 0 && d.dgh) ? sc.dg1h : RowF16()));
       } else {
         VMM_TRY(ln_backward_rows(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, Planes(), sc.c1, sc.c2,
                                  t > 0 ? sc.dgamma : nullptr, sc.dxw1, t > 0 ? sc.dg1 : Planes(), st));

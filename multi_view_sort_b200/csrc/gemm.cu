@@ -239,14 +239,16 @@ static int fill_common(GemmParams& p, int M, int N, int nseg, const vmm_gemm_seg
 }
 
 int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool b_mn, float* C, long long ldc,
-              const float* bias, bool accumulate, int splits, int chain_kb, cudaStream_t stream) {
+              const float* bias, bool accumulate, int splits, int chain_kb, cudaStream_t stream, const float* row_scale) {
   GemmParams p;
   VMM_TRY(fill_common(p, M, N, nseg, segs, a_mn, b_mn, splits, accumulate, chain_kb));
   VMM_REQUIRE(C != nullptr && ldc >= N, "bad C / ldc");
   VMM_REQUIRE(!(accumulate && bias), "bias cannot be combined with accumulate");
+  VMM_REQUIRE(!(row_scale && bias), "row_scale cannot be combined with bias");
   p.C = C;
   p.ldc = ldc;
   p.bias = bias;
+  p.row_scale = row_scale;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0 &&
               (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) ? 1 : 0;
   if (accumulate) return launch_major<EPI_RED, float, 1>(p, a_mn, b_mn, stream);
@@ -313,13 +315,14 @@ static int estep_common(GemmParams& p, int rows, int D, int zk, const Planes& z,
 
 int estep_forward(int rows, int D, int zk, const Planes& z, const Planes& w3, const float* b3, const void* x,
                   int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
-                  float* part_pp, void* delta, int delta_fmt, cudaStream_t stream) {
+                  float* part_pp, void* delta, int delta_fmt, cudaStream_t stream, float* part_dmax) {
   GemmParams p;
   VMM_TRY(estep_common(p, rows, D, zk, z, w3, b3, x, ldx, k_latent, m_views, sigma));
   VMM_REQUIRE(part_e != nullptr, "part_e is null");
   p.part_e = part_e;
   p.part_sq = part_sq;
   p.part_pp = part_pp;
+  p.part_dmax = part_dmax;
   if (!delta) delta_fmt = VMM_DELTA_NONE;
   VMM_REQUIRE(delta_fmt >= VMM_DELTA_NONE && delta_fmt <= VMM_DELTA_F32, "delta_fmt must be 0, 1 or 2");
   VMM_REQUIRE((reinterpret_cast<uintptr_t>(delta) & 15) == 0, "delta must be 16-byte aligned");
@@ -508,7 +511,13 @@ const char* vmm_last_error(void) { return vmm::g_err; }
 int vmm_gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major, float* C,
                   long long ldc, const float* bias, int accumulate, int splits, int chain_kblocks, void* stream) {
   return vmm::gemm_bf16(M, N, nseg, segs, a_mn_major != 0, b_mn_major != 0, C, ldc, bias, accumulate != 0, splits,
-                        chain_kblocks, static_cast<cudaStream_t>(stream));
+                        chain_kblocks, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int vmm_gemm_rowscaled(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major, float* C,
+                       long long ldc, const float* row_scale, int accumulate, int splits, int chain_kblocks, void* stream) {
+  return vmm::gemm_bf16(M, N, nseg, segs, a_mn_major != 0, b_mn_major != 0, C, ldc, nullptr, accumulate != 0, splits,
+                        chain_kblocks, static_cast<cudaStream_t>(stream), row_scale);
 }
 
 int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major, float* C,

@@ -65,6 +65,8 @@ struct alignas(64) GemmParams {
   float* C;
   long long ldc;
   const float* bias;         // [N] or null (EPI_STORE); b3 for ESTEP/EBWD
+  const float* row_scale;    // [M] or null (EPI_STORE / EPI_RED): D row m is multiplied by row_scale[m] (un-scales a
+                             // row-scaled fp16 A operand)
   // ---- E-step epilogues ----
   const void* x;             // features [B*Mv, N] (float or bf16), row pitch ldx
   long long ldx;
@@ -74,6 +76,7 @@ struct alignas(64) GemmParams {
   float* part_e;             // [M, 2*num_n_blk]  sum_d exp(...) per 128-column half tile
   float* part_sq;            // [M, 2*num_n_blk]  sum_d (x-pred)^2   (nullable)
   float* part_pp;            // [M, 2*num_n_blk]  sum_d pred^2       (nullable)
+  float* part_dmax;          // [M, 2*num_n_blk]  max_d |x-pred|     (nullable; scales the fp16 copy of dL/dpred)
   const float* row_alpha;    // EBWD per-row scalars
   const float* row_beta;
   const float* row_kappa;    // nullable
@@ -233,6 +236,10 @@ __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint3
     const int grow = row0 + r, gcol = col0 + c4 * 4;
     if (grow < p.M && gcol < p.N) {
       float4 val = st[st_slot(r, c4)];
+      if (p.row_scale) {
+        const float rs = __ldg(p.row_scale + grow);
+        val.x *= rs; val.y *= rs; val.z *= rs; val.w *= rs;
+      }
       float* dst = p.C + static_cast<long long>(grow) * p.ldc + gcol;
       if (p.vec_ok && gcol + 3 < p.N) {
         if constexpr (EPI == EPI_STORE) {
@@ -454,6 +461,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (nbase + lane * 4 < p.N) mybias = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + lane * 4));
       }
       const bool want_sq = kFused && (EPI == EPI_ESTEP) && p.part_sq != nullptr;   // last iteration only
+      const bool want_dmax = kFused && (EPI == EPI_ESTEP) && p.part_dmax != nullptr;
+      float dmax = 0.f;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -492,6 +501,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                   if constexpr (EPI == EPI_ESTEP) {
                     sum_e += e;
                     if (want_sq) { sum_sq += dd; sum_pp = fmaf(pred, pred, sum_pp); }
+                    if (want_dmax) dmax = fmaxf(dmax, fabsf(d));
                     if constexpr (kSave != 0) out[4 * j + q] = d;
                   } else {
                     out[4 * j + q] = fmaf(d, fmaf(alpha, e, -beta), kappa * pred);
@@ -589,6 +599,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           p.part_e[o] = sum_e;
           if (p.part_sq) p.part_sq[o] = sum_sq;
           if (p.part_pp) p.part_pp[o] = sum_pp;
+          if (p.part_dmax) p.part_dmax[o] = dmax;
         }
       }
       tc_fence_before();

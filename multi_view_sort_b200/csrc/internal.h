@@ -1,5 +1,7 @@
 // Internal C++ interfaces between the translation units of libvmm_b200.so.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.h"
 
 namespace vmm {
@@ -70,17 +72,19 @@ struct Bump {
 int make_segs(vmm_gemm_seg* s, const Planes& a, long long lda, const Planes& b, long long ldb, long long k);
 
 int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool b_mn, float* C, long long ldc,
-              const float* bias, bool accumulate, int splits, int chain_kb, cudaStream_t stream);
+              const float* bias, bool accumulate, int splits, int chain_kb, cudaStream_t stream,
+              const float* row_scale = nullptr);   // row_scale[m] multiplies output row m (un-scales a row-scaled A)
 int estep_forward(int rows, int D, int zk, const Planes& z, const Planes& w3, const float* b3, const void* x,
                   int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, float* part_e, float* part_sq,
-                  float* part_pp, void* delta, int delta_fmt, cudaStream_t stream);
+                  float* part_pp, void* delta, int delta_fmt, cudaStream_t stream, float* part_dmax = nullptr);
 int estep_backward(int rows, int D, int zk, const Planes& z, const Planes& w3, const float* b3, const void* x,
                    int x_is_bf16, long long ldx, int k_latent, int m_views, float sigma, const float* alpha,
                    const float* beta, const float* kappa, const Planes& dpred, float* colsum, cudaStream_t stream);
 // Streaming E-step backward from the saved delta = x - pred (stages.cu).
 int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x, int x_is_bf16, long long ldx,
                 int k_latent, int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
-                const Planes& dpred, float* colsum, cudaStream_t stream);
+                const Planes& dpred, float* colsum, cudaStream_t stream, __half* dpred_h = nullptr,
+                float* inv_scale = nullptr, const float* row_dmax = nullptr);   // + row-scaled fp16 copy (kappa == nullptr only)
 int split_planes(const float* src, long long n, const Planes& out, cudaStream_t stream);
 int split_op(const float* src, long long n, const Op& out, cudaStream_t stream);   // both operand sets
 int bf16_to_f16(const void* src_bf16, long long n, void* dst_f16, cudaStream_t stream);

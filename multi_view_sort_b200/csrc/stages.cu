@@ -31,6 +31,28 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return warp_sum_f(t);
 }
 
+// power-of-two row scale that puts amax into [2^11, 2^12) (fp16 keeps 11 bits for everything within 2^-25 of it)
+__device__ __forceinline__ float row_scale_pow2(float amax) {
+  if (!(amax > 0.f) || amax > 3.0e38f) return 1.f;
+  int e;
+  frexpf(amax, &e);                       // amax = m * 2^e, m in [0.5, 1)
+  e = 12 - e;
+  e = e > 120 ? 120 : (e < -100 ? -100 : e);
+  return ldexpf(1.f, e);
+}
+__device__ __forceinline__ void store_half4(__half* p, long long idx, float a, float b, float c, float d) {
+  const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&h0);
+  u.y = *reinterpret_cast<const uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(p + idx) = u;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ float act_fwd(int act, float y) {
@@ -507,9 +529,10 @@ template <int NR>
 __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
     LnDesc d, int act, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
     const float* __restrict__ d_out, long long ldd, float* __restrict__ dgamma, float* __restrict__ dxw1, Planes dg1,
-    float* __restrict__ d_ln_g, float* __restrict__ d_ln_b, float* __restrict__ d_bias, float* __restrict__ d_w1b3) {
+    float* __restrict__ d_ln_g, float* __restrict__ d_ln_b, float* __restrict__ d_bias, float* __restrict__ d_w1b3,
+    RowF16 dg1h) {
   __shared__ float red[2][8][2 * NR];
-  __shared__ float red2[2][8][NR];
+  __shared__ float red2[2][8][2 * NR];     // per row: sum for dgamma, max|dG1| for the row-scaled fp16 copy
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = tid * 4;
   const int groups = d.rows / NR;
@@ -556,7 +579,8 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
     }
     __syncthreads();
     float4 accx = make_float4(0.f, 0.f, 0.f, 0.f);
-    float dgam[NR];
+    float dgam[NR], amaxk[NR];
+    float4 ngk[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
       float c1 = 0.f, c2 = 0.f;
@@ -580,6 +604,8 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
       accx.z = fmaf(gam[k], dv.z, accx.z); accx.w = fmaf(gam[k], dv.w, accx.w);
       const float4 ng = make_float4(-gam[k] * dv.x, -gam[k] * dv.y, -gam[k] * dv.z, -gam[k] * dv.w);
       if (dg1.n) store_planes4(dg1, static_cast<long long>(row) * W1K + c, ng);
+      ngk[k] = ng;
+      amaxk[k] = fmaxf(fmaxf(fabsf(ng.x), fabsf(ng.y)), fmaxf(fabsf(ng.z), fabsf(ng.w)));
       a_g.x = fmaf(dy[k].x, xh[0], a_g.x); a_g.y = fmaf(dy[k].y, xh[1], a_g.y);
       a_g.z = fmaf(dy[k].z, xh[2], a_g.z); a_g.w = fmaf(dy[k].w, xh[3], a_g.w);
       a_b.x += dy[k].x; a_b.y += dy[k].y; a_b.z += dy[k].z; a_b.w += dy[k].w;
@@ -592,18 +618,33 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
       a.x += accx.x; a.y += accx.y; a.z += accx.z; a.w += accx.w;
       *px = a;
     }
-    if (dgamma) {
+    if (dgamma || dg1h.p) {
 #pragma unroll
       for (int k = 0; k < NR; ++k) {
-        const float t = warp_sum_f(dgam[k]);
-        if (lane == 0) red2[par][warp][k] = t;
+        const float t = warp_sum_f(dgam[k]), mx = warp_max_f(amaxk[k]);
+        if (lane == 0) {
+          red2[par][warp][2 * k] = t;
+          red2[par][warp][2 * k + 1] = mx;
+        }
       }
       __syncthreads();
-      if (tid < NR) {
+      if (dgamma && tid < NR) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += red2[par][w][tid];
+        for (int w = 0; w < 8; ++w) t += red2[par][w][2 * tid];
         dgamma[(b * NR + tid) * d.mv + m] = t;
+      }
+      if (dg1h.p) {                                  // row-scaled fp16 copy of dG1 for the data-gradient contraction
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+          float mx = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red2[par][w][2 * k + 1]);
+          const float sc = row_scale_pow2(mx);
+          const int row = (b * NR + k) * d.mv + m;
+          if (tid == 0) dg1h.inv_scale[row] = 1.f / sc;
+          store_half4(dg1h.p, static_cast<long long>(row) * W1K + c, ngk[k].x * sc, ngk[k].y * sc, ngk[k].z * sc, ngk[k].w * sc);
+        }
       }
     }
   }
@@ -624,10 +665,11 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
 __global__ void __launch_bounds__(512, 1) lnw4k_backward_fused_kernel(
     LnDesc d, int act, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
     const float* __restrict__ d_out, long long ldd, Planes dvp, float* __restrict__ d_ln_g, float* __restrict__ d_ln_b,
-    float* __restrict__ d_bias) {
+    float* __restrict__ d_bias, RowF16 dvh) {
   // 512 threads x 2 float4 (columns 4t..4t+3 and 2048+4t..): two rows are prefetched into registers ahead of the
   // one being reduced, i.e. 64 KB in flight per SM - what Little's law asks for at ~6 TB/s and ~1.5 us of latency.
   __shared__ float2 red[2][16];
+  __shared__ float redm[2][16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
   float4 g[2], bb[2], bias[2], a_g[2], a_b[2], a_bias[2];
@@ -689,13 +731,32 @@ __global__ void __launch_bounds__(512, 1) lnw4k_backward_fused_kernel(
     }
     c1 *= (1.0f / 4096.f);
     c2 *= (1.0f / 4096.f);
+    float dvv[2][4];
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float gg[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dvv[i][q] = rstd * (dy[i][q] * gg[q] - c1 - xh[i][q] * c2);
+        amax = fmaxf(amax, fabsf(dvv[i][q]));
+      }
+    }
+    if (dvh.p) {                                       // row-scaled fp16 copy for the data-gradient contraction
+      amax = warp_max_f(amax);
+      if (lane == 0) redm[par][warp] = amax;
+      __syncthreads();
+      const float sc = row_scale_pow2(warp_max_f(redm[par][lane & 15]));
+      if (tid == 0) dvh.inv_scale[row] = 1.f / sc;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        store_half4(dvh.p, static_cast<long long>(row) * d.width + tid * 4 + i * 2048, dvv[i][0] * sc, dvv[i][1] * sc,
+                    dvv[i][2] * sc, dvv[i][3] * sc);
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int c = tid * 4 + i * 2048;
-      const float gg[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
-      float dv[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dv[q] = rstd * (dy[i][q] * gg[q] - c1 - xh[i][q] * c2);
+      const float* dv = dvv[i];
       store_planes4(dvp, static_cast<long long>(row) * d.width + c, make_float4(dv[0], dv[1], dv[2], dv[3]));
       a_g[i].x = fmaf(dy[i][0], xh[i][0], a_g[i].x); a_g[i].y = fmaf(dy[i][1], xh[i][1], a_g[i].y);
       a_g[i].z = fmaf(dy[i][2], xh[i][2], a_g[i].z); a_g[i].w = fmaf(dy[i][3], xh[i][3], a_g[i].w);
@@ -720,7 +781,7 @@ __global__ void __launch_bounds__(1024) lnw_backward_rows_kernel(LnDesc d, int a
                                                                  const float* __restrict__ rstd_in,
                                                                  const float* __restrict__ d_out, long long ldd,
                                                                  Planes dvp, float* __restrict__ c1_out,
-                                                                 float* __restrict__ c2_out) {
+                                                                 float* __restrict__ c2_out, RowF16 dvh) {
   __shared__ float red[32];
   const int row = blockIdx.x, tid = threadIdx.x;
   const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
@@ -749,12 +810,25 @@ __global__ void __launch_bounds__(1024) lnw_backward_rows_kernel(LnDesc d, int a
     c1_out[row] = c1;
     c2_out[row] = c2;
   }
+  float amax = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = (tid + i * blockDim.x) * 4;
-    store_planes4(dvp, rbase + c,
-                  make_float4(rstd * (dx[i].x - c1 - xh[i].x * c2), rstd * (dx[i].y - c1 - xh[i].y * c2),
-                              rstd * (dx[i].z - c1 - xh[i].z * c2), rstd * (dx[i].w - c1 - xh[i].w * c2)));
+  for (int i = 0; i < 4; ++i) {                        // dx now holds dv
+    dx[i] = make_float4(rstd * (dx[i].x - c1 - xh[i].x * c2), rstd * (dx[i].y - c1 - xh[i].y * c2),
+                        rstd * (dx[i].z - c1 - xh[i].z * c2), rstd * (dx[i].w - c1 - xh[i].w * c2));
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(dx[i].x), fabsf(dx[i].y))), fmaxf(fabsf(dx[i].z), fabsf(dx[i].w)));
+    store_planes4(dvp, rbase + (tid + i * blockDim.x) * 4, dx[i]);
+  }
+  if (dvh.p) {                                         // row-scaled fp16 copy for the data-gradient contraction
+    amax = warp_max_f(amax);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = amax;
+    __syncthreads();
+    float t = (tid & 31) < (blockDim.x >> 5) ? red[tid & 31] : 0.f;
+    const float sc = row_scale_pow2(warp_max_f(t));
+    if (tid == 0) dvh.inv_scale[row] = 1.f / sc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      store_half4(dvh.p, rbase + (tid + i * blockDim.x) * 4, dx[i].x * sc, dx[i].y * sc, dx[i].z * sc, dx[i].w * sc);
   }
 }
 
@@ -924,6 +998,91 @@ __global__ void __launch_bounds__(256) gru_backward_kernel(int rows, int H, int 
   atomicAdd(d_b_hh + j, s_r);
   atomicAdd(d_b_hh + H + j, s_z);
   atomicAdd(d_b_hh + 2 * H + j, s_hn);
+}
+
+// GRU backward, row-oriented (H <= 1024 threads, thread j owns hidden unit j of every row of its strip): same math
+// as gru_backward_kernel, plus the row-scaled fp16 copies of dgi / dgh for the data-gradient contractions - their
+// row maxima span all three gates, which a column-strip kernel cannot see.
+__global__ void __launch_bounds__(1024) gru_backward_rows_kernel(int rows, int H, int rows_per_block,
+                                                                const float* __restrict__ gi, const float* __restrict__ gh,
+                                                                const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                                                const float* __restrict__ h_prev, const float* __restrict__ dh,
+                                                                Planes dgi, Planes dgh, float* __restrict__ dh_prev,
+                                                                float* d_b_ih, float* d_b_hh, RowF16 dgih, RowF16 dghh) {
+  __shared__ float2 redm[2][32];
+  const int j = threadIdx.x, lane = j & 31, warp = j >> 5, nw = (blockDim.x + 31) >> 5;
+  const bool on = j < H;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float bir = 0.f, biz = 0.f, bin = 0.f, bhr = 0.f, bhz = 0.f, bhn = 0.f;
+  if (on) {
+    bir = b_ih[j]; biz = b_ih[H + j]; bin = b_ih[2 * H + j];
+    bhr = b_hh[j]; bhz = b_hh[H + j]; bhn = b_hh[2 * H + j];
+  }
+  float s_r = 0.f, s_z = 0.f, s_in = 0.f, s_hn = 0.f;
+  int par = 0;
+  for (int row = r0; row < r1; ++row, par ^= 1) {
+    const long long g0 = static_cast<long long>(row) * 3 * H + j;
+    const long long hidx = static_cast<long long>(row) * H + j;
+    float dr_pre = 0.f, dz_pre = 0.f, dn_pre = 0.f, dhn = 0.f;
+    if (on) {
+      const float r = sigmoidf_((gi[g0] + bir) + (gh[g0] + bhr));
+      const float z = sigmoidf_((gi[g0 + H] + biz) + (gh[g0 + H] + bhz));
+      const float ghn = gh[g0 + 2 * H] + bhn;
+      const float n = tanhf((gi[g0 + 2 * H] + bin) + r * ghn);
+      const float hp = h_prev[hidx];
+      const float g = dh[hidx];
+      const float dn = g * (1.f - z);
+      const float dz = g * (hp - n);
+      dn_pre = dn * (1.f - n * n);
+      dr_pre = dn_pre * ghn * r * (1.f - r);
+      dz_pre = dz * z * (1.f - z);
+      dhn = dn_pre * r;
+      store_planes1(dgi, g0, dr_pre);
+      store_planes1(dgi, g0 + H, dz_pre);
+      store_planes1(dgi, g0 + 2 * H, dn_pre);
+      store_planes1(dgh, g0, dr_pre);
+      store_planes1(dgh, g0 + H, dz_pre);
+      store_planes1(dgh, g0 + 2 * H, dhn);
+      dh_prev[hidx] = g * z;
+      s_r += dr_pre; s_z += dz_pre; s_in += dn_pre; s_hn += dhn;
+    }
+    const float m2 = fmaxf(fabsf(dr_pre), fabsf(dz_pre));
+    const float mi = warp_max_f(fmaxf(m2, fabsf(dn_pre))), mh = warp_max_f(fmaxf(m2, fabsf(dhn)));
+    if (lane == 0) redm[par][warp] = make_float2(mi, mh);
+    __syncthreads();
+    const float2 t = lane < nw ? redm[par][lane] : make_float2(0.f, 0.f);
+    const float si = row_scale_pow2(warp_max_f(t.x)), sh = row_scale_pow2(warp_max_f(t.y));
+    if (j == 0) {
+      dgih.inv_scale[row] = 1.f / si;
+      dghh.inv_scale[row] = 1.f / sh;
+    }
+    if (on) {
+      dgih.p[g0] = __float2half_rn(dr_pre * si);
+      dgih.p[g0 + H] = __float2half_rn(dz_pre * si);
+      dgih.p[g0 + 2 * H] = __float2half_rn(dn_pre * si);
+      dghh.p[g0] = __float2half_rn(dr_pre * sh);
+      dghh.p[g0 + H] = __float2half_rn(dz_pre * sh);
+      dghh.p[g0 + 2 * H] = __float2half_rn(dhn * sh);
+    }
+  }
+  if (on) {
+    atomicAdd(d_b_ih + j, s_r);
+    atomicAdd(d_b_ih + H + j, s_z);
+    atomicAdd(d_b_ih + 2 * H + j, s_in);
+    atomicAdd(d_b_hh + j, s_r);
+    atomicAdd(d_b_hh + H + j, s_z);
+    atomicAdd(d_b_hh + 2 * H + j, s_hn);
+  }
+}
+
+// out[r] = max_j part[r, j]  (row maxima of |x - pred| from the E-step epilogue's per-tile partials)
+__global__ void __launch_bounds__(256) row_max_partials_kernel(int rows, int nblk, const float* __restrict__ part, float* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float m = 0.f;
+  for (int j = 0; j < nblk; ++j) m = fmaxf(m, part[static_cast<long long>(r) * nblk + j]);
+  out[r] = m;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1222,7 +1381,9 @@ __global__ void __launch_bounds__(256) estep_dpred_kernel(int rows, int D, int r
                                                           const float* __restrict__ kappa, const void* __restrict__ x,
                                                           int x_is_bf16, long long ldx, int km, int mv, float exp_scale,
                                                           __nv_bfloat16* __restrict__ p0, __nv_bfloat16* __restrict__ p1,
-                                                          __nv_bfloat16* __restrict__ p2, float* __restrict__ colsum) {
+                                                          __nv_bfloat16* __restrict__ p2, float* __restrict__ colsum,
+                                                          __half* __restrict__ ph, float* __restrict__ inv_scale,
+                                                          const float* __restrict__ row_dmax, float sigma) {
   const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (col >= D) return;
   const int r0 = blockIdx.y * rows_per_block;
@@ -1244,6 +1405,14 @@ __global__ void __launch_bounds__(256) estep_dpred_kernel(int rows, int D, int r
       for (int q = 0; q < 8; ++q) {
         const float d = dv[i][q];
         out[q] = d * fmaf(a, exp2f(d * d * exp_scale), -b);
+      }
+      if (ph) {
+        // row-scaled fp16 copy for the data-gradient contraction.  |delta * E(delta)| <= sigma * e^-1/2 for every
+        // delta, so max|dpred_r| <= 0.607 sigma |alpha_r| + max|delta_r| |beta_r| (max|delta_r| from the forward pass).
+        const float sc = row_scale_pow2(0.62f * sigma * fabsf(a) + __ldg(row_dmax + r) * fabsf(b));
+        if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[r] = 1.f / sc;
+        store_half4(ph, static_cast<long long>(r) * D + col, out[0] * sc, out[1] * sc, out[2] * sc, out[3] * sc);
+        store_half4(ph, static_cast<long long>(r) * D + col + 4, out[4] * sc, out[5] * sc, out[6] * sc, out[7] * sc);
       }
       if (kappa) {                                                   // if_gamma_prior == 0 only: + kappa * pred
         const float k = __ldg(kappa + r);
@@ -1335,8 +1504,10 @@ int ln_forward(int mode, int act, const LnDesc& d, const Op& out, float* mean, f
 
 int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out,
                      long long ldd, const Planes& dv, float* c1, float* c2, float* dgamma, float* dxw1, const Planes& dg1,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, RowF16 dvh) {
   VMM_TRY(check_ln(d, mode));
+  VMM_REQUIRE(!dvh.p || (mode == LN_BIAS && d.width != W1K && d.width % 512 == 0 && d.width / 16 <= 1024 && dv.n > 0 && dvh.inv_scale),
+              "ln_backward_rows: the row-scaled fp16 output exists only on the wide LN_BIAS path");
   VMM_REQUIRE(mean && rstd && d_out && c1 && c2 && ldd % 4 == 0 && (dv.n > 0 || mode == LN_ENC1),
               "ln_backward_rows: null argument");
   if (d.width == W1K) {                 // warp-per-row fast path
@@ -1352,7 +1523,7 @@ int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, cons
     return 0;
   }
   if (mode == LN_BIAS && d.width % 512 == 0 && d.width / 16 <= 1024 && dv.n > 0) {
-    lnw_backward_rows_kernel<<<d.rows, d.width / 16, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2);
+    lnw_backward_rows_kernel<<<d.rows, d.width / 16, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2, dvh);
     VMM_LAUNCHED();
     return 0;
   }
@@ -1390,21 +1561,22 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
 }
 
 int lnw_backward_fused(int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out, long long ldd,
-                       const Planes& dv, float* d_ln_g, float* d_ln_b, float* d_bias, cudaStream_t stream) {
+                       const Planes& dv, float* d_ln_g, float* d_ln_b, float* d_bias, cudaStream_t stream, RowF16 dvh) {
   VMM_TRY(check_ln(d, LN_BIAS));
+  VMM_REQUIRE(!dvh.p || dvh.inv_scale, "lnw_backward_fused: row-scaled output without a scale buffer");
   VMM_REQUIRE(lnw_backward_fused_ok(d.width) && dv.n > 0, "lnw_backward_fused: needs width 4096 and output planes");
   VMM_REQUIRE(mean && rstd && d_out && ldd % 4 == 0 && d_ln_g && d_ln_b && d_bias, "lnw_backward_fused: null argument");
   VMM_REQUIRE(((reinterpret_cast<uintptr_t>(d_ln_g) | reinterpret_cast<uintptr_t>(d_ln_b) |
                 reinterpret_cast<uintptr_t>(d_bias)) & 15) == 0, "lnw_backward_fused: gradient buffers must be 16-byte aligned");
   const int blocks = std::min(d.rows, device_sm_count());
-  lnw4k_backward_fused_kernel<<<blocks, 512, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, d_ln_g, d_ln_b, d_bias);
+  lnw4k_backward_fused_kernel<<<blocks, 512, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, d_ln_g, d_ln_b, d_bias, dvh);
   VMM_LAUNCHED();
   return 0;
 }
 
 int enc1_backward_fused(int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out, long long ldd,
                         float* dgamma, float* dxw1, const Planes& dg1, float* d_ln_g, float* d_ln_b, float* d_bias,
-                        float* d_w1b3, cudaStream_t stream) {
+                        float* d_w1b3, cudaStream_t stream, RowF16 dg1h) {
   VMM_TRY(check_ln(d, LN_ENC1));
   const int K = d.km / d.mv;
   VMM_REQUIRE(enc1_backward_fused_ok(d.width, K), "enc1_backward_fused: needs width 1024 and 1 <= K <= 6");
@@ -1416,7 +1588,7 @@ int enc1_backward_fused(int act, const LnDesc& d, const float* mean, const float
   const int blocks = std::min(groups, device_sm_count() * 2);
 #define VMM_ENC1B(NR)                                                                                                  \
   enc1_backward_fused_kernel<NR><<<blocks, 256, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dgamma, dxw1, dg1, d_ln_g, \
-                                                             d_ln_b, d_bias, d_w1b3)
+                                                             d_ln_b, d_bias, d_w1b3, dg1h)
   switch (K) {
     case 1: VMM_ENC1B(1); break;
     case 2: VMM_ENC1B(2); break;
@@ -1442,14 +1614,30 @@ int gru_forward(int rows, int H, const float* gi, const float* gh, const float* 
 
 int gru_backward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
                  const float* h_prev, const float* dh, const Planes& dgi, const Planes& dgh, float* dh_prev, float* d_b_ih,
-                 float* d_b_hh, cudaStream_t stream) {
+                 float* d_b_hh, cudaStream_t stream, RowF16 dgih, RowF16 dghh) {
   VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && dh && dgi.n >= 1 && dgh.n >= 1 && dh_prev &&
                   d_b_ih && d_b_hh, "gru_backward: bad argument");
+  if (dgih.p) {                                       // row-oriented variant: also writes the row-scaled fp16 copies
+    VMM_REQUIRE(H <= 1024 && dghh.p && dgih.inv_scale && dghh.inv_scale, "gru_backward: fp16 copies need H <= 1024 and both outputs");
+    const int threads = (H + 31) / 32 * 32;
+    const int rpb = std::max(1, ceil_div(rows, device_sm_count() * (2048 / threads)));
+    gru_backward_rows_kernel<<<ceil_div(rows, rpb), threads, 0, stream>>>(rows, H, rpb, gi, gh, b_ih, b_hh, h_prev, dh, dgi, dgh,
+                                                                         dh_prev, d_b_ih, d_b_hh, dgih, dghh);
+    VMM_LAUNCHED();
+    return 0;
+  }
   const int col_blocks = ceil_div(H, 256);
   const int rpb = pick_rows_per_block(rows, col_blocks);
   dim3 grid(col_blocks, ceil_div(rows, rpb));
   gru_backward_kernel<<<grid, 256, 0, stream>>>(rows, H, rpb, gi, gh, b_ih, b_hh, h_prev, dh, dgi, dgh, dh_prev, d_b_ih,
                                                 d_b_hh);
+  VMM_LAUNCHED();
+  return 0;
+}
+
+int row_max_partials(int rows, int nblk, const float* part, float* out, cudaStream_t stream) {
+  VMM_REQUIRE(rows > 0 && nblk > 0 && part && out, "row_max_partials: bad argument");
+  row_max_partials_kernel<<<ceil_div(rows, 256), 256, 0, stream>>>(rows, nblk, part, out);
   VMM_LAUNCHED();
   return 0;
 }
@@ -1560,8 +1748,11 @@ int act_backward(int act, long long n, const float* pre, float* grad, float drop
 
 int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x, int x_is_bf16, long long ldx,
                 int k_latent, int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
-                const Planes& dpred, float* colsum, cudaStream_t stream) {
+                const Planes& dpred, float* colsum, cudaStream_t stream, __half* dpred_h, float* inv_scale,
+                const float* row_dmax) {
   VMM_REQUIRE(rows > 0 && D > 0 && D % 8 == 0 && delta && alpha && beta, "estep_dpred: bad argument");
+  VMM_REQUIRE(!dpred_h || (!kappa && inv_scale && row_dmax && (reinterpret_cast<uintptr_t>(dpred_h) & 15) == 0),
+              "estep_dpred: the row-scaled fp16 copy needs kappa == NULL, a scale buffer and the row maxima of delta");
   VMM_REQUIRE(delta_fmt == VMM_DELTA_F16 || delta_fmt == VMM_DELTA_F32, "estep_dpred: delta_fmt must be fp16 or fp32");
   VMM_REQUIRE(dpred.n >= 1 && dpred.n <= 3 && dpred.fmt == VMM_FMT_BF16, "estep_dpred: dpred must be 1..3 bf16 planes");
   for (int i = 0; i < dpred.n; ++i)
@@ -1582,7 +1773,7 @@ int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x
 #define VMM_DPRED(DT, N)                                                                                            \
   estep_dpred_kernel<DT, N><<<grid, 256, 0, stream>>>(rows, D, rpb, static_cast<const DT*>(delta), alpha, beta, kappa, x,  \
                                                       x_is_bf16, ldx, km, m_views, exp_scale, dpred.p[0], dpred.p[1],   \
-                                                      dpred.p[2], colsum)
+                                                      dpred.p[2], colsum, dpred_h, inv_scale, row_dmax, sigma)
   if (delta_fmt == VMM_DELTA_F16) {
     if (dpred.n == 1) VMM_DPRED(__half, 1);
     else if (dpred.n == 2) VMM_DPRED(__half, 2);

@@ -4,11 +4,22 @@
 // Every kernel reads the fp32 output of a contraction and writes the bf16 operand planes the
 // next contraction consumes.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "internal.h"
 
 namespace vmm {
 
 enum { ACT_NONE = 0, ACT_ELU = 1, ACT_RELU = 2 };
+
+// Row-scaled fp16 copy of a gradient tensor for the data-gradient contractions ("fp16 gradient" mode): row r holds
+// fp16(v * s_r) with s_r the power of two that puts max|v_r| into [2^11, 2^12) (1 for an all-zero row) and
+// inv_scale[r] = 1 / s_r, which the contraction's epilogue multiplies back in (gemm_bf16(..., row_scale)).  Exact
+// per-row maxima: no overflow by construction; elements 2^-26 below their row's maximum flush to zero.
+struct RowF16 {
+  __half* p = nullptr;
+  float* inv_scale = nullptr;
+};
 enum { LN_BIAS = 0, LN_ENC1 = 1 };
 
 // One LayerNorm(+activation) stage.  The pre-normalisation value of element (row, j) is
@@ -72,7 +83,7 @@ int ln_forward(int mode, int act, const LnDesc& d, const Op& out, float* mean, f
 // row, and dG1 = -gamma*dv as operand planes (nullable).
 int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out,
                      long long ldd, const Planes& dv, float* c1, float* c2, float* dgamma, float* dxw1, const Planes& dg1,
-                     cudaStream_t stream);
+                     cudaStream_t stream, RowF16 dvh = RowF16());   // dvh: only the wide LN_BIAS fast path writes it
 
 // Column reductions of the same stage, accumulated (+=) into fp32 parameter gradients:
 // d_ln_g += sum_rows dy*xhat, d_ln_b += sum_rows dy, d_bias += sum_rows dv, and for LN_ENC1
@@ -84,13 +95,14 @@ int ln_backward_cols(int mode, int act, const LnDesc& d, const float* mean, cons
 // LN_BIAS stages of width 4096 (enc2, dec1): ln_backward_rows + ln_backward_cols in ONE pass over C and d_out.
 inline bool lnw_backward_fused_ok(int width) { return width == 4096; }
 int lnw_backward_fused(int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out, long long ldd,
-                       const Planes& dv, float* d_ln_g, float* d_ln_b, float* d_bias, cudaStream_t stream);
+                       const Planes& dv, float* d_ln_g, float* d_ln_b, float* d_bias, cudaStream_t stream,
+                       RowF16 dvh = RowF16());
 
 // enc1 (LN_ENC1, width 1024, K <= 6): ln_backward_rows + ln_backward_cols in ONE pass over G1 and d_out.
 inline bool enc1_backward_fused_ok(int width, int k_latent) { return width == 1024 && k_latent >= 1 && k_latent <= 6; }
 int enc1_backward_fused(int act, const LnDesc& d, const float* mean, const float* rstd, const float* d_out, long long ldd,
                         float* dgamma, float* dxw1, const Planes& dg1, float* d_ln_g, float* d_ln_b, float* d_bias,
-                        float* d_w1b3, cudaStream_t stream);
+                        float* d_w1b3, cudaStream_t stream, RowF16 dg1h = RowF16());
 
 // GRUCell gate math (train_nem.py:177,232; torch.nn.GRUCell, gate order r,z,n).
 // gi = e Wih^T, gh = h Whh^T are the raw contraction outputs [rows, 3H] (biases added here).
@@ -100,7 +112,7 @@ int gru_forward(int rows, int H, const float* gi, const float* gh, const float* 
 // path dh_prev = dh * z (the Whh contraction adds the rest), and accumulates the bias gradients.
 int gru_backward(int rows, int H, const float* gi, const float* gh, const float* b_ih, const float* b_hh,
                  const float* h_prev, const float* dh, const Planes& dgi, const Planes& dgh, float* dh_prev,
-                 float* d_b_ih, float* d_b_hh, cudaStream_t stream);
+                 float* d_b_ih, float* d_b_hh, cudaStream_t stream, RowF16 dgih = RowF16(), RowF16 dghh = RowF16());
 
 // Responsibilities from the fused E-step partial sums (train_nem.py:253-270):
 //   p = coef * sum_d exp(..) + 1e-10,  gamma = p / sum_k p.   Also folds the partial sums of
@@ -110,6 +122,8 @@ int gamma_forward(int B, int K, int Mv, int nblk, float sigma, const float* part
 // dgamma -> alpha[row] = dL/dp[row] * coef / sigma^2 (the per-row scalar of the E-step backward).
 int gamma_backward(int B, int K, int Mv, float sigma, const float* gamma, const float* inv_s, const float* dgamma,
                    float* alpha, cudaStream_t stream);
+
+int row_max_partials(int rows, int nblk, const float* part, float* out, cudaStream_t stream);   // out[r] = max_j part[r, j]
 
 // Outer loss of the last iteration (tools/NEM_utilities.py:98-128).  out[0..2] = total, intra, inter.
 int loss_forward(int B, int K, int Mv, int D, int if_gamma_prior, const float* gamma, const float* prior,

@@ -46,8 +46,10 @@ def _segs(pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]], a_mn: bool, b_mn: 
     return arr, M, N
 
 
-def gemm(pairs, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, splits=0, chain=0, check_kernel=False):
-    """C[M,N] (+)= sum_i A_i B_i^T.  A_i is (M,K) when a_mn is False, (K,M) when True; same for B."""
+def gemm(pairs, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, splits=0, chain=0, check_kernel=False,
+         row_scale=None):
+    """C[M,N] (+)= sum_i A_i B_i^T.  A_i is (M,K) when a_mn is False, (K,M) when True; same for B.
+    row_scale (float[M]): output row m is multiplied by row_scale[m] (vmm_gemm_rowscaled)."""
     arr, M, N = _segs(pairs, a_mn, b_mn)
     if out is None:
         assert not accumulate
@@ -56,6 +58,10 @@ def gemm(pairs, a_mn=False, b_mn=False, bias=None, out=None, accumulate=False, s
     if check_kernel:
         check(lib().vmm_gemm_check(M, N, len(pairs), arr, int(a_mn), int(b_mn), ptr(out), C.c_longlong(out.stride(0)),
                                    ptr(bias), int(accumulate), stream_ptr()))
+    elif row_scale is not None:
+        assert bias is None and row_scale.dtype == torch.float32 and row_scale.numel() == M and not a_mn
+        check(lib().vmm_gemm_rowscaled(M, N, len(pairs), arr, int(a_mn), int(b_mn), ptr(out), C.c_longlong(out.stride(0)),
+                                       ptr(row_scale), int(accumulate), int(splits), int(chain), stream_ptr()))
     else:
         check(lib().vmm_gemm_bf16(M, N, len(pairs), arr, int(a_mn), int(b_mn), ptr(out), C.c_longlong(out.stride(0)),
                                   ptr(bias), int(accumulate), int(splits), int(chain), stream_ptr()))

@@ -131,6 +131,33 @@ def test_run_em_bf16_features_mode(name):
     assert not bad, f"bf16-features parity (value, tolerance): {bad}"
 
 
+@pytest.mark.parametrize("name", ["cfg1_b8_k3_m12_t10", "prior0_b5_k2_m12_t3"])
+def test_run_em_bf16_h_mode(name):
+    """'bf16_h' = the bf16-features preset with row-scaled fp16 operands in every data-gradient contraction of the
+    BPTT chain (same number of tensor-core passes): gradient errors 2-3x below the plain preset - every tensor
+    outside dec1 within 7e-3 in max-norm (1e-2 for 'bf16'; what is left is the bf16 rounding of the weight-gradient
+    contractions, worst on matrices summed over few rows), dec1's tensors within 7e-3 in relative L2."""
+    _, cfg = load_golden(name)
+    nem, _ = seeded_models(cfg)
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    xb = x.bfloat16()
+    ref, pn = _oracle(cfg, nem, xb.float(), torch.float32)
+    res, nem_c = _cuda(cfg, nem, xb, "bf16_h", torch.bfloat16)
+    for k in ("h", "gamma", "nem_loss"):
+        assert rel_err(res[k].reshape(-1), ref[k].reshape(-1)) < 1e-3, k
+    named = dict(nem_c.named_parameters())
+    bad = {}
+    for n, p in pn.items():
+        if p.grad is None:
+            assert named[n].grad is None
+            continue
+        a, b = named[n].grad.double().cpu(), p.grad.double()
+        e = ((a - b).norm() / b.norm()).item() if n.startswith("dec1.0") or n == "dec1.1.bias" else rel_err(named[n].grad, p.grad)
+        if not e < 7e-3:
+            bad[n] = e
+    assert not bad, bad
+
+
 def test_run_em_bf16_fast_forward():
     """Single-pass bf16 (inference grade): forward state within 5e-2 of the reference at cfg1."""
     name = "cfg1_b8_k3_m12_t10"

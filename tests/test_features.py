@@ -82,8 +82,8 @@ def test_precision_rules_of_the_bf16_preset():
     from types import SimpleNamespace as NS
     from multi_view_sort_b200.functional import (DEC3_SINGLE_MIN_SIGMA, FWD_CONTRACTIONS, FWD_SINGLE, PRECISIONS, fwd_modes,
                                                  precision_planes, resolve_precision)
-    assert precision_planes((1, 0, 1, 0)) == (1, 0, 1, 0, 0, 0)
-    assert precision_planes("fp32") == PRECISIONS["fp32"]
+    assert precision_planes((1, 0, 1, 0)) == (1, 0, 1, 0, 0, 0, 0)
+    assert precision_planes("fp32") == PRECISIONS["fp32"] + (0,)
     dec3 = fwd_modes(dec3=FWD_SINGLE)
     every = fwd_modes(**{n: FWD_SINGLE for n in FWD_CONTRACTIONS})
     assert dec3 == 1 << 14 and every == 0x15555

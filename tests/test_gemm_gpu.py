@@ -243,3 +243,30 @@ def test_cta_pair_kernel_is_bit_identical_to_single_cta(M, N, K, a_mn, b_mn):
         lib().vmm_gemm_force_ncta(0)
     torch.cuda.synchronize()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_row_scaled_fp16_operand(accumulate):
+    """vmm_gemm_rowscaled: A rows stored as fp16(a * s_m) with per-row powers of two spanning 40 binades, the
+    contraction un-scales them in its epilogue - the result matches the unscaled product to fp16 operand precision
+    although most rows of A would underflow or overflow fp16 without the scale."""
+    from multi_view_sort_b200 import ops
+    M, N, K = 300, 520, 1024
+    A = _rand((M, K), 61)
+    A = A * torch.exp2(torch.randint(-30, 10, (M, 1), device="cuda").float())          # rows of very different magnitude
+    W = _rand((K, N), 62, 0.05)                                                        # weight stored [n=K... ] MN-major
+    amax = A.abs().amax(1, keepdim=True)
+    s = torch.exp2(12 - torch.ceil(torch.log2(amax)))
+    Ah = (A * s).half()
+    assert torch.isfinite(Ah).all()
+    Wh = W.half()
+    C0 = _rand((M, N), 63) if accumulate else None
+    out = C0.clone() if accumulate else None
+    out = ops.gemm([(Ah, Wh)], False, True, out=out, accumulate=accumulate, row_scale=(1.0 / s).reshape(-1).contiguous())
+    torch.cuda.synchronize()
+    ref = (Ah.double() / s.double()) @ Wh.double()
+    if accumulate:
+        ref = ref + C0.double()
+    err = ((out.double() - ref).abs() / ref.abs().amax(1, keepdim=True).clamp_min(1e-300)).max().item()
+    assert err < 2e-5, err                                                             # per ROW: every row keeps its precision
+    assert _relmax(out.double() - (C0.double() if accumulate else 0), A.double() @ W.double()) < 2e-3   # vs the fp32 operands

@@ -9,17 +9,22 @@ from oracle.make_golden import seeded_models
 from helpers import load_golden, rel_err
 from test_em_gpu import _oracle, _cuda
 
-for B in [int(a) for a in sys.argv[1:]] or [8, 32, 96]:
+presets = [a for a in sys.argv[1:] if not a.isdigit()] or ["bf16"]
+for B in [int(a) for a in sys.argv[1:] if a.isdigit()] or [8, 32, 96]:
     _, cfg = load_golden("cfg1_b8_k3_m12_t10")
     cfg = dict(cfg, B=B)
     nem, _ = seeded_models(cfg)
     x, _ = O.make_inputs(B, cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
     xb = x.bfloat16()
     ref, pn = _oracle(cfg, nem, xb.float(), torch.float32)
-    res, nem_c = _cuda(cfg, nem, xb, "bf16", torch.bfloat16)
-    named = dict(nem_c.named_parameters())
-    g = {n: rel_err(named[n].grad, p.grad) for n, p in pn.items() if p.grad is not None}
-    l2 = {n: ((named[n].grad.double().cpu() - p.grad.double()).norm() / p.grad.double().norm()).item() for n, p in pn.items() if p.grad is not None}
-    w = max(g, key=g.get)
-    print(f"B={B:4d} h {rel_err(res['h'], ref['h']):.1e} gamma {rel_err(res['gamma'].reshape(-1), ref['gamma'].reshape(-1)):.1e} "
-          f"grad max-norm worst {g[w]:.2e} ({w}) median {sorted(g.values())[len(g)//2]:.2e}; relative-L2 worst {max(l2.values()):.2e}", flush=True)
+    for preset in presets:
+        for p in nem.parameters():
+            p.grad = None
+        res, nem_c = _cuda(cfg, nem, xb, preset, torch.bfloat16)
+        named = dict(nem_c.named_parameters())
+        g = {n: rel_err(named[n].grad, p.grad) for n, p in pn.items() if p.grad is not None}
+        l2 = {n: ((named[n].grad.double().cpu() - p.grad.double()).norm() / p.grad.double().norm()).item() for n, p in pn.items() if p.grad is not None}
+        w = max(g, key=g.get)
+        print(f"B={B:4d} {preset:8s} h {rel_err(res['h'], ref['h']):.1e} gamma {rel_err(res['gamma'].reshape(-1), ref['gamma'].reshape(-1)):.1e} "
+              f"grad max-norm worst {g[w]:.2e} ({w}) median {sorted(g.values())[len(g)//2]:.2e}; relative-L2 worst {max(l2.values()):.2e}", flush=True)
+        nem = nem.cpu()
