@@ -10,6 +10,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvmm_b200.so")
+if os.environ.get("VMM_B200_LIB"):          # A/B builds of the same sources (tools/): never a fallback path
+    LIB_PATH = os.environ["VMM_B200_LIB"]
 _lib = None
 
 

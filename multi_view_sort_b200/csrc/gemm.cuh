@@ -45,7 +45,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
-constexpr int GROUP_M = 16;
+#ifndef VMM_GROUP_M
+#define VMM_GROUP_M 32   // m-blocks per rasterisation group (measured 8 / 16 / 32: 171.3 / 170.6 / 169.4 ms of contractions per step)
+#endif
+constexpr int GROUP_M = VMM_GROUP_M;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;   // per epilogue warp (XOR-swizzled 32x32 fp32 tile)
 
 enum { EPI_STORE = 0, EPI_RED = 1, EPI_ESTEP = 2, EPI_EBWD = 3 };
