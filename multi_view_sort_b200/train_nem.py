@@ -58,7 +58,7 @@ parser.add_argument("-arch", type=int, help="net architecture", default=0)
 parser.add_argument("-e_sigma", type=float, help="net architecture", default=0.1)
 parser.add_argument("-dataset", type=str, help="dataset to use, MNet40, MNet10, ShapeNet are supported", default='MNet40')
 # additions of this implementation
-parser.add_argument("-precision", type=str, default="fp32", help="fp32 | bf16 | bf16_fast (tensor-core operand precision)")
+parser.add_argument("-precision", type=str, default="fp32", help="fp32 | bf16 | bf16_h | bf16_fast (tensor-core operand precision, DESIGN.md 6)")
 parser.add_argument("-model_path", type=str, default="", help="test mode: directory holding <name>/NEM and <name>/MV_C_Net "
                     "(the reference hard-codes /mnt/cloud_disk/huangjj/exp_mvcnn/)")
 parser.add_argument("-feature_out", type=str, default="", help="test mode: where the descriptors are written")
