@@ -45,7 +45,9 @@ class GradBucket:
         return [p for p in self.params if p.grad is not None]
 
     def allreduce_mean(self, group=None) -> int:
-        """Average gradients over the group in place; returns the bucket size in bytes."""
+        """Average gradients over the group; returns the bucket size in bytes.  One fused copy packs the gradients
+        into the flat buffer, one collective averages it (NCCL's AVG; SUM + scale on backends without it), and the
+        parameters' .grad are re-pointed at views of the flat buffer (no copy back)."""
         live = self._live()
         if not live:
             return 0
@@ -53,18 +55,19 @@ class GradBucket:
         dev = live[0].grad.device
         if self.flat is None or self.flat.numel() != n or self.flat.device != dev:
             self.flat = torch.empty(n, dtype=torch.float32, device=dev)
-        off = 0
+        views, off = [], 0
         for p in live:
             k = p.grad.numel()
-            self.flat[off:off + k].copy_(p.grad.reshape(-1))
+            views.append(self.flat[off:off + k].view_as(p.grad))
             off += k
+        torch._foreach_copy_(views, [p.grad for p in live])
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(world)
-        off = 0
-        for p in live:
-            k = p.grad.numel()
-            p.grad.copy_(self.flat[off:off + k].view_as(p.grad))
-            off += k
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(world)
+        for p, v in zip(live, views):
+            p.grad = v
         return n * 4
