@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map construction, tile/split planning, launch,
 // and the extern "C" entry points vmm_gemm_bf16 / vmm_estep_forward / vmm_estep_backward.
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -90,6 +91,28 @@ static int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long inner, long
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner %lld outer %lld pitch %lld)", static_cast<int>(r),
               inner, outer, pitch);
+    return VMM_E_CUDA;
+  }
+  return 0;
+}
+
+// fp32 tensor [outer][inner] written by the epilogues with TMA stores: 32 x 32 boxes (128-byte rows), 128-byte swizzle
+// (the layout of the warps' staging tiles); parts of a box outside the tensor are clipped by the hardware.
+static int make_tmap_f32_store(CUtensorMap* m, void* ptr, long long inner, long long outer, long long pitch) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return VMM_E_CUDA;
+  }
+  VMM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && pitch % 4 == 0 && inner > 0 && outer > 0, "bad fp32 store tensor");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32 store) failed with CUresult %d", static_cast<int>(r));
     return VMM_E_CUDA;
   }
   return 0;
@@ -251,6 +274,9 @@ int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool 
   p.row_scale = row_scale;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 4 == 0 &&
               (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) ? 1 : 0;
+  static const bool tma_epilogue = !(getenv("VMM_TMA_EPILOGUE") && getenv("VMM_TMA_EPILOGUE")[0] == '0');   // A/B switch
+  p.tma_c = (tma_epilogue && p.vec_ok && N % 4 == 0) ? 1 : 0;
+  if (p.tma_c) VMM_TRY(make_tmap_f32_store(&p.tma_out, C, N, M, ldc));
   if (accumulate) return launch_major<EPI_RED, float, 1>(p, a_mn, b_mn, stream);
   return launch_major<EPI_STORE, float, 1>(p, a_mn, b_mn, stream);
 }
@@ -328,6 +354,7 @@ int estep_forward(int rows, int D, int zk, const Planes& z, const Planes& w3, co
   VMM_REQUIRE((reinterpret_cast<uintptr_t>(delta) & 15) == 0, "delta must be 16-byte aligned");
   p.delta_out = delta;
   p.ldo = D;
+  if (delta && delta_fmt == VMM_DELTA_F32) VMM_TRY(make_tmap_f32_store(&p.tma_out, delta, D, rows, D));
   // the kernel's OPL template slot selects the delta output of the forward epilogue: 1 none, 2 fp16, 3 fp32
   if (x_is_bf16) {
     if (delta_fmt == VMM_DELTA_F16) return launch_major<EPI_ESTEP, __nv_bfloat16, 2>(p, false, false, stream);

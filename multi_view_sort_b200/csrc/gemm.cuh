@@ -56,6 +56,7 @@ enum { EPI_STORE = 0, EPI_RED = 1, EPI_ESTEP = 2, EPI_EBWD = 3 };
 struct alignas(64) GemmParams {
   CUtensorMap tma_a[VMM_MAX_SEG];
   CUtensorMap tma_b[VMM_MAX_SEG];
+  CUtensorMap tma_out;       // ESTEP with fp32 delta: the delta tensor, written with TMA stores from the staging tiles
   int seg_kb[VMM_MAX_SEG];   // k-blocks (of BK) in each segment
   unsigned seg_flags[VMM_MAX_SEG];   // VMM_SEG_* bits of each segment
   int nseg;
@@ -65,6 +66,7 @@ struct alignas(64) GemmParams {
   int num_m_blk, num_n_blk;
   int splits;
   int vec_ok;                // C rows are 16-byte aligned -> float4 path
+  int tma_c;                 // C is written through tma_out (TMA store / reduce-add of the staging tiles)
   float* C;
   long long ldc;
   const float* bias;         // [N] or null (EPI_STORE); b3 for ESTEP/EBWD
@@ -213,7 +215,38 @@ __device__ __forceinline__ void x_stage(const XRegs<XT>& xr, float4* st, int lan
 // STORE / RED: accumulator chunk -> staging (row per lane) -> coalesced 4-rows-per-instruction.
 template <int EPI>
 __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint32_t (&v)[32], float4* st, int row0,
-                                                int col0, int lane, bool add_to_c) {
+                                                int col0, int lane, bool add_to_c, bool& st_busy) {
+  if (p.tma_c) {
+    // TMA path: scale / bias in the row-per-lane layout, stage the 32x32 tile (its XOR swizzle IS the SWIZZLE_128B box
+    // layout) and let ONE bulk tensor store - or reduce-add, for accumulation chains, split-K and gradient
+    // accumulation - write it: no read-modify-write loads, no per-element guards (the hardware clips the box).
+    if (st_busy) {
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
+    float rs = 1.f;
+    if (p.row_scale && row0 + lane < p.M) rs = __ldg(p.row_scale + row0 + lane);
+    const bool add_bias = (EPI == EPI_STORE) && !add_to_c && p.bias != nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 val = make_float4(__uint_as_float(v[4 * j]) * rs, __uint_as_float(v[4 * j + 1]) * rs,
+                               __uint_as_float(v[4 * j + 2]) * rs, __uint_as_float(v[4 * j + 3]) * rs);
+      if (add_bias && col0 + j * 4 < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
+        val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
+      }
+      st[st_slot(lane, j)] = val;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (EPI == EPI_RED || add_to_c) tma_reduce_add_2d(&p.tma_out, st, col0, row0);
+      else tma_store_2d(&p.tma_out, st, col0, row0);
+      tma_store_commit();
+    }
+    st_busy = true;
+    return;
+  }
   // For the read-modify-write chains, issue all eight loads of the running sum before anything
   // depends on them (one exposed L2 round trip per chunk instead of eight).
   float4 old[8];
@@ -436,6 +469,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     float4* st = reinterpret_cast<float4*>(epi_smem + ew * EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
+    bool st_busy = false;                      // a TMA store of this warp's staging tile may still be reading it
     const uint32_t tempty0 = NCTA == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;   // the leader's barriers
     for (int work = worker; work < total_work; work += nworkers) {
       const WorkItem w = decode_work(p, work, NCTA, rank);
@@ -481,8 +515,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr0 + static_cast<uint32_t>((c + 1) * 32), vn);
         if (col0 < p.N) {                                            // warp-uniform
           if constexpr (!kFused) {
-            epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0);
+            epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0, st_busy);
           } else {
+            if constexpr (kSave == 2) {
+              if (st_busy) {
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+                st_busy = false;
+              }
+            }
             x_stage<XT>(xr, st, lane);
             if (c + 1 < NCH) x_fetch<XT>(p, xr, xrows, col0 + 32, lane);
             __syncwarp();
@@ -536,19 +577,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               }
               __syncwarp();
             } else if constexpr (kSave == 2) {
+              // fp32 delta: the swizzled staging tile IS a SWIZZLE_128B box - one TMA store writes it (clipped at the
+              // tensor's edges) while the warp goes on; the tile is reused only after the TMA engine has read it
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 st[st_slot(lane, j)] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+              fence_proxy_async();
               __syncwarp();
-              float* outp = static_cast<float*>(p.delta_out);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int r = j * 4 + (lane >> 3), c4 = lane & 7;
-                const int grow = row0 + r, gcol = col0 + c4 * 4;
-                if (grow < p.M && gcol < p.N)
-                  *reinterpret_cast<float4*>(outp + static_cast<long long>(grow) * p.ldo + gcol) = st[st_slot(r, c4)];
+              if (lane == 0) {
+                tma_store_2d(&p.tma_out, st, col0, row0);
+                tma_store_commit();
               }
-              __syncwarp();
+              st_busy = true;
             }
             if constexpr (EPI == EPI_EBWD) {
               if (p.colsum) {
@@ -614,6 +654,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
       }
+    }
+    if (kSave == 2 || (!kFused && p.tma_c)) {
+      if (lane == 0) tma_store_wait_all();               // every TMA store of this warp has landed before the CTA exits
+      __syncwarp();
     }
   }
 
