@@ -221,7 +221,13 @@ __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint3
     // layout) and let ONE bulk tensor store - or reduce-add, for accumulation chains, split-K and gradient
     // accumulation - write it: no read-modify-write loads, no per-element guards (the hardware clips the box).
     if (st_busy) {
-      if (lane == 0) tma_store_wait_read();
+      // the staging tile is free once the TMA engine has read it; an accumulation chain also needs the operation that
+      // last wrote THESE global addresses - this warp's group of four chunks ago (one chain earlier, 4 chunks per
+      // chain) - to have completed, bulk operations being unordered among themselves
+      if (lane == 0) {
+        tma_store_wait_read();
+        if (add_to_c) tma_store_wait_keep3();
+      }
       __syncwarp();
     }
     float rs = 1.f;
@@ -463,6 +469,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     // the tile's columns in halves; each walks its half in 32-column chunks with the TMEM
     // load of chunk c+1 and the feature fetch of chunk c+1 in flight while chunk c is processed.
     constexpr int NCH = BN / 2 / 32;
+    static_assert(NCH == 4, "epi_store_chunk (tma_store_wait_keep3) assumes 4 chunks per accumulation chain and warp");
     const int ew = warp - 2;
     const int lane_grp = warp & 3;
     const int col_half = ew >> 2;
