@@ -285,7 +285,8 @@ VMM_API int vmm_em_step_forward(const vmm_em_config* cfg, const vmm_em_params* p
 
 /* Address of a named intermediate of iteration `iter` inside `workspace` (for stage-level
  * parity tests and debugging); returns NULL for an unknown name.  Names: "xw1", "g1", "a_hi",
- * "g2", "e_hi", "gi", "gh", "h", "h_hi", "g4", "u_hi", "g5", "z_hi", "z_lo", "gamma", "row_sq". */
+ * "g2", "e_hi", "gi", "gh", "h", "h_hi", "g4", "u_hi", "g5", "z_hi", "z_lo", "gamma", "row_sq", "mean2", "rstd2", "mean4",
+ * "rstd4" (LayerNorm row statistics of enc2 / dec1), "delta" (saved x - pred, training with save_delta only). */
 VMM_API const void* vmm_em_workspace_ptr(const vmm_em_config* cfg, const void* workspace, const char* name, int iter);
 
 /* ---------------------------------------------------------------------------------------

@@ -691,7 +691,8 @@ const void* vmm_em_workspace_ptr(const vmm_em_config* cfg, const void* workspace
   struct { const char* n; const void* p; } tab[] = {
       {"xw1", ws.xw1}, {"g1", b.g1}, {"a_hi", b.a.f.p[0]}, {"g2", b.g2}, {"e_hi", b.e.f.p[0]}, {"gi", b.gi}, {"gh", b.gh},
       {"h", b.h}, {"h_hi", b.hp.f.p[0]}, {"g4", b.g4}, {"u_hi", b.u.f.p[0]}, {"g5", b.g5}, {"z_hi", b.z.f.p[0]}, {"z_lo", b.z.f.p[1]},
-      {"gamma", b.gamma}, {"row_sq", ws.row_sq}};
+      {"gamma", b.gamma}, {"row_sq", ws.row_sq}, {"mean4", b.mean4}, {"rstd4", b.rstd4}, {"mean2", b.mean2}, {"rstd2", b.rstd2},
+      {"delta", b.delta}};
   for (auto& e : tab)
     if (strcmp(e.n, name) == 0) return e.p;
   return nullptr;

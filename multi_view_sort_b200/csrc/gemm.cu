@@ -126,14 +126,18 @@ template <int BN, bool A_MN, bool B_MN, int EPI, typename XT, int OPL, int NCTA>
 static int launch_one(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, NCTA>;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, XT, OPL, NCTA>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-  });
-  if (attr_err != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
-    return VMM_E_CUDA;
+  // the dynamic shared-memory opt-in is a per-device attribute of the function: set it once per (kernel, device)
+  static std::atomic<unsigned long long> opted_in{0ull};
+  int dev = 0;
+  VMM_CHECK_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(opted_in.load(std::memory_order_acquire) & bit)) {
+    const cudaError_t attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (attr_err != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
+      return VMM_E_CUDA;
+    }
+    opted_in.fetch_or(bit, std::memory_order_release);
   }
   const int units = ceil_div(p.num_m_blk, NCTA);
   const int total_work = units * p.num_n_blk * p.splits;

@@ -215,18 +215,19 @@ __device__ __forceinline__ void x_stage(const XRegs<XT>& xr, float4* st, int lan
 // STORE / RED: accumulator chunk -> staging (row per lane) -> coalesced 4-rows-per-instruction.
 template <int EPI>
 __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint32_t (&v)[32], float4* st, int row0,
-                                                int col0, int lane, bool add_to_c, bool& st_busy) {
+                                                int col0, int lane, bool add_to_c, bool& st_busy, int groups_per_chain) {
   if (p.tma_c) {
     // TMA path: scale / bias in the row-per-lane layout, stage the 32x32 tile (its XOR swizzle IS the SWIZZLE_128B box
     // layout) and let ONE bulk tensor store - or reduce-add, for accumulation chains, split-K and gradient
     // accumulation - write it: no read-modify-write loads, no per-element guards (the hardware clips the box).
     if (st_busy) {
       // the staging tile is free once the TMA engine has read it; an accumulation chain also needs the operation that
-      // last wrote THESE global addresses - this warp's group of four chunks ago (one chain earlier, 4 chunks per
-      // chain) - to have completed, bulk operations being unordered among themselves
+      // last wrote THESE global addresses - this warp's group of one chain earlier, i.e. `groups_per_chain` groups ago
+      // (4 chunks per chain, fewer on a tile clipped at the N edge: chunks past N issue nothing) - to have completed,
+      // bulk operations being unordered among themselves
       if (lane == 0) {
         tma_store_wait_read();
-        if (add_to_c) tma_store_wait_keep3();
+        if (add_to_c) tma_store_wait_keep(groups_per_chain - 1);
       }
       __syncwarp();
     }
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     // the tile's columns in halves; each walks its half in 32-column chunks with the TMEM
     // load of chunk c+1 and the feature fetch of chunk c+1 in flight while chunk c is processed.
     constexpr int NCH = BN / 2 / 32;
-    static_assert(NCH == 4, "epi_store_chunk (tma_store_wait_keep3) assumes 4 chunks per accumulation chain and warp");
+    static_assert(NCH == 4, "epi_store_chunk (tma_store_wait_keep) handles up to 4 chunks per accumulation chain and warp");
     const int ew = warp - 2;
     const int lane_grp = warp & 3;
     const int col_half = ew >> 2;
@@ -482,6 +483,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const WorkItem w = decode_work(p, work, NCTA, rank);
       const int row0 = w.m_blk * BM + lane_grp * 32;                 // first row of this warp
       const int nbase = w.n_blk * BN + col_half * (BN / 2);
+      const int groups_per_chain = min(NCH, max(0, (p.N - nbase + 31) / 32));   // chunks of this warp that lie inside N
       for (int ch = w.c0; ch < w.c1; ++ch) {
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                               static_cast<uint32_t>(acc * BN + col_half * (BN / 2));
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr0 + static_cast<uint32_t>((c + 1) * 32), vn);
         if (col0 < p.N) {                                            // warp-uniform
           if constexpr (!kFused) {
-            epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0, st_busy);
+            epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0, st_busy, groups_per_chain);
           } else {
             if constexpr (kSave == 2) {
               if (st_busy) {

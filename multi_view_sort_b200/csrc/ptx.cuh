@@ -78,8 +78,15 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// all but the 3 most recent groups have completed (their global writes are performed)
-__device__ __forceinline__ void tma_store_wait_keep3() { asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); }
+// all but the `keep` (0..3) most recent groups have completed (their global writes are performed)
+__device__ __forceinline__ void tma_store_wait_keep(int keep) {
+  switch (keep) {
+    case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+  }
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- clusters / CTA pairs ---------------------------------------------------------------

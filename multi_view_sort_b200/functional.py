@@ -215,6 +215,8 @@ class _EMFunction(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.module = module
         ctx.nparams = len(params)
+        if module.__dict__.get("keep_workspace"):           # tests / tools: stage-level inspection through vmm_em_workspace_ptr
+            module.__dict__["_vmm_last_workspace"] = (cfg, ws)
         if training:
             ctx.save_for_backward(x, gamma0, prior, ws, weights, *params)
         return h, gamma, loss

@@ -109,9 +109,15 @@ def _stage_seed(seed: int, stage: int, it: int) -> int:
 # ----------------------------------------------------------------------------
 # one EM iteration (train_nem.py:219-294)
 # ----------------------------------------------------------------------------
-def run_inner_rnn(p: Params, masked: torch.Tensor, h_old: torch.Tensor, b: int, k: int, m: int, drop=None):
+def run_inner_rnn(p: Params, masked: torch.Tensor, h_old: torch.Tensor, b: int, k: int, m: int, drop=None,
+                  dec1_mask: Optional[torch.Tensor] = None, dec1_pre: Optional[list] = None):
     """train_nem.py:219-245.  drop=None: eval mode (Dropout = identity); drop=(p, seed, iteration): the
-    Dropout(0.5) layers of enc1 / enc2 / dec1 (train_nem.py:172,175,181) with the library's masks."""
+    Dropout(0.5) layers of enc1 / enc2 / dec1 (train_nem.py:172,175,181) with the library's masks.
+
+    ReLU-kink diagnostics (tests/test_em_gpu.py::test_bf16_dec1_relu_flips): `dec1_pre` collects dec1's
+    pre-activation; `dec1_mask` (0/1, same shape) replaces ReLU by `pre * mask`, i.e. evaluates the network with
+    ANOTHER implementation's decision about which dec1 units are active - the two differ only for units whose
+    pre-activation is within that implementation's forward rounding error of zero."""
     x = masked.view(b * k * m, -1)
     a = F.elu(F.layer_norm(F.linear(x, p["enc1.0.weight"], p["enc1.0.bias"]), (ENC1_W,),
                            p["enc1.1.weight"], p["enc1.1.bias"]))
@@ -124,8 +130,15 @@ def run_inner_rnn(p: Params, masked: torch.Tensor, h_old: torch.Tensor, b: int, 
         e = e * dropout_mask(drop[0], _stage_seed(drop[1], 2, drop[2]), e.shape, e.dtype)
     h = torch._VF.gru_cell(e, h_old, p["rnn_nem.weight_ih"], p["rnn_nem.weight_hh"],
                            p["rnn_nem.bias_ih"], p["rnn_nem.bias_hh"])
-    u = F.relu(F.layer_norm(F.linear(h, p["dec1.0.weight"], p["dec1.0.bias"]), (DEC1_W,),
-                            p["dec1.1.weight"], p["dec1.1.bias"]))
+    if dec1_mask is None and dec1_pre is None:
+        u = F.relu(F.layer_norm(F.linear(h, p["dec1.0.weight"], p["dec1.0.bias"]), (DEC1_W,),
+                                p["dec1.1.weight"], p["dec1.1.bias"]))
+    else:
+        pre = F.layer_norm(F.linear(h, p["dec1.0.weight"], p["dec1.0.bias"]), (DEC1_W,),
+                           p["dec1.1.weight"], p["dec1.1.bias"])
+        if dec1_pre is not None:
+            dec1_pre.append(pre.detach())
+        u = F.relu(pre) if dec1_mask is None else pre * dec1_mask.to(pre.dtype)
     if drop:
         u = u * dropout_mask(drop[0], _stage_seed(drop[1], 3, drop[2]), u.shape, u.dtype)
     v = F.layer_norm(F.linear(u, p["dec2.0.weight"], p["dec2.0.bias"]), (DEC3_IN * m,),
@@ -150,13 +163,13 @@ def e_step(pred: torch.Tensor, t_data: torch.Tensor, sigma: float):
     return probs / probs.sum(1).unsqueeze(1)
 
 
-def em_iteration(p: Params, x: torch.Tensor, state, sigma: float, drop=None):
+def em_iteration(p: Params, x: torch.Tensor, state, sigma: float, drop=None, dec1_mask=None, dec1_pre=None):
     """train_nem.py:272-294.  x: (B,1,M,D); state = (h, pred, gamma)."""
     h_old, pred_old, gamma_old = state
     b, k, m = gamma_old.shape[0], gamma_old.shape[1], gamma_old.shape[2]
     delta = x - pred_old
     masked = delta * gamma_old
-    pred, h = run_inner_rnn(p, masked, h_old, b, k, m, drop)
+    pred, h = run_inner_rnn(p, masked, h_old, b, k, m, drop, dec1_mask, dec1_pre)
     gamma = e_step(pred, x, sigma)
     return h, pred, gamma
 
@@ -237,9 +250,10 @@ def head_forward(p: Params, h: torch.Tensor, gamma: torch.Tensor, k: int, if_sor
 def run_em(p: Params, x: torch.Tensor, k: int, iters: int, sigma: float = 0.1,
            init_type: str = "bin_uniform", if_gamma_prior: int = 1, stop_gamma_grad: int = 0,
            gamma0: Optional[torch.Tensor] = None, gamma_prior: Optional[torch.Tensor] = None,
-           keep_all: bool = False, drop=None):
+           keep_all: bool = False, drop=None, dec1_masks=None, dec1_pre: Optional[list] = None):
     """T iterations + the last iteration's outer loss.  x: (B,M,D).
-    Returns dict(h, gamma, pred, nem_loss, intra, inter[, hist])."""
+    Returns dict(h, gamma, pred, nem_loss, intra, inter[, hist]).  dec1_masks / dec1_pre: per-iteration
+    ReLU-kink diagnostics, see run_inner_rnn."""
     B, M, D = x.shape
     hidden = p["rnn_nem.weight_hh"].shape[1]
     h, pred, g0, gp = init_state(B, k, M, D, hidden, init_type)
@@ -253,7 +267,8 @@ def run_em(p: Params, x: torch.Tensor, k: int, iters: int, sigma: float = 0.1,
     xin = x.unsqueeze(1)
     hist = []
     for it in range(iters):
-        state = em_iteration(p, xin, state, sigma, (drop[0], drop[1], it) if drop else None)
+        state = em_iteration(p, xin, state, sigma, (drop[0], drop[1], it) if drop else None,
+                             dec1_masks[it] if dec1_masks is not None else None, dec1_pre)
         if keep_all:
             hist.append(state)
     h, pred, gamma = state

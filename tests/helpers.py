@@ -37,3 +37,31 @@ def params_of(module, requires_grad=True, dtype=None, device=None):
             t = t.to(device)
         out[k] = t.requires_grad_(requires_grad)
     return out
+
+
+def cuda_dec1_pre(nem, T):
+    """dec1's pre-activation (the input of the ONE ReLU of the path, train_nem.py:181) of every EM iteration of the last
+    CUDA training forward of `nem` (needs nem.keep_workspace = True), recomputed from the library's workspace - the raw
+    contraction output g4 and the LayerNorm row statistics - with the kernels' own formula."""
+    import ctypes as C
+    from multi_view_sort_b200._lib import lib
+    cfg, ws = nem.__dict__["_vmm_last_workspace"]
+    L = lib()
+    L.vmm_em_workspace_ptr.restype = C.c_void_p
+    R, W = cfg.B * cfg.K, 4096
+    base = ws.data_ptr()
+    named = dict(nem.named_parameters())
+    b4, g, be = named["dec1.0.bias"].detach(), named["dec1.1.weight"].detach(), named["dec1.1.bias"].detach()
+    wsf = ws.view(torch.float32)
+    out = []
+    for t in range(T):
+        def view(name, n):
+            p = L.vmm_em_workspace_ptr(C.byref(cfg), C.c_void_p(base), name.encode(), t)
+            assert p, name
+            off = (p - base) // 4
+            return wsf[off:off + n]
+        g4 = view("g4", R * W).view(R, W)
+        mean, rstd = view("mean4", R), view("rstd4", R)
+        xh = ((g4 + b4) - mean[:, None]) * rstd[:, None]
+        out.append(torch.addcmul(be, xh, g).cpu())
+    return out

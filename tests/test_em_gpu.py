@@ -27,18 +27,50 @@ def _probe(cfg):
     return wh, wg
 
 
-def _oracle(cfg, nem, x, dtype):
+def _oracle(cfg, nem, x, dtype, dec1_masks=None, dec1_pre=None):
     pn = params_of(nem, dtype=dtype)
-    r = O.run_em(pn, x.to(dtype), cfg["K"], cfg["T"], cfg["sigma"], "bin_uniform", cfg["if_gamma_prior"], cfg["stop_gamma_grad"])
+    r = O.run_em(pn, x.to(dtype), cfg["K"], cfg["T"], cfg["sigma"], "bin_uniform", cfg["if_gamma_prior"], cfg["stop_gamma_grad"],
+                 dec1_masks=dec1_masks, dec1_pre=dec1_pre)
     wh, wg = _probe(cfg)
     loss = r["nem_loss"] + (r["h"] * wh.to(dtype)).sum() + (r["gamma"] * wg.to(dtype)).sum()
     loss.backward()
     return r, pn
 
 
+# dec1 is the ONE ReLU of the path (train_nem.py:181).  A unit whose pre-activation lies within the forward rounding
+# error of zero has no defined derivative at the parity bar: two fp32-accurate evaluations (the reference on another
+# BLAS, its own fp64 run, this library) may disagree on its sign, and ONE such unit moves dec1's bias / LayerNorm-beta /
+# weight gradients by ~1e-2 of their max-norm at batch 8 (a column sum over only B*K*T = 240 terms), whatever the
+# precision of the backward pass.  Measured (tools/relu_flips.py, profiles/r02_relu_flips.txt): at cfg1 with
+# bf16-rounded features exactly one unit, |pre| = 4.0e-7, flips - in the fp32 preset too, whose gradients are then
+# 1.2e-2 off the plain oracle and 1.8e-5 off the oracle that takes the library's decision for that unit.
+KINK = 1e-4          # |pre| / max|pre| below which a ReLU decision is within the fp32-mode forward bar
+
+
+def _resolve_relu_kinks(cfg, nem, x, ref, pn, ref_pre, nem_c, max_units=1e-4):
+    """Compare dec1's ReLU decisions of the CUDA run with the oracle's.  Every disagreement must sit on the kink
+    (|pre_oracle| <= KINK * max|pre|) and be rare; if there is one, the oracle is re-evaluated with the library's
+    decision for exactly those units.  Returns (ref, pn, number of such units)."""
+    from helpers import cuda_dec1_pre
+    pre_c = cuda_dec1_pre(nem_c, cfg["T"])
+    masks, n_flip, n_all = [], 0, 0
+    for a, b in zip(pre_c, ref_pre):
+        flipped = (a > 0) != (b > 0)
+        n_flip += int(flipped.sum())
+        n_all += b.numel()
+        if flipped.any():
+            assert b[flipped].abs().max().item() <= KINK * b.abs().max().item(), "a ReLU decision differs AWAY from the kink"
+        masks.append(((b > 0) ^ flipped).float())
+    assert n_flip <= max(2, max_units * n_all), (n_flip, n_all)
+    if n_flip:
+        ref, pn = _oracle(cfg, nem.cpu(), x, torch.float32, dec1_masks=masks)
+    return ref, pn, n_flip
+
+
 def _cuda(cfg, nem, x, precision, xdtype):
     nem = nem.cuda().eval()          # parity is defined in eval mode (dropout off) with gradients enabled
     nem.precision = precision
+    nem.keep_workspace = True        # stage-level inspection (helpers.cuda_dec1_pre)
     h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda().to(xdtype), cfg["T"])
     wh, wg = _probe(cfg)
     loss = nem_loss + (h * wh.cuda()).sum() + (gamma * wg.cuda()).sum()
@@ -103,46 +135,69 @@ def test_run_em_fp32_mode(name):
 
 @pytest.mark.parametrize("name", CASES)
 def test_run_em_bf16_features_mode(name):
-    """bf16 features: the oracle consumes the bf16-rounded features up-cast to fp32."""
+    """bf16 features: the oracle consumes the bf16-rounded features up-cast to fp32.  Flat 1e-2 in
+    max-norm on every output and every gradient tensor (widened only for the ill-conditioned 'peaky' case, by the
+    reference's own fp32-vs-fp64 noise); ReLU decisions on the kink are taken from the library (see KINK above)."""
     _, cfg = load_golden(name)
     nem, _ = seeded_models(cfg)
     x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
     xb = x.bfloat16()
-    ref, pn = _oracle(cfg, nem, xb.float(), torch.float32)
+    ref_pre = []
+    ref, pn = _oracle(cfg, nem, xb.float(), torch.float32, dec1_pre=ref_pre)
     truth, pt = _oracle(cfg, nem, xb.float(), torch.float64)
+    ref_plain, pn_plain = ref, pn
     res, nem_c = _cuda(cfg, nem, xb, "bf16", torch.bfloat16)
+    ref, pn, n_kink = _resolve_relu_kinks(cfg, nem, xb.float(), ref, pn, ref_pre, nem_c)
     rows = _report(name, "bf16", cfg, res, nem_c, ref, pn, truth, pt)
-    noise = json.load(open(os.path.join(OUT, f"em_parity_{name}_bf16.json")))["oracle_fp32_vs_fp64"]
-    tol = _tolerances(rows, 1e-2, noise, slack=20.0)
-    # dec1 is the one ReLU stage: a pre-activation within the forward error of zero flips its derivative
-    # between the two implementations and changes ONE gradient entry by O(1) of its typical size (the
-    # reference itself does this between its fp32 and fp64 runs on the ill-conditioned case).  For dec1's
-    # gradients the max-norm bound is therefore 3e-2 and the 1e-2 bar is applied to the relative L2 error.
+    report = json.load(open(os.path.join(OUT, f"em_parity_{name}_bf16.json")))
+    report["relu_units_on_the_kink"] = n_kink
     named = dict(nem_c.named_parameters())
-    for k in list(tol):
-        if k.startswith("grad/dec1.0") or k == "grad/dec1.1.bias":
-            n = k[len("grad/"):]
-            a, b = named[n].grad.double().cpu(), pn[n].grad.double()
-            l2 = ((a - b).norm() / b.norm()).item()
-            assert l2 < max(1e-2, tol[k]), (k, "relative L2", l2)
-            tol[k] = max(3e-2, tol[k])
-    print(name, "bf16 worst", max(rows.items(), key=lambda kv: kv[1] / tol[kv[0]]))
+    report["cuda_vs_plain_oracle"] = {"grad/" + n: rel_err(named[n].grad, p.grad) for n, p in pn_plain.items() if p.grad is not None}
+    json.dump(report, open(os.path.join(OUT, f"em_parity_{name}_bf16.json"), "w"), indent=1)
+    tol = _tolerances(rows, 1e-2, report["oracle_fp32_vs_fp64"] if name.startswith("peaky") else None, slack=20.0)
+    print(name, "bf16 worst", max(rows.items(), key=lambda kv: kv[1] / tol[kv[0]]), "kink units", n_kink)
     bad = {k: (v, tol[k]) for k, v in rows.items() if not v < tol[k]}
     assert not bad, f"bf16-features parity (value, tolerance): {bad}"
+
+
+def test_dec1_relu_kink_is_the_only_dec1_error():
+    """The proof behind KINK: the fp32 preset (1e-4 bar) on the SAME bf16-rounded features as the test above.  Its
+    forward is fp32-class, yet dec1's gradients are ~1e-2 off the plain oracle whenever a unit sits on the kink - and
+    within 1e-4 of the oracle that takes the library's decision for those (asserted to be on the kink) units."""
+    name = "cfg1_b8_k3_m12_t10"
+    _, cfg = load_golden(name)
+    nem, _ = seeded_models(cfg)
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    xb = x.bfloat16()
+    ref_pre = []
+    ref, pn = _oracle(cfg, nem, xb.float(), torch.float32, dec1_pre=ref_pre)
+    res, nem_c = _cuda(cfg, nem, xb, "fp32", torch.bfloat16)
+    named = dict(nem_c.named_parameters())
+    plain = {n: rel_err(named[n].grad, p.grad) for n, p in pn.items() if p.grad is not None}
+    ref, pn, n_kink = _resolve_relu_kinks(cfg, nem, xb.float(), ref, pn, ref_pre, nem_c)
+    fixed = {n: rel_err(named[n].grad, p.grad) for n, p in pn.items() if p.grad is not None}
+    print("kink units", n_kink, "worst vs plain oracle", max(plain.values()), "vs kink-resolved oracle", max(fixed.values()))
+    assert max(fixed.values()) < 1e-4, fixed
+    for k in ("h", "gamma", "nem_loss"):
+        assert rel_err(res[k].reshape(-1), ref[k].reshape(-1)) < 1e-4, k
+    if n_kink == 0:
+        assert max(plain.values()) < 1e-4, plain
 
 
 @pytest.mark.parametrize("name", ["cfg1_b8_k3_m12_t10", "prior0_b5_k2_m12_t3"])
 def test_run_em_bf16_h_mode(name):
     """'bf16_h' = the bf16-features preset with row-scaled fp16 operands in every data-gradient contraction of the
     BPTT chain (same number of tensor-core passes): gradient errors 2-3x below the plain preset - every tensor
-    outside dec1 within 7e-3 in max-norm (1e-2 for 'bf16'; what is left is the bf16 rounding of the weight-gradient
-    contractions, worst on matrices summed over few rows), dec1's tensors within 7e-3 in relative L2."""
+    within 7e-3 in max-norm (1e-2 for 'bf16'; what is left is the bf16 rounding of the weight-gradient
+    contractions, worst on matrices summed over few rows)."""
     _, cfg = load_golden(name)
     nem, _ = seeded_models(cfg)
     x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
     xb = x.bfloat16()
-    ref, pn = _oracle(cfg, nem, xb.float(), torch.float32)
+    ref_pre = []
+    ref, pn = _oracle(cfg, nem, xb.float(), torch.float32, dec1_pre=ref_pre)
     res, nem_c = _cuda(cfg, nem, xb, "bf16_h", torch.bfloat16)
+    ref, pn, _ = _resolve_relu_kinks(cfg, nem, xb.float(), ref, pn, ref_pre, nem_c)
     for k in ("h", "gamma", "nem_loss"):
         assert rel_err(res[k].reshape(-1), ref[k].reshape(-1)) < 1e-3, k
     named = dict(nem_c.named_parameters())
@@ -151,8 +206,7 @@ def test_run_em_bf16_h_mode(name):
         if p.grad is None:
             assert named[n].grad is None
             continue
-        a, b = named[n].grad.double().cpu(), p.grad.double()
-        e = ((a - b).norm() / b.norm()).item() if n.startswith("dec1.0") or n == "dec1.1.bias" else rel_err(named[n].grad, p.grad)
+        e = rel_err(named[n].grad, p.grad)
         if not e < 7e-3:
             bad[n] = e
     assert not bad, bad

@@ -100,6 +100,24 @@ def test_gemm_chained_accumulation_layouts(chain):
     assert _relmax(acc, C0.double() + A.double() @ B.double().t()) < 2e-6
 
 
+@pytest.mark.parametrize("N", [40, 72, 160, 1000])
+def test_gemm_chained_accumulation_clipped_n(N):
+    """Accumulation chains on tiles clipped at the N edge (the head's logits GEMM: N = 40 classes, K = 4096, chain 16
+    -> 4 chains): a clipped tile issues fewer than four TMA groups per chain, and the reduce-add of chain c must still
+    wait for the store of chain c-1 to the same addresses (bulk operations are unordered).  Repeated: the hazard is a
+    race, and large M keeps many warps in flight."""
+    from multi_view_sort_b200 import ops
+    M, K = 4096, 4096
+    A, B = _rand((M, K), 41).bfloat16(), _rand((N, K), 42, 0.05).bfloat16()
+    bias = _rand((N,), 43)
+    ref = A.double() @ B.double().t() + bias.double()
+    for chain in (16, 4, 1):
+        for _ in range(3):
+            out = ops.gemm([(A, B)], bias=bias, chain=chain)
+            torch.cuda.synchronize()
+            assert _relmax(out, ref) < 2e-5, (N, chain)
+
+
 def test_gemm_two_logical_segments():
     from multi_view_sort_b200 import ops
     M, N = 640, 1024
