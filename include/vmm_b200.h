@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VMM_ABI_VERSION 2
+#define VMM_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VMM_API __attribute__((visibility("default")))
@@ -211,6 +211,15 @@ typedef struct vmm_em_config {
    * mantissa bits instead of 8 where rounding errors accumulate, at the same number of tensor-core passes.  The
    * weight-gradient contractions (reductions over rows) keep bf16 operands. */
   int dgrad_fp16;
+  /* 1: decoder warm-up (tools/Trainer.py:184-185, `-if_decoder_warm_up 1`, epochs < 10): EVERY iteration's residual is
+   * weighted by `prior` (NEM.init_state's gamma_prior) instead of the previous iteration's responsibilities (and
+   * gamma0 is not read).  The responsibilities then feed only the outer loss and the head. */
+  int warm_up;
+  /* 1: the outer loss of EVERY iteration is computed (the reference evaluates compute_outer_loss T times,
+   * Trainer.py:191-195; `-if_total_loss 1` logs their mean, :203): loss_out holds 3*T floats, iteration t at
+   * [3t, 3t+2].  Gradients flow from the LAST iteration's loss only, as in the reference (its list of losses is
+   * rebuilt with torch.Tensor(...), which detaches it). */
+  int loss_all;
 } vmm_em_config;
 
 #define VMM_FWD_FULL 0u      /* all planes of both operands                                   */
@@ -259,7 +268,7 @@ VMM_API int vmm_em_prepare(const vmm_em_config* cfg, const vmm_em_params* params
 
 /* Forward.  x: [B,M,D]; gamma0, prior: [B,K,M] float (NEM.init_state's gamma / gamma_prior).
  * Outputs: h_out [B*K,H], gamma_out [B,K,M], loss_out[3] = (nem_loss, intra, inter) of the
- * last iteration, all float on the device. */
+ * last iteration (3*T floats with cfg->loss_all), all float on the device. */
 VMM_API int vmm_em_forward(const vmm_em_config* cfg, const vmm_em_params* params, const void* weights, const void* x,
                            const float* gamma0, const float* prior, void* workspace, void* scratch, float* h_out,
                            float* gamma_out, float* loss_out, void* stream);
@@ -274,14 +283,28 @@ VMM_API int vmm_em_backward(const vmm_em_config* cfg, const vmm_em_params* param
 
 /* Step-level API: ONE EM iteration from an arbitrary state - exactly NEM.forward(x, (h, pred, gamma))
  * of the reference (train_nem.py:272-294), for callers that drive the loop themselves
- * (tools/Trainer.py:322-336 validation, :433-446 descriptor export).  It materialises pred
- * [B,K,M,D] (the reference returns it).  Forward only; workspace sized with training = 0,
- * scratch with vmm_em_step_scratch_bytes. */
+ * (tools/Trainer.py:180-198 training, :322-336 validation, :433-446 descriptor export).  It materialises pred
+ * [B,K,M,D] (the reference returns it).  Workspace sized with T = 1 (and cfg->training as in this call),
+ * scratch with vmm_em_step_scratch_bytes.  With cfg->training = 1 (needs save_delta = VMM_DELTA_F32) the call keeps what
+ * vmm_em_step_backward needs in workspace and scratch. */
 VMM_API long long vmm_em_step_scratch_bytes(const vmm_em_config* cfg);
 VMM_API int vmm_em_step_forward(const vmm_em_config* cfg, const vmm_em_params* params, const void* weights,
                                 const void* x, const float* h_in, const float* pred_in, const float* gamma_in,
                                 void* workspace, void* scratch, float* h_out, float* pred_out, float* gamma_out,
                                 void* stream);
+
+/* Backward of ONE vmm_em_step_forward call made with cfg->training = 1 and save_delta = VMM_DELTA_F32 (workspace sized with
+ * T = 1, training = 1; it and step_scratch must be kept unchanged between the two calls): what autograd needs to train
+ * through the reference's own loop `for j: state = nem(input, state)` followed by compute_outer_loss on (pred, gamma) of
+ * every iteration (tools/Trainer.py:180-198, 219).  d_h_out [B*K,H], d_pred_out [B,K,M,D], d_gamma_out [B,K,M] are the
+ * upstream gradients (NULL = zero); parameter gradients are accumulated into `grads`; d_h_in / d_pred_in / d_gamma_in
+ * receive the gradients w.r.t. the input state (NULL = not wanted; d_gamma_in needs d_pred_in).  `scratch` is transient,
+ * sized with vmm_em_scratch_bytes. */
+VMM_API int vmm_em_step_backward(const vmm_em_config* cfg, const vmm_em_params* params, const void* weights, const void* x,
+                                 const float* h_in, const float* pred_in, const float* gamma_in, const void* workspace,
+                                 const void* step_scratch, void* scratch, const float* d_h_out, const float* d_pred_out,
+                                 const float* d_gamma_out, const vmm_em_grads* grads, float* d_h_in, float* d_pred_in,
+                                 float* d_gamma_in, void* stream);
 
 /* Address of a named intermediate of iteration `iter` inside `workspace` (for stage-level
  * parity tests and debugging); returns NULL for an unknown name.  Names: "xw1", "g1", "a_hi",

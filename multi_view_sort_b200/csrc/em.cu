@@ -212,6 +212,7 @@ int check_cfg(const vmm_em_config* c) {
   VMM_REQUIRE(c->save_delta >= VMM_DELTA_NONE && c->save_delta <= VMM_DELTA_F32, "save_delta must be 0, 1 or 2");
   VMM_REQUIRE(!c->dgrad_fp16 || c->fwd_fp16, "dgrad_fp16 needs fwd_fp16 (the fp16 hi planes of the weights)");
   VMM_REQUIRE((c->fwd_modes >> 20) == 0, "fwd_modes has 9 two-bit fields and 2 gradient-contraction bits");
+  VMM_REQUIRE((c->warm_up == 0 || c->warm_up == 1) && (c->loss_all == 0 || c->loss_all == 1), "warm_up / loss_all must be 0 or 1");
   VMM_REQUIRE(1ll * c->B * c->K * c->M < (1ll << 31) / 2, "too many rows for 32-bit indexing; split the batch");
   return 0;
 }
@@ -343,6 +344,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
   VMM_TRY(check_cfg(c));
   VMM_REQUIRE(p && weights && x && gamma0 && workspace && scratch, "null argument");
   VMM_REQUIRE(!loss_out || c->if_gamma_prior == 0 || prior, "prior is required for if_gamma_prior 1/2");
+  VMM_REQUIRE(!c->warm_up || prior, "warm_up weights every residual by `prior`");
   Dims d(*c);
   Weights w(*c, const_cast<void*>(weights));
   Workspace ws(*c, workspace);
@@ -368,7 +370,7 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
     const IterBufs cur = ws.slot(t);
     const IterBufs prev = ws.slot(t > 0 ? t - 1 : 0);
     const bool last = (t == d.T - 1);
-    const float* gam_prev = t > 0 ? prev.gamma : gamma0;
+    const float* gam_prev = c->warm_up ? prior : (t > 0 ? prev.gamma : gamma0);
     // --- enc1 on the responsibility-weighted residual (train_nem.py:280-284, 226)
     if (t > 0) VMM_TRY(linear_fwd(d, FC_G1, prev.z.f, w.w13.f, d.RM, E1, E1, cur.g1, st));
     {
@@ -398,16 +400,19 @@ int em_forward(const vmm_em_config* c, const vmm_em_params* p, const void* weigh
     VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps),
                        fwd_out(d, tr, cur.z, FC_DEC3, FC_G1), cur.mean5, cur.rstd5, st));
     // --- dec3 fused with the E-step (train_nem.py:241-270)
-    const bool want_pp = last && c->if_gamma_prior == 0;
+    const bool want_loss = loss_out && (last || c->loss_all);     // the row sums of the LAST iteration stay in ws.row_* for backward
+    const bool want_sq = last || want_loss;
+    const bool want_pp = want_sq && c->if_gamma_prior == 0;
     VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, sel_act(d, FC_DEC3, cur.z.f), sel_w(d, FC_DEC3, w.w3.f), p->dec3_b, x,
-                          c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
+                          c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.part_e, want_sq ? sc.part_sq : nullptr,
                           want_pp ? sc.part_pp : nullptr, cur.delta, d.save_delta, st, cur.dmax ? sc.part_dmax : nullptr));
     if (cur.dmax) VMM_TRY(row_max_partials(static_cast<int>(d.RM), d.nblk, sc.part_dmax, cur.dmax, st));
-    VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, last ? sc.part_sq : nullptr,
+    VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, want_sq ? sc.part_sq : nullptr,
                           want_pp ? sc.part_pp : nullptr, cur.gamma, cur.inv_s, ws.row_sq, ws.row_pp, st));
+    if (want_loss)
+      VMM_TRY(loss_forward(d.B, d.K, d.M, d.D, c->if_gamma_prior, cur.gamma, prior, ws.row_sq, ws.row_pp,
+                           loss_out + (c->loss_all ? 3 * t : 0), st));
     if (last) {
-      if (loss_out)
-        VMM_TRY(loss_forward(d.B, d.K, d.M, d.D, c->if_gamma_prior, cur.gamma, prior, ws.row_sq, ws.row_pp, loss_out, st));
       if (h_out) VMM_CHECK_CUDA(cudaMemcpyAsync(h_out, cur.h, sizeof(float) * d.R * d.H, cudaMemcpyDeviceToDevice, st));
       if (gamma_out)
         VMM_CHECK_CUDA(cudaMemcpyAsync(gamma_out, cur.gamma, sizeof(float) * d.RM, cudaMemcpyDeviceToDevice, st));
@@ -427,8 +432,8 @@ struct StepScratch {
   StepScratch(const vmm_em_config& c, void* base) {
     Dims d(c);
     Bump b(base);
-    masked = b.op(d.RM * d.D, d.planes, d.f16, 1);
-    hin = b.op(d.R * d.H, d.planes, d.f16, 1);
+    masked = b.op(d.RM * d.D, d.planes, d.f16, d.pb);
+    hin = b.op(d.R * d.H, d.planes, d.f16, d.pb);
     part_e = b.take<float>(d.RM * d.nblk);
     bytes = b.off + 256;
   }
@@ -440,39 +445,131 @@ int em_step_forward(const vmm_em_config* c, const vmm_em_params* p, const void* 
   VMM_TRY(check_cfg(c));
   VMM_REQUIRE(p && weights && x && h_in && pred_in && gamma_in && workspace && scratch && h_out && pred_out && gamma_out,
               "null argument");
-  Dims d(*c);
-  Weights w(*c, const_cast<void*>(weights));
+  VMM_REQUIRE(!c->training || c->save_delta == VMM_DELTA_F32, "the step-level API trains with save_delta = VMM_DELTA_F32");
   vmm_em_config c1 = *c;
-  c1.training = 0;
+  c1.T = 1;                      // one iteration: one workspace slot (kept for vmm_em_step_backward when training)
+  Dims d(c1);
+  Weights w(c1, const_cast<void*>(weights));
   Workspace ws(c1, workspace);
-  StepScratch sc(*c, scratch);
+  StepScratch sc(c1, scratch);
   const IterBufs cur = ws.slot(0);
   const float eps = c->ln_eps;
+  const bool tr = c->training != 0;
   VMM_TRY(residual_op(d.RM, d.D, d.K * d.M, d.M, x, c->x_is_bf16, pred_in, gamma_in, sc.masked, st));
   VMM_TRY(linear_fwd(d, FC_XW1, sc.masked.f, w.w1.f, d.RM, E1, d.D, cur.g1, st));
-  VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.RM, E1, cur.g1, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps), cur.a, cur.mean1,
-                     cur.rstd1, st));
+  VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.RM, E1, cur.g1, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps, c, ST_ENC1, 0), cur.a,
+                     cur.mean1, cur.rstd1, st));
   VMM_TRY(linear_fwd(d, FC_ENC2, cur.a.f, w.w2.f, d.R, E2, d.ZW, cur.g2, st));
-  VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps), cur.e, cur.mean2,
-                     cur.rstd2, st));
+  VMM_TRY(ln_forward(LN_BIAS, ACT_ELU, ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps, c, ST_ENC2, 0), cur.e,
+                     cur.mean2, cur.rstd2, st));
   VMM_TRY(linear_fwd(d, FC_GI, cur.e.f, w.wih.f, d.R, 3 * d.H, E2, cur.gi, st));
   VMM_TRY(split_op(h_in, d.R * d.H, sc.hin, st));
   VMM_TRY(linear_fwd(d, FC_GH, sc.hin.f, w.whh.f, d.R, 3 * d.H, d.H, cur.gh, st));
   VMM_TRY(gru_forward(static_cast<int>(d.R), d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, h_in, h_out, cur.hp, st));
   VMM_TRY(linear_fwd(d, FC_DEC1, cur.hp.f, w.w4.f, d.R, E2, d.H, cur.g4, st));
-  VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps), cur.u, cur.mean4,
-                     cur.rstd4, st));
+  VMM_TRY(ln_forward(LN_BIAS, ACT_RELU, ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps, c, ST_DEC1, 0), cur.u,
+                     cur.mean4, cur.rstd4, st));
   VMM_TRY(linear_fwd(d, FC_DEC2, cur.u.f, w.w5.f, d.R, static_cast<int>(d.ZW), E2, cur.g5, st));
   VMM_TRY(ln_forward(LN_BIAS, ACT_NONE, ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps), cur.z, cur.mean5,
                      cur.rstd5, st));
   {
+    const Planes z = sel_act(d, FC_DEC3, cur.z.f), w3 = sel_w(d, FC_DEC3, w.w3.f);
     vmm_gemm_seg s[9];
-    const int ns = make_segs(s, cur.z.f, E1, w.w3.f, E1, E1);
+    const int ns = make_segs(s, z, E1, w3, E1, E1);
     VMM_TRY(gemm_bf16(static_cast<int>(d.RM), d.D, ns, s, false, false, pred_out, d.D, p->dec3_b, false, 1, d.chain, st));
+    VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, z, w3, p->dec3_b, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.part_e,
+                          nullptr, nullptr, tr ? cur.delta : nullptr, tr ? d.save_delta : VMM_DELTA_NONE, st));
   }
-  VMM_TRY(estep_forward(static_cast<int>(d.RM), d.D, E1, cur.z.f, w.w3.f, p->dec3_b, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
-                        sc.part_e, nullptr, nullptr, nullptr, VMM_DELTA_NONE, st));
-  VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, nullptr, nullptr, gamma_out, cur.inv_s, nullptr, nullptr, st));
+  VMM_TRY(gamma_forward(d.B, d.K, d.M, d.nblk, c->sigma, sc.part_e, nullptr, nullptr, cur.gamma, cur.inv_s, nullptr, nullptr, st));
+  VMM_CHECK_CUDA(cudaMemcpyAsync(gamma_out, cur.gamma, sizeof(float) * d.RM, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// Backward of ONE vmm_em_step_forward call (cfg->training = 1): the building block of autograd through the reference's
+// own loop `for j: state = nem(input, state)` (tools/Trainer.py:180-198).  Upstream gradients d_h_out / d_pred_out /
+// d_gamma_out (any may be NULL = zero) -> parameter gradients (+=) and d_h_in / d_pred_in / d_gamma_in.
+int em_step_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weights, const void* x, const float* h_in,
+                     const float* pred_in, const float* gamma_in, const void* workspace, const void* step_scratch,
+                     void* scratch, const float* d_h_out, const float* d_pred_out, const float* d_gamma_out,
+                     const vmm_em_grads* g, float* d_h_in, float* d_pred_in, float* d_gamma_in, cudaStream_t st) {
+  VMM_TRY(check_cfg(c));
+  VMM_REQUIRE(c->training && c->save_delta == VMM_DELTA_F32, "vmm_em_step_backward needs a step forward with training = 1, save_delta = F32");
+  VMM_REQUIRE(p && weights && x && h_in && pred_in && gamma_in && workspace && step_scratch && scratch && g, "null argument");
+  VMM_REQUIRE(!d_gamma_in || d_pred_in, "d_gamma_in needs the d_pred_in buffer (it holds dL/dmasked on the way)");
+  vmm_em_config c1 = *c;
+  c1.T = 1;
+  Dims d(c1);
+  Weights w(c1, const_cast<void*>(weights));
+  Workspace ws(c1, const_cast<void*>(workspace));
+  StepScratch ss(c1, const_cast<void*>(step_scratch));
+  Scratch sc(c1, scratch);
+  const IterBufs cur = ws.slot(0);
+  const float eps = c->ln_eps;
+  const int R = static_cast<int>(d.R);
+  g_bwd_bits = 0;
+
+  if (d_h_out) VMM_CHECK_CUDA(cudaMemcpyAsync(sc.dh, d_h_out, sizeof(float) * d.R * d.H, cudaMemcpyDeviceToDevice, st));
+  else VMM_CHECK_CUDA(cudaMemsetAsync(sc.dh, 0, sizeof(float) * d.R * d.H, st));
+  if (d_gamma_out) VMM_CHECK_CUDA(cudaMemcpyAsync(sc.dgamma, d_gamma_out, sizeof(float) * d.RM, cudaMemcpyDeviceToDevice, st));
+  else VMM_CHECK_CUDA(cudaMemsetAsync(sc.dgamma, 0, sizeof(float) * d.RM, st));
+  VMM_CHECK_CUDA(cudaMemsetAsync(sc.beta, 0, sizeof(float) * d.RM, st));
+  // --- E-step (train_nem.py:247-270) and the caller's explicit dL/dpred
+  VMM_TRY(gamma_backward(d.B, d.K, d.M, c->sigma, cur.gamma, cur.inv_s, sc.dgamma, sc.alpha, st));
+  VMM_TRY(estep_dpred(static_cast<int>(d.RM), d.D, cur.delta, d.save_delta, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.alpha,
+                      sc.beta, nullptr, sc.dpred, g->dec3_b, st, nullptr, nullptr, nullptr, d_pred_out));
+  // --- dec3, dec2, dec1
+  VMM_TRY(linear_wgrad(sc.dpred, cur.z.b, d.RM, d.D, E1, g->dec3_w, d.chain_b, st));
+  VMM_TRY(linear_dgrad(sc.dpred, w.w3.b, d.RM, d.D, E1, sc.dz, false, d.chain_b, st));
+  {
+    LnDesc ln = ln_desc(d.R, d.ZW, cur.g5, p->dec2_b, p->dec2_ln_g, p->dec2_ln_b, eps);
+    VMM_TRY(ln_backward_rows(LN_BIAS, ACT_NONE, ln, cur.mean5, cur.rstd5, sc.dz, d.ZW, sc.dv5, sc.c1, sc.c2, nullptr, nullptr,
+                             Planes(), st));
+    VMM_TRY(ln_backward_cols(LN_BIAS, ACT_NONE, ln, cur.mean5, cur.rstd5, sc.c1, sc.c2, sc.dz, d.ZW, g->dec2_ln_g, g->dec2_ln_b,
+                             g->dec2_b, nullptr, st));
+  }
+  VMM_TRY(linear_dgrad(sc.dv5, w.w5.b, d.R, static_cast<int>(d.ZW), E2, sc.du, false, d.chain_b, st));
+  VMM_TRY(linear_wgrad(sc.dv5, cur.u.b, d.R, static_cast<int>(d.ZW), E2, g->dec2_w, d.chain_b, st));
+  {
+    LnDesc ln = ln_desc(d.R, E2, cur.g4, p->dec1_b, p->dec1_ln_g, p->dec1_ln_b, eps, c, ST_DEC1, 0);
+    VMM_TRY(ln_backward_rows(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.du, E2, sc.dv4, sc.c1, sc.c2, nullptr, nullptr,
+                             Planes(), st));
+    VMM_TRY(ln_backward_cols(LN_BIAS, ACT_RELU, ln, cur.mean4, cur.rstd4, sc.c1, sc.c2, sc.du, E2, g->dec1_ln_g, g->dec1_ln_b,
+                             g->dec1_b, nullptr, st));
+  }
+  VMM_TRY(linear_dgrad(sc.dv4, w.w4.b, d.R, E2, d.H, sc.dh, true, d.chain_b, st));
+  VMM_TRY(linear_wgrad(sc.dv4, cur.hp.b, d.R, E2, d.H, g->dec1_w, d.chain_b, st));
+  // --- GRU
+  VMM_TRY(gru_backward(R, d.H, cur.gi, cur.gh, p->gru_b_ih, p->gru_b_hh, h_in, sc.dh, sc.dgi, sc.dgh, sc.dh_prev, g->gru_b_ih,
+                       g->gru_b_hh, st));
+  VMM_TRY(linear_dgrad(sc.dgi, w.wih.b, d.R, 3 * d.H, E2, sc.de, false, d.chain_b, st));
+  VMM_TRY(linear_wgrad(sc.dgi, cur.e.b, d.R, 3 * d.H, E2, g->gru_w_ih, d.chain_b, st));
+  VMM_TRY(linear_dgrad(sc.dgh, w.whh.b, d.R, 3 * d.H, d.H, sc.dh_prev, true, d.chain_b, st));
+  VMM_TRY(linear_wgrad(sc.dgh, ss.hin.b, d.R, 3 * d.H, d.H, g->gru_w_hh, d.chain_b, st));
+  if (d_h_in) VMM_CHECK_CUDA(cudaMemcpyAsync(d_h_in, sc.dh_prev, sizeof(float) * d.R * d.H, cudaMemcpyDeviceToDevice, st));
+  // --- enc2
+  {
+    LnDesc ln = ln_desc(d.R, E2, cur.g2, p->enc2_b, p->enc2_ln_g, p->enc2_ln_b, eps, c, ST_ENC2, 0);
+    VMM_TRY(ln_backward_rows(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.de, E2, sc.dv2, sc.c1, sc.c2, nullptr, nullptr,
+                             Planes(), st));
+    VMM_TRY(ln_backward_cols(LN_BIAS, ACT_ELU, ln, cur.mean2, cur.rstd2, sc.c1, sc.c2, sc.de, E2, g->enc2_ln_g, g->enc2_ln_b,
+                             g->enc2_b, nullptr, st));
+  }
+  VMM_TRY(linear_dgrad(sc.dv2, w.w2.b, d.R, E2, d.ZW, sc.da, false, d.chain_b, st));
+  VMM_TRY(linear_wgrad(sc.dv2, cur.a.b, d.R, E2, d.ZW, g->enc2_w, d.chain_b, st));
+  // --- enc1 on the explicit residual: G1 = masked W1^T, no fold
+  {
+    LnDesc ln = ln_desc(d.RM, E1, cur.g1, p->enc1_b, p->enc1_ln_g, p->enc1_ln_b, eps, c, ST_ENC1, 0);
+    VMM_TRY(ln_backward_rows(LN_BIAS, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, sc.dg1, sc.c1, sc.c2, nullptr, nullptr,
+                             Planes(), st));
+    VMM_TRY(ln_backward_cols(LN_BIAS, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.c1, sc.c2, sc.da, E1, g->enc1_ln_g, g->enc1_ln_b,
+                             g->enc1_b, nullptr, st));
+  }
+  VMM_TRY(linear_wgrad(sc.dg1, ss.masked.b, d.RM, E1, d.D, g->enc1_w, d.chain_b, st));
+  // --- residual: dL/dmasked = dv1 W1 -> dL/dpred_in = -gamma dL/dmasked, dL/dgamma_in = <dL/dmasked, x - pred_in>
+  if (d_pred_in) {
+    VMM_TRY(linear_dgrad(sc.dg1, w.w1.b, d.RM, E1, d.D, d_pred_in, false, d.chain_b, st));
+    VMM_TRY(residual_backward(d.RM, d.D, d.K * d.M, d.M, x, c->x_is_bf16, pred_in, gamma_in, d_pred_in, d_gamma_in, st));
+  }
   return 0;
 }
 
@@ -510,7 +607,8 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     const IterBufs cur = ws.slot(t);
     const IterBufs prev = ws.slot(t > 0 ? t - 1 : 0);
     const bool last = (t == d.T - 1);
-    const float* gam_prev = t > 0 ? prev.gamma : gamma0;
+    const float* gam_prev = c->warm_up ? prior : (t > 0 ? prev.gamma : gamma0);
+    const bool gam_grad = t > 0 && !c->warm_up;      // the residual's weight is the previous iteration's gamma: it gets a gradient
     const float* kappa = nullptr;
     bool dv5_h = false;
     // --- loss and E-step: per-row scalars of dL/dpred
@@ -612,17 +710,18 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
       ln.km = d.K * d.M;
       ln.mv = d.M;
       if (enc1_backward_fused_ok(E1, d.K)) {
-        VMM_TRY(enc1_backward_fused(ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, t > 0 ? sc.dgamma : nullptr, sc.dxw1,
+        VMM_TRY(enc1_backward_fused(ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, gam_grad ? sc.dgamma : nullptr, sc.dxw1,
                                     t > 0 ? sc.dg1 : Planes(), g->enc1_ln_g, g->enc1_ln_b, g->enc1_b,
                                     t > 0 ? sc.dw1b3 : nullptr, st, (t > 0 && d.dgh) ? sc.dg1h : RowF16()));
       } else {
         VMM_TRY(ln_backward_rows(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.da, E1, Planes(), sc.c1, sc.c2,
-                                 t > 0 ? sc.dgamma : nullptr, sc.dxw1, t > 0 ? sc.dg1 : Planes(), st));
+                                 gam_grad ? sc.dgamma : nullptr, sc.dxw1, t > 0 ? sc.dg1 : Planes(), st));
         VMM_TRY(ln_backward_cols(LN_ENC1, ACT_ELU, ln, cur.mean1, cur.rstd1, sc.c1, sc.c2, sc.da, E1, g->enc1_ln_g,
                                  g->enc1_ln_b, g->enc1_b, t > 0 ? sc.dw1b3 : nullptr, st));
       }
     }
     if (t > 0) VMM_TRY(linear_wgrad(sc.dg1, prev.z.b, d.RM, E1, E1, sc.dw13, d.chain_b, st));
+    if (t > 0 && c->warm_up) VMM_CHECK_CUDA(cudaMemsetAsync(sc.dgamma, 0, sizeof(float) * d.RM, st));   // gamma_{t-1} feeds nothing
   }
   // --- parameters behind the fold: XW1 = x W1^T, W13 = W1 W3, w1b3 = W1 b3
   VMM_TRY(split_planes(sc.dxw1, d.BM * E1, sc.dxw1p, st));
@@ -683,6 +782,14 @@ int vmm_em_step_forward(const vmm_em_config* cfg, const vmm_em_params* params, c
                         float* h_out, float* pred_out, float* gamma_out, void* stream) {
   return vmm::em_step_forward(cfg, params, weights, x, h_in, pred_in, gamma_in, workspace, scratch, h_out, pred_out,
                               gamma_out, static_cast<cudaStream_t>(stream));
+}
+int vmm_em_step_backward(const vmm_em_config* cfg, const vmm_em_params* params, const void* weights, const void* x,
+                         const float* h_in, const float* pred_in, const float* gamma_in, const void* workspace,
+                         const void* step_scratch, void* scratch, const float* d_h_out, const float* d_pred_out,
+                         const float* d_gamma_out, const vmm_em_grads* grads, float* d_h_in, float* d_pred_in, float* d_gamma_in,
+                         void* stream) {
+  return vmm::em_step_backward(cfg, params, weights, x, h_in, pred_in, gamma_in, workspace, step_scratch, scratch, d_h_out,
+                               d_pred_out, d_gamma_out, grads, d_h_in, d_pred_in, d_gamma_in, static_cast<cudaStream_t>(stream));
 }
 const void* vmm_em_workspace_ptr(const vmm_em_config* cfg, const void* workspace, const char* name, int iter) {
   if (vmm::check_cfg(cfg) != 0 || !name || iter < 0 || iter >= cfg->T) return nullptr;

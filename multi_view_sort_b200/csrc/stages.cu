@@ -1342,6 +1342,36 @@ __global__ void __launch_bounds__(256) residual_op_kernel(long long rows, int D,
   }
 }
 
+// Backward of the residual stage of the step-level API: masked = (x - pred) * gamma (train_nem.py:280-284).
+// io holds dL/dmasked [rows, D] on entry and dL/dpred = -gamma * dL/dmasked on exit; dgamma[r] = <dL/dmasked_r, x - pred_r>.
+__global__ void __launch_bounds__(256) residual_backward_kernel(int D, int km, int mv, const float* __restrict__ xf,
+                                                                const __nv_bfloat16* __restrict__ xb,
+                                                                const float* __restrict__ pred, const float* __restrict__ gamma,
+                                                                float* __restrict__ io, float* __restrict__ dgamma) {
+  __shared__ float red[32];
+  const long long r = blockIdx.x;
+  const long long xrow = (r / km) * mv + r % mv;
+  const float g = gamma[r];
+  float acc = 0.f;
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+    float4 xv;
+    if (xf) {
+      xv = ld4(xf + xrow * D + c);
+    } else {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(xb + xrow * D + c));
+      xv = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+    }
+    const float4 pv = ld4(pred + r * D + c);
+    float4* pio = reinterpret_cast<float4*>(io + r * D + c);
+    const float4 dm = *pio;
+    acc += (dm.x * (xv.x - pv.x) + dm.y * (xv.y - pv.y)) + (dm.z * (xv.z - pv.z) + dm.w * (xv.w - pv.w));
+    *pio = make_float4(-g * dm.x, -g * dm.y, -g * dm.z, -g * dm.w);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && dgamma) dgamma[r] = acc;
+}
+
 int pick_rows_per_block(int rows, int col_blocks) {
   // aim for ~8 blocks per SM in total
   const int target = device_sm_count() * 8;
@@ -1383,7 +1413,8 @@ __global__ void __launch_bounds__(256) estep_dpred_kernel(int rows, int D, int r
                                                           __nv_bfloat16* __restrict__ p0, __nv_bfloat16* __restrict__ p1,
                                                           __nv_bfloat16* __restrict__ p2, float* __restrict__ colsum,
                                                           __half* __restrict__ ph, float* __restrict__ inv_scale,
-                                                          const float* __restrict__ row_dmax, float sigma) {
+                                                          const float* __restrict__ row_dmax, float sigma,
+                                                          const float* __restrict__ add) {
   const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (col >= D) return;
   const int r0 = blockIdx.y * rows_per_block;
@@ -1405,6 +1436,11 @@ __global__ void __launch_bounds__(256) estep_dpred_kernel(int rows, int D, int r
       for (int q = 0; q < 8; ++q) {
         const float d = dv[i][q];
         out[q] = d * fmaf(a, exp2f(d * d * exp_scale), -b);
+      }
+      if (add) {                                                     // step-level API: + an explicit dL/dpred of the caller
+        const float4 ua = ld4(add + static_cast<long long>(r) * D + col), ub = ld4(add + static_cast<long long>(r) * D + col + 4);
+        out[0] += ua.x; out[1] += ua.y; out[2] += ua.z; out[3] += ua.w;
+        out[4] += ub.x; out[5] += ub.y; out[6] += ub.z; out[7] += ub.w;
       }
       if (ph) {
         // row-scaled fp16 copy for the data-gradient contraction.  |delta * E(delta)| <= sigma * e^-1/2 for every
@@ -1696,6 +1732,16 @@ int residual_op(long long rows, int D, int km, int mv, const void* x, int x_is_b
   return 0;
 }
 
+int residual_backward(long long rows, int D, int km, int mv, const void* x, int x_is_bf16, const float* pred,
+                      const float* gamma, float* io, float* dgamma, cudaStream_t stream) {
+  VMM_REQUIRE(rows > 0 && D % 4 == 0 && x && pred && gamma && io, "residual_backward: bad argument");
+  residual_backward_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(
+      D, km, mv, x_is_bf16 ? nullptr : static_cast<const float*>(x),
+      x_is_bf16 ? static_cast<const __nv_bfloat16*>(x) : nullptr, pred, gamma, io, dgamma);
+  VMM_LAUNCHED();
+  return 0;
+}
+
 int gemv_rows(int n, int k, const float* W, const float* v, float* out, cudaStream_t stream) {
   gemv_rows_kernel<<<n, 256, 0, stream>>>(n, k, W, v, out);
   VMM_LAUNCHED();
@@ -1749,8 +1795,9 @@ int act_backward(int act, long long n, const float* pre, float* grad, float drop
 int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x, int x_is_bf16, long long ldx,
                 int k_latent, int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
                 const Planes& dpred, float* colsum, cudaStream_t stream, __half* dpred_h, float* inv_scale,
-                const float* row_dmax) {
+                const float* row_dmax, const float* add) {
   VMM_REQUIRE(rows > 0 && D > 0 && D % 8 == 0 && delta && alpha && beta, "estep_dpred: bad argument");
+  VMM_REQUIRE(!add || (!dpred_h && (reinterpret_cast<uintptr_t>(add) & 15) == 0), "estep_dpred: `add` needs 16-byte alignment and no fp16 copy");
   VMM_REQUIRE(!dpred_h || (!kappa && inv_scale && row_dmax && (reinterpret_cast<uintptr_t>(dpred_h) & 15) == 0),
               "estep_dpred: the row-scaled fp16 copy needs kappa == NULL, a scale buffer and the row maxima of delta");
   VMM_REQUIRE(delta_fmt == VMM_DELTA_F16 || delta_fmt == VMM_DELTA_F32, "estep_dpred: delta_fmt must be fp16 or fp32");
@@ -1773,7 +1820,7 @@ int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x
 #define VMM_DPRED(DT, N)                                                                                            \
   estep_dpred_kernel<DT, N><<<grid, 256, 0, stream>>>(rows, D, rpb, static_cast<const DT*>(delta), alpha, beta, kappa, x,  \
                                                       x_is_bf16, ldx, km, m_views, exp_scale, dpred.p[0], dpred.p[1],   \
-                                                      dpred.p[2], colsum, dpred_h, inv_scale, row_dmax, sigma)
+                                                      dpred.p[2], colsum, dpred_h, inv_scale, row_dmax, sigma, add)
   if (delta_fmt == VMM_DELTA_F16) {
     if (dpred.n == 1) VMM_DPRED(__half, 1);
     else if (dpred.n == 2) VMM_DPRED(__half, 2);

@@ -139,6 +139,11 @@ int loss_backward(int B, int K, int Mv, int D, int if_gamma_prior, int stop_gamm
 int residual_op(long long rows, int D, int km, int mv, const void* x, int x_is_bf16, const float* pred,
                 const float* gamma, const Op& out, cudaStream_t stream);
 
+// Its backward: io = dL/dmasked [rows, D] in, dL/dpred = -gamma * dL/dmasked out; dgamma[r] = <dL/dmasked_r, x - pred_r>
+// (nullable).
+int residual_backward(long long rows, int D, int km, int mv, const void* x, int x_is_bf16, const float* pred,
+                      const float* gamma, float* io, float* dgamma, cudaStream_t stream);
+
 // Small dense helpers on fp32 parameters.
 int gemv_rows(int n, int k, const float* W, const float* v, float* out, cudaStream_t stream);            // out[i] = W[i,:].v
 int rank1_update(int n, int k, const float* u, const float* v, float* W, cudaStream_t stream);            // W[i,j] += u[i] v[j]

@@ -25,10 +25,11 @@ HEAD_WIDTH = 4096   # VGG-11 classifier width, models/MVCNN.py:55-56
 class NEM(Model):
     """Neural-EM latent-view decomposition (train_nem.py:145-294).
 
-    Extra keyword (not in the reference): ``precision`` - ``"fp32"`` runs every
-    contraction as error-compensated split-bf16 on the tcgen05 tensor cores (matches the
-    reference's fp32 results to ~1e-5), ``"bf16"`` runs single-pass bf16 with bf16
-    features (north_star's 1e-2 mode).
+    Extra keyword (not in the reference): ``precision`` - a preset of functional.PRECISIONS.  ``"fp32"``: every
+    forward contraction on fp16 hi/lo operand pairs (3 tensor-core passes, fp32-class), gradient contractions on two
+    bf16 planes - matches the reference's fp32 results to ~1e-5 (1e-4 bar).  ``"bf16"`` (bf16 features, 1e-2 bar): the
+    same forward except a single-pass dec3, single-plane bf16 gradient contractions; forward-only calls run every
+    contraction in one fp16 pass.  See DESIGN.md 6.
     """
 
     def __init__(self, nclasses=40, view_num=12, layer_norm=1, k=3, batch_size=32, input_dim=4096,
@@ -104,17 +105,18 @@ class NEM(Model):
         if wc is not None:
             wc.invalidate()
 
-    def run_em(self, x, iters=None, gamma0=None, gamma_prior=None, labels=None):
+    def run_em(self, x, iters=None, gamma0=None, gamma_prior=None, labels=None, warm_up=False):
         """Fused path: all `iters` EM iterations and the last iteration's outer loss in one
         autograd node.  x: (B, M, D) on the GPU (fp32, or bf16 when precision='bf16').
         Returns (h_T (B*K,H), gamma_T (B,K,M,1), nem_loss, intra, inter)  - the values the
         reference trainer reads after its loop (tools/Trainer.py:180-203)."""
         from .functional import run_em
-        return run_em(self, x, self.iter_num if iters is None else iters, gamma0, gamma_prior)
+        return run_em(self, x, self.iter_num if iters is None else iters, gamma0, gamma_prior, warm_up=warm_up)
 
     def forward(self, x, state):
         """Step-level drop-in (train_nem.py:272-294): x (B,1,M,D), state=(h,pred,gamma) ->
-        (h', pred', gamma').  One EM iteration; differentiable."""
+        (h', pred', gamma').  One EM iteration; differentiable w.r.t. parameters and state (functional.em_step), so the
+        reference's trainer loop (tools/Trainer.py:180-219) trains on this module unchanged."""
         from .functional import em_step
         if x.shape[0] != self.b:
             self.b = x.shape[0]

@@ -24,44 +24,61 @@ from .features import KmeanImgDataset
 from .nem import NEM, Multi_View_Net
 from .trainer import ModelNetTrainer
 
-parser = argparse.ArgumentParser()
-parser.add_argument("-name", "--name", type=str, help="Name of the experiment", default="MVCNN_kmean")
-parser.add_argument("-bs", "--batchSize", type=int, help="Batch size for the second stage", default=32)
-parser.add_argument("-num_models", type=int, help="number of models per class", default=1000)
-parser.add_argument("-lr", type=float, help="learning rate", default=5e-5)
-parser.add_argument("-weight_decay", type=float, help="weight decay", default=0.0001)
-parser.add_argument("-no_pretraining", dest='no_pretraining', action='store_true')
-parser.add_argument("-cnn_name", "--cnn_name", type=str, help="cnn model name", default="vggm")
-parser.add_argument("-num_views", type=int, help="number of views", default=12)
-parser.set_defaults(train=False)
-parser.add_argument("-train_path", type=str, default="/mnt/cloud_disk/yw/MVCNN_features_vggm_pretrained_imagenet_shapenetcore_train/")
-parser.add_argument("-val_path", type=str, default="/mnt/cloud_disk/yw/MVCNN_features_vggm_pretrained_imagenet_shapenetcore_test/")
-parser.add_argument("-fea_type", type=str, help="feature type for NEM, fc or conv", default='fc')
-parser.add_argument("-layer_norm", type=int, help="use layernorm for NEM or not", default=1)
-parser.add_argument("-cluster_n", type=int, help="cluster number", default=4)
-parser.add_argument("-rnn_hidden_size", type=int, help="rnn hidden size", default=1024)
-parser.add_argument("-iter_num", type=int, help="iteration number for EM", default=15)
-parser.add_argument("-stop_gamma_grad", type=int, help="stop the gradient propagation from gamma", default=0)
-parser.add_argument("-if_sort", type=int, help="if sort the disentangled views or not ", default=1)
-parser.add_argument("-epoch", type=int, help="epoch number", default=70)
-parser.add_argument("-if_pool", type=int, help="use pooling rather than concatenation for multi-view", default=0)
-parser.add_argument("-train_or_test_mode", type=str, help="train or test", default='train')
-parser.add_argument("-modelfile", type=str, help="model file name", default='')
-parser.add_argument("-init_type", type=str, help="initializetion strategy for NEM", default='bin_uniform')
-parser.add_argument("-no_sig", type=int, help="no sigmoid after rnn-nem", default=1)
-parser.add_argument("-bn_init_sigma", type=int, help="use minibatch data to init sigma", default=0)
-parser.add_argument("-if_bn", type=int, help="use bn layers", default=0)
-parser.add_argument("-if_gamma_prior", type=int, help="if use gamma prior loss", default=1)
-parser.add_argument("-if_decoder_warm_up", type=int, help="if warm up decoder", default=0)
-parser.add_argument("-if_total_loss", type=int, help="if use loss from each time stamp", default=0)
-parser.add_argument("-arch", type=int, help="net architecture", default=0)
-parser.add_argument("-e_sigma", type=float, help="net architecture", default=0.1)
-parser.add_argument("-dataset", type=str, help="dataset to use, MNet40, MNet10, ShapeNet are supported", default='MNet40')
-# additions of this implementation
-parser.add_argument("-precision", type=str, default="fp32", help="fp32 | bf16 | bf16_h | bf16_fast (tensor-core operand precision, DESIGN.md 6)")
-parser.add_argument("-model_path", type=str, default="", help="test mode: directory holding <name>/NEM and <name>/MV_C_Net "
-                    "(the reference hard-codes /mnt/cloud_disk/huangjj/exp_mvcnn/)")
-parser.add_argument("-feature_out", type=str, default="", help="test mode: where the descriptors are written")
+# The reference's option schema (train_nem.py:21-64): names, types and defaults are the compatibility contract and are
+# checked against the reference's own parser in tests/test_features.py; the descriptions are this implementation's.
+# Deviation: -train_path / -val_path default to "" (the reference defaults to its authors' private mount points) and
+# are validated in main().
+_INT, _FLT, _STR = int, float, str
+OPTIONS = [
+    # (flags, type, default, description)
+    (("-name", "--name"), _STR, "MVCNN_kmean", "experiment name = log / checkpoint directory"),
+    (("-bs", "--batchSize"), _INT, 32, "objects per batch (per rank under torchrun)"),
+    (("-num_models",), _INT, 1000, "cap on objects per class (accepted for compatibility; the feature store is read whole)"),
+    (("-lr",), _FLT, 5e-5, "Adam learning rate; halved every 15 epochs"),
+    (("-weight_decay",), _FLT, 0.0001, "Adam weight decay"),
+    (("-cnn_name", "--cnn_name"), _STR, "vggm", "backbone that produced the view features; fixes the feature width"),
+    (("-num_views",), _INT, 12, "views per object (M)"),
+    (("-train_path",), _STR, "", "root of the training feature store: <root>/<class>/<feature dir>/*.npy"),
+    (("-val_path",), _STR, "", "root of the validation feature store"),
+    (("-fea_type",), _STR, "fc", "view feature kind; only 'fc' (vectors) is implemented"),
+    (("-layer_norm",), _INT, 1, "LayerNorm inside the NEM encoder/decoder (always on in this implementation)"),
+    (("-cluster_n",), _INT, 4, "latent views per object (K)"),
+    (("-rnn_hidden_size",), _INT, 1024, "GRU state width (H) = width of one latent view"),
+    (("-iter_num",), _INT, 15, "EM iterations per object (T); `-iter N` works as an abbreviation"),
+    (("-stop_gamma_grad",), _INT, 0, "1: detach the responsibilities inside the intra-cluster loss"),
+    (("-if_sort",), _INT, 1, "0 concat latent views as they are, 1 sort by score, 2 sort by responsibility spread"),
+    (("-epoch",), _INT, 70, "training epochs"),
+    (("-if_pool",), _INT, 0, "1: max-pool the latent views instead of concatenating them"),
+    (("-train_or_test_mode",), _STR, "train", "'train', or 'test' = export descriptors with a saved model"),
+    (("-modelfile",), _STR, "", "checkpoint file name inside <name>/<module>/ (default: the latest)"),
+    (("-init_type",), _STR, "bin_uniform", "initial responsibilities: bin_uniform | bin_rand | rand"),
+    (("-no_sig",), _INT, 1, "kept for compatibility (the reference never reads it on this path)"),
+    (("-bn_init_sigma",), _INT, 0, "1: gradient clipping at 5 (the tensor-sigma branch itself is not implemented)"),
+    (("-if_bn",), _INT, 0, "kept for compatibility (unused by the reference's NEM)"),
+    (("-if_gamma_prior",), _INT, 1, "outer-loss variant: 0 Gaussian KL, 1 view-prior KL, 2 view-prior KL + entropy terms"),
+    (("-if_decoder_warm_up",), _INT, 0, "1: weight residuals by the view prior during the first 10 epochs"),
+    (("-if_total_loss",), _INT, 0, "1: log/add the mean of all T NEM losses (detached) instead of the last one"),
+    (("-arch",), _INT, 0, "kept for compatibility"),
+    (("-e_sigma",), _FLT, 0.1, "standard deviation of the E-step's Gaussian"),
+    (("-dataset",), _STR, "MNet40", "class list: MNet40 | MNet10 | ShapeNet"),
+    # ---- additions of this implementation ----
+    (("-precision",), _STR, "fp32", "fp32 | bf16 | bf16_h | bf16_fast: tensor-core operand precision (DESIGN.md 6)"),
+    (("-model_path",), _STR, "", "test mode: directory that holds <name>/NEM and <name>/MV_C_Net"),
+    (("-feature_out",), _STR, "", "test mode: where the descriptors are written"),
+]
+
+
+def make_parser():
+    ap = argparse.ArgumentParser(description="VMM / NEM trainer on the sm_100a library (the reference's train_nem.py flags)")
+    for flags, typ, default, text in OPTIONS:
+        ap.add_argument(*flags, type=typ, default=default, help=text)
+    ap.add_argument("-no_pretraining", dest="no_pretraining", action="store_true",
+                    help="kept for compatibility (no image backbone is built on this path)")
+    ap.set_defaults(train=False)
+    return ap
+
+
+parser = make_parser()
 
 
 def create_folder(log_dir):
@@ -112,6 +129,12 @@ def main(argv=None):
     np.random.seed(10)
     args = parser.parse_args(argv)
     class_num = class_num_of(args.dataset)
+    # reject what cannot run BEFORE create_folder() wipes an existing log directory
+    if args.fea_type != 'fc':
+        raise KeyError("only 'fc' features are supported by the CUDA path")
+    if not args.val_path or (args.train_or_test_mode == 'train' and not args.train_path):
+        raise SystemExit("-train_path / -val_path are required (the reference's defaults are its authors' private mounts)")
+    input_dim_of(args.cnn_name)
     distributed = int(os.environ.get("WORLD_SIZE", "1")) > 1
     if distributed:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
@@ -119,7 +142,14 @@ def main(argv=None):
     rank = torch.distributed.get_rank() if distributed else 0
 
     def loader(ds, shuffle):
-        sampler = torch.utils.data.distributed.DistributedSampler(ds, shuffle=shuffle) if distributed else None
+        sampler = None
+        if distributed and shuffle:
+            sampler = torch.utils.data.distributed.DistributedSampler(ds, shuffle=True)     # the trainer calls set_epoch()
+        elif distributed:
+            # evaluation: a strided shard WITHOUT the padding duplicates of DistributedSampler; the trainer sums the
+            # per-rank counters (update_validation_accuracy_nem), so the metrics are those of the whole set
+            world = torch.distributed.get_world_size()
+            sampler = list(range(rank, len(ds), world))
         return torch.utils.data.DataLoader(ds, batch_size=args.batchSize, shuffle=(shuffle and sampler is None),
                                            sampler=sampler, num_workers=0)
 

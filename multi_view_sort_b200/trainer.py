@@ -77,10 +77,10 @@ class ModelNetTrainer(object):
         self.writer = ScalarWriter(log_dir) if (log_dir is not None and self.rank == 0) else None
 
     # ------------------------------------------------------------------------------------------
-    def _forward(self, nem, c_net, in_data):
-        if nem.if_decoder_warm_up == 1:
-            raise NotImplementedError("if_decoder_warm_up=1 (Trainer.py:184-185) is not supported by the fused EM loop")
-        h, gamma, nem_loss, intra, inter = nem.run_em(in_data)
+    def _forward(self, nem, c_net, in_data, warm_up=False):
+        """The reference's per-batch loop (Trainer.py:160-200) as ONE fused call.  warm_up: `-if_decoder_warm_up 1` during
+        the first 10 epochs - every iteration's residual is weighted by gamma_prior (Trainer.py:184-185)."""
+        h, gamma, nem_loss, intra, inter = nem.run_em(in_data, warm_up=warm_up)
         return c_net(h, gamma), gamma, nem_loss, intra, inter
 
     def train_nem_mvcnn(self, n_epochs):
@@ -92,6 +92,10 @@ class ModelNetTrainer(object):
             lr = self.optimizer.state_dict()['param_groups'][0]['lr']
             if self.writer:
                 self.writer.add_scalar('params/lr', lr, epoch)
+            sampler = getattr(self.train_loader, "sampler", None)
+            if hasattr(sampler, "set_epoch"):
+                sampler.set_epoch(epoch)                                          # DistributedSampler: a new shuffle every epoch
+            warm_up = nem.if_decoder_warm_up == 1 and epoch < 10                  # Trainer.py:184
             for i, i_data in enumerate(DevicePrefetcher(self.train_loader)):     # batch i+1 is copied while step i runs
                 start = time.time()
                 in_data = i_data[1]
@@ -102,19 +106,19 @@ class ModelNetTrainer(object):
                     in_data = in_data.float()
                 target = i_data[0].cuda(non_blocking=True).long()
                 self.optimizer.zero_grad()
-                out_data, gamma, nem_loss, intra_loss, inter_loss = self._forward(nem, c_net, in_data)
+                out_data, gamma, nem_loss, intra_loss, inter_loss = self._forward(nem, c_net, in_data, warm_up)
                 closs = self.loss_fn(out_data, target)
-                # Trainer.py:203 - with if_total_loss == 1 the reference rebuilds the loss list with torch.Tensor(...),
-                # which detaches it: only the classification loss carries gradient.
-                loss = closs + (nem_loss if nem.if_total_loss == 0 else nem_loss.detach())
+                # Trainer.py:203 - with if_total_loss == 1 the loss is closs + the MEAN of the T per-iteration NEM losses,
+                # rebuilt with torch.Tensor(...), which detaches them: only the classification loss carries gradient.
+                loss = closs + (nem_loss if nem.if_total_loss == 0 else nem.iteration_losses[:, 0].mean())
                 i_acc += 1
                 pred = torch.max(out_data, 1)[1]
                 acc = (pred == target).float().mean()
                 loss.backward()
-                if nem.bn_init_sigma == 1:
-                    clip_gradient(self.optimizer, 5)
                 if self.world > 1:
                     self.bucket.allreduce_mean()
+                if nem.bn_init_sigma == 1:
+                    clip_gradient(self.optimizer, 5)      # after the all-reduce: the single-process semantics of Trainer.py:220-221
                 self.optimizer.step()
                 # one device->host read for all scalars of the step
                 vals = torch.stack([loss.detach(), closs.detach(), nem_loss.detach(), intra_loss.detach(),
@@ -173,6 +177,14 @@ class ModelNetTrainer(object):
                 wrong_class += np.bincount(t[wrong], minlength=self.class_num)
                 all_correct += int((~wrong).sum())
                 all_points += t.shape[0]
+        if self.world > 1:
+            # every rank saw its shard of the validation set: sum the counters before any accuracy is formed
+            t = torch.tensor(np.concatenate([samples_class, wrong_class, [all_loss, nb, all_correct, all_points]]),
+                             dtype=torch.float64, device='cuda')
+            torch.distributed.all_reduce(t)
+            t = t.cpu().numpy()
+            samples_class, wrong_class = t[:self.class_num], t[self.class_num:2 * self.class_num]
+            all_loss, nb, all_correct, all_points = float(t[-4]), int(t[-3]), int(t[-2]), int(t[-1])
         with np.errstate(divide='ignore', invalid='ignore'):
             each_class_acc = (samples_class - wrong_class) / samples_class
         val_mean_class_acc = float(np.nanmean(each_class_acc))

@@ -37,6 +37,9 @@ CASES = {
     # reduced BASELINE configs[2]: 80 views, K=5 (NEM(view_num=80): 700 M parameters)
     "cfg3_b2_k5_m80_t3": dict(B=2, K=5, M=80, D=4096, H=1024, T=3, sigma=0.1, scale=1.0, nclasses=40,
                               if_gamma_prior=1, stop_gamma_grad=0, if_sort=1, if_pooling=0),
+    # BASELINE configs[2] at its real K and T (80 views, K=5, 20 iterations), one object
+    "cfg3_b1_k5_m80_t20": dict(B=1, K=5, M=80, D=4096, H=1024, T=20, sigma=0.1, scale=1.0, nclasses=40,
+                               if_gamma_prior=1, stop_gamma_grad=0, if_sort=1, if_pooling=0),
 }
 
 

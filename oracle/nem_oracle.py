@@ -250,10 +250,13 @@ def head_forward(p: Params, h: torch.Tensor, gamma: torch.Tensor, k: int, if_sor
 def run_em(p: Params, x: torch.Tensor, k: int, iters: int, sigma: float = 0.1,
            init_type: str = "bin_uniform", if_gamma_prior: int = 1, stop_gamma_grad: int = 0,
            gamma0: Optional[torch.Tensor] = None, gamma_prior: Optional[torch.Tensor] = None,
-           keep_all: bool = False, drop=None, dec1_masks=None, dec1_pre: Optional[list] = None):
+           keep_all: bool = False, drop=None, dec1_masks=None, dec1_pre: Optional[list] = None,
+           warm_up: bool = False, losses: Optional[list] = None):
     """T iterations + the last iteration's outer loss.  x: (B,M,D).
     Returns dict(h, gamma, pred, nem_loss, intra, inter[, hist]).  dec1_masks / dec1_pre: per-iteration
-    ReLU-kink diagnostics, see run_inner_rnn."""
+    ReLU-kink diagnostics, see run_inner_rnn.  warm_up: tools/Trainer.py:184-185 (`if_decoder_warm_up == 1 and
+    epoch < 10`): every iteration is fed gamma_prior instead of the running responsibilities.  losses: collects
+    compute_outer_loss of EVERY iteration (Trainer.py:191-195) as (total, intra, inter) tuples."""
     B, M, D = x.shape
     hidden = p["rnn_nem.weight_hh"].shape[1]
     h, pred, g0, gp = init_state(B, k, M, D, hidden, init_type)
@@ -267,8 +270,11 @@ def run_em(p: Params, x: torch.Tensor, k: int, iters: int, sigma: float = 0.1,
     xin = x.unsqueeze(1)
     hist = []
     for it in range(iters):
-        state = em_iteration(p, xin, state, sigma, (drop[0], drop[1], it) if drop else None,
+        st_in = (state[0], state[1], gp) if warm_up else state
+        state = em_iteration(p, xin, st_in, sigma, (drop[0], drop[1], it) if drop else None,
                              dec1_masks[it] if dec1_masks is not None else None, dec1_pre)
+        if losses is not None:
+            losses.append(compute_outer_loss(state[1], state[2], xin, stop_gamma_grad, gp, if_gamma_prior))
         if keep_all:
             hist.append(state)
     h, pred, gamma = state

@@ -44,10 +44,11 @@ def _oracle(cfg, nem, x, dtype, dec1_masks=None, dec1_pre=None):
 # precision of the backward pass.  Measured (tools/relu_flips.py, profiles/r02_relu_flips.txt): at cfg1 with
 # bf16-rounded features exactly one unit, |pre| = 4.0e-7, flips - in the fp32 preset too, whose gradients are then
 # 1.2e-2 off the plain oracle and 1.8e-5 off the oracle that takes the library's decision for that unit.
-KINK = 1e-4          # |pre| / max|pre| below which a ReLU decision is within the fp32-mode forward bar
+KINK = 1e-5          # |pre| / max|pre| below which a ReLU decision is inside the reference's own fp32 rounding of |pre|
+                     # (measured flips: 1e-7 .. 1e-6; the fp32-mode forward bar is 1e-4)
 
 
-def _resolve_relu_kinks(cfg, nem, x, ref, pn, ref_pre, nem_c, max_units=1e-4):
+def _resolve_relu_kinks(cfg, nem, x, ref, pn, ref_pre, nem_c, max_units=1e-5):
     """Compare dec1's ReLU decisions of the CUDA run with the oracle's.  Every disagreement must sit on the kink
     (|pre_oracle| <= KINK * max|pre|) and be rare; if there is one, the oracle is re-evaluated with the library's
     decision for exactly those units.  Returns (ref, pn, number of such units)."""
@@ -185,18 +186,17 @@ def test_dec1_relu_kink_is_the_only_dec1_error():
 
 
 @pytest.mark.parametrize("name", ["cfg1_b8_k3_m12_t10", "prior0_b5_k2_m12_t3"])
-def test_run_em_bf16_h_mode(name):
-    """'bf16_h' = the bf16-features preset with row-scaled fp16 operands in every data-gradient contraction of the
-    BPTT chain (same number of tensor-core passes): gradient errors 2-3x below the plain preset - every tensor
-    within 7e-3 in max-norm (1e-2 for 'bf16'; what is left is the bf16 rounding of the weight-gradient
-    contractions, worst on matrices summed over few rows)."""
+def test_run_em_bf16_margin(name):
+    """The margin of the 'bf16' preset on the well-conditioned cases: with row-scaled fp16 operands in every
+    data-gradient contraction of the BPTT chain every gradient tensor is within 7e-3 in max-norm (what is left is the
+    bf16 rounding of the weight-gradient contractions, worst on matrices summed over few rows)."""
     _, cfg = load_golden(name)
     nem, _ = seeded_models(cfg)
     x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
     xb = x.bfloat16()
     ref_pre = []
     ref, pn = _oracle(cfg, nem, xb.float(), torch.float32, dec1_pre=ref_pre)
-    res, nem_c = _cuda(cfg, nem, xb, "bf16_h", torch.bfloat16)
+    res, nem_c = _cuda(cfg, nem, xb, "bf16", torch.bfloat16)
     ref, pn, _ = _resolve_relu_kinks(cfg, nem, xb.float(), ref, pn, ref_pre, nem_c)
     for k in ("h", "gamma", "nem_loss"):
         assert rel_err(res[k].reshape(-1), ref[k].reshape(-1)) < 1e-3, k
@@ -209,6 +209,23 @@ def test_run_em_bf16_h_mode(name):
         e = rel_err(named[n].grad, p.grad)
         if not e < 7e-3:
             bad[n] = e
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name", ["cfg1_b8_k3_m12_t10", "prior0_b5_k2_m12_t3"])
+def test_run_em_bf16_b8_variant(name):
+    """'bf16_b8' (round 1's headline: single bf16 planes in the data-gradient contractions as well): 1e-2 on the
+    well-conditioned cases - it has no margin on 'peaky', which is why it is no longer the default."""
+    _, cfg = load_golden(name)
+    nem, _ = seeded_models(cfg)
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    xb = x.bfloat16()
+    ref_pre = []
+    ref, pn = _oracle(cfg, nem, xb.float(), torch.float32, dec1_pre=ref_pre)
+    res, nem_c = _cuda(cfg, nem, xb, "bf16_b8", torch.bfloat16)
+    ref, pn, _ = _resolve_relu_kinks(cfg, nem, xb.float(), ref, pn, ref_pre, nem_c)
+    named = dict(nem_c.named_parameters())
+    bad = {n: rel_err(named[n].grad, p.grad) for n, p in pn.items() if p.grad is not None and not rel_err(named[n].grad, p.grad) < 1e-2}
     assert not bad, bad
 
 
@@ -406,6 +423,47 @@ def test_cfg3_80_views_matches_reference_golden():
     assert not bad, bad
 
 
+def test_cfg3_full_k_and_t_matches_reference_golden():
+    """BASELINE configs[2] at its real K = 5 and T = 20 (80 views x 4096-d; one object - what the CPU reference finishes
+    in a minute): full training step against the frozen reference outputs, fp32 preset at 1e-4; the bf16 preset's
+    forward (descriptors, responsibilities, argmax) at 1e-2 on the same object with bf16-rounded features is checked
+    against the oracle."""
+    from helpers import grad_summary
+    from multi_view_sort_b200.functional import cross_entropy
+    z, cfg = load_golden("cfg3_b1_k5_m80_t20")
+    nem, head = seeded_models(cfg)
+    x, y = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    nem, head = nem.cuda().eval(), head.cuda().eval()
+    h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda(), cfg["T"])
+    logits = head(h, gamma)
+    loss = cross_entropy(logits, y.cuda()) + nem_loss
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel_err(h, z["h"]) < 1e-4
+    assert rel_err(gamma.reshape(z["gamma"].shape), z["gamma"]) < 1e-4
+    assert rel_err(logits, z["logits"]) < 1e-4
+    assert (logits.argmax(1).cpu().numpy() == z["logits"].argmax(1)).all()
+    assert abs(loss.item() - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
+    worst = {}
+    for prefix, mod in (("nem.", nem), ("head.", head)):
+        for n, p in mod.named_parameters():
+            g = z["grad/" + prefix + n]
+            if g.size == 1:
+                assert p.grad is None, n
+                continue
+            mine = grad_summary(p.grad)
+            worst[prefix + n] = max(abs(mine[1] - g[1]) / g[1], float(abs(mine[3:] - g[3:]).max() / g[1]))
+    bad = {k: v for k, v in worst.items() if not v < (5e-4 if k.endswith("att.0.bias") else 1e-4)}
+    assert not bad, bad
+    # bf16 preset, forward-only: single-pass contractions, 2-slot ring at M = 80
+    nem.precision = head.precision = "bf16"
+    with torch.no_grad():
+        hb, gb, lb, _, _ = nem.run_em(x.cuda().bfloat16(), cfg["T"])
+        r = O.run_em(params_of(nem, requires_grad=False, device="cpu"), x.bfloat16().float(), cfg["K"], cfg["T"], cfg["sigma"])
+    assert rel_err(hb, r["h"]) < 1e-2 and rel_err(gb, r["gamma"]) < 1e-2
+    assert abs(lb.item() - r["nem_loss"].item()) < 1e-2 * abs(r["nem_loss"].item())
+
+
 def test_step_level_forward_matches_oracle_iterations():
     """The reference's own driving pattern (tools/Trainer.py:304-336): init_state, then T x
     nem(input, state) under no_grad - every intermediate state against the oracle's."""
@@ -426,8 +484,81 @@ def test_step_level_forward_matches_oracle_iterations():
             assert rel_err(h, ref[t][0]) < 1e-4, t
             assert rel_err(pred, ref[t][1]) < 1e-4, t
             assert rel_err(gamma, ref[t][2]) < 1e-4, t
-    with pytest.raises(NotImplementedError):
-        nem(xc.unsqueeze(1), (init[0], init[1], init[2]))     # grads enabled: directs the caller to run_em
+
+
+@pytest.mark.parametrize("name", ["prior0_b5_k2_m12_t3", "peaky_b6_k4_m12_t4"])
+def test_step_level_training_loop_matches_oracle(name):
+    """The reference's TRAINING loop, unchanged (tools/Trainer.py:160-219): init_state, T x `state = nem(input, state)`
+    with gradients enabled, compute_outer_loss in torch on the returned (pred, gamma) of EVERY iteration, backward
+    through autograd.  NEM.forward is one autograd node per iteration (vmm_em_step_forward / _backward); gradients flow
+    through h, pred and gamma between the nodes.  Every parameter gradient against the oracle's, and against the fused
+    run_em path."""
+    _, cfg = load_golden(name)
+    nem, _ = seeded_models(cfg)
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    wh, wg = _probe(cfg)
+    wl = [0.3, 0.5, 1.0, 0.7, 0.2][:cfg["T"]]                  # a gradient into every iteration's loss, not only the last
+    pn = params_of(nem)
+    losses = []
+    r = O.run_em(pn, x, cfg["K"], cfg["T"], cfg["sigma"], "bin_uniform", cfg["if_gamma_prior"], cfg["stop_gamma_grad"], losses=losses)
+    ref_loss = sum(w * l[0] for w, l in zip(wl, losses)) + (r["h"] * wh).sum() + (r["gamma"] * wg).sum()
+    ref_loss.backward()
+    tol = 4e-2 if name.startswith("peaky") else 1e-4           # see test_train_step_fp32_mode_matches_reference_golden
+    nem = nem.cuda().eval()
+    xc = x.cuda()
+    init = nem.init_state(xc.shape, xc)
+    state, gamma_prior = (init[0], init[1], init[2]), init[3]
+    total = 0.0
+    for t in range(cfg["T"]):
+        state = nem(xc.unsqueeze(1), state)
+        assert state[0].requires_grad and state[1].requires_grad and state[2].requires_grad
+        nl, _, _ = O.compute_outer_loss(state[1], state[2], xc.unsqueeze(1), cfg["stop_gamma_grad"], gamma_prior, cfg["if_gamma_prior"])
+        assert abs(nl.item() - losses[t][0].item()) < max(tol, 1e-4) * abs(losses[t][0].item()), t
+        total = total + wl[t] * nl
+    h, pred, gamma = state
+    (total + (h * wh.cuda()).sum() + (gamma * wg.cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel_err(h, r["h"]) < tol and rel_err(gamma, r["gamma"]) < tol and rel_err(pred, r["pred"]) < tol
+    named = dict(nem.named_parameters())
+    errs = {n: rel_err(named[n].grad, p.grad) for n, p in pn.items() if p.grad is not None}
+    assert all(named[n].grad is None for n, p in pn.items() if p.grad is None)
+    bad = {n: v for n, v in errs.items() if not v < tol}
+    assert not bad, bad
+
+
+def test_warm_up_and_total_loss_match_oracle():
+    """-if_decoder_warm_up 1 (tools/Trainer.py:184-185: every iteration is fed gamma_prior) and -if_total_loss 1
+    (:203: the mean of all T NEM losses, detached) on the fused path: outputs, every iteration's loss and every
+    gradient against the oracle."""
+    _, cfg = load_golden("prior0_b5_k2_m12_t3")
+    cfg = dict(cfg, if_gamma_prior=1, stop_gamma_grad=0)
+    nem, _ = seeded_models(cfg)
+    nem.if_total_loss = 1
+    x, _ = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=10, scale=cfg["scale"])
+    wh, wg = _probe(cfg)
+    pn = params_of(nem)
+    losses = []
+    r = O.run_em(pn, x, cfg["K"], cfg["T"], cfg["sigma"], "bin_uniform", 1, 0, warm_up=True, losses=losses)
+    (r["nem_loss"] + (r["h"] * wh).sum() + (r["gamma"] * wg).sum()).backward()
+    nem = nem.cuda().eval()
+    h, gamma, nem_loss, intra, inter = nem.run_em(x.cuda(), cfg["T"], warm_up=True)
+    (nem_loss + (h * wh.cuda()).sum() + (gamma * wg.cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel_err(h, r["h"]) < 1e-4 and rel_err(gamma, r["gamma"]) < 1e-4
+    il = nem.iteration_losses.cpu()
+    assert il.shape == (cfg["T"], 3)
+    for t in range(cfg["T"]):
+        for j in range(3):
+            assert abs(il[t, j].item() - losses[t][j].item()) < 1e-4 * abs(losses[t][j].item()) + 1e-9, (t, j)
+    assert abs(nem_loss.item() - losses[-1][0].item()) < 1e-4 * abs(losses[-1][0].item())
+    named = dict(nem.named_parameters())
+    errs = {n: rel_err(named[n].grad, p.grad) for n, p in pn.items() if p.grad is not None}
+    bad = {n: v for n, v in errs.items() if not v < 1e-4}
+    assert not bad, bad
+    # and without warm-up the result differs (the flag is live)
+    with torch.no_grad():
+        h2, _, _, _, _ = nem.run_em(x.cuda(), cfg["T"])
+    assert rel_err(h2, r["h"]) > 1e-3
 
 
 def test_train_mode_dropout():
@@ -479,7 +610,7 @@ def test_train_mode_dropout():
         nem.dropout_seed = 99
         t3 = step()[3].item()
     assert close(loss.item(), t2) and not close(t2, t3)
-    from multi_view_sort_b200.csrc_probe import kept_fraction
+    from csrc_probe import kept_fraction
     assert abs(kept_fraction(0.5, 1234, 1 << 16) - 0.5) < 0.01
 
 
@@ -568,6 +699,20 @@ def test_full_size_properties_configs1():
         _, _, lb, _, _ = nem.run_em(x[1000:])
         assert torch.equal(gs, gamma[:1000]) and torch.equal(hs, h[:K * 1000])
         assert abs((1000 * la.item() + 3096 * lb.item()) / B - loss.item()) < 1e-5 * abs(loss.item())
+        # ... and pinned to the ORACLE: objects are independent in the forward pass, so the first and the last 8 objects
+        # of the 4096-batch (the CTA-pair tiles, the 10.4-wave schedule, the 2-slot inference ring at full size) must
+        # reproduce the CPU oracle run on those 16 objects alone: north_star's 1e-2 for bf16 features, 1e-4 for fp32
+        idx = torch.cat([torch.arange(0, 8), torch.arange(B - 8, B)])
+        pn = params_of(nem, requires_grad=False, device="cpu")
+        r = O.run_em(pn, x[idx.cuda()].float().cpu(), K, T, 0.1, "bin_uniform", 1, 0)
+        assert rel_err(h.view(B, K, H)[idx.cuda()], r["h"].view(16, K, H)) < 1e-2
+        assert rel_err(gamma[idx.cuda()], r["gamma"]) < 1e-2
+        nem.precision = "fp32"
+        hf, gf, _, _, _ = nem.run_em(x.float())
+        assert rel_err(hf.view(B, K, H)[idx.cuda()], r["h"].view(16, K, H)) < 1e-4
+        assert rel_err(gf[idx.cuda()], r["gamma"]) < 1e-4
+        del hf, gf
+        nem.precision = "bf16"
     # gradients: full batch == weighted sum of two halves (bf16 gradient planes: compare in relative L2)
     wh = torch.randn(B * K, H, device="cuda", generator=g) * 1e-3
     def grads(xs, whs, weight):
