@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """Headline benchmark: VMM EM objects/sec, fwd+bwd (BASELINE.json metric, configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32|bf16_fast]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32|...] [--scaling weak|strong]
     python bench.py --impl reference ...       # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl eager_gpu ...       # the reference's eager PyTorch path (oracle port) on the B200, micro-batched
+    python bench.py --workload infer_sweep [--objects 1000000]   # BASELINE configs[4]: forward-only sweep over (K, T)
 
 One "step" = one training pass over a batch of synthetic objects: 12 views x 4096-d features,
 K = 3 latent views, 10 EM iterations -> head -> cross-entropy + NEM loss -> hand-written backward
--> (N > 1: one NCCL all-reduce of the flat gradient bucket) -> Adam.  Weak scaling: every rank
-holds `--batch` objects (default 4096, configs[1]); `value` is the whole-job objects/s.
+-> (N > 1: NCCL all-reduce of the flat gradient bucket) -> Adam.  Weak scaling (default): every rank
+holds `--batch` objects (4096, configs[1]); strong scaling: the 4096 objects are split over the ranks.
+`value` is the whole-job objects/s.
 
 Timing: CUDA events on the launching stream around exactly K steps, bracketed by a barrier and
 torch.cuda.synchronize(), max over ranks.  The step's working set (tens of GB of activations)
 is far larger than the 126 MB L2, so no explicit L2 flush is needed ("l2": "inputs>L2").
+
+At N = 1 the one JSON line also carries `presets.fp32` (the reference's own arithmetic class, 1e-4 parity: value, e2e,
+roofline - same steps), `gpu_eager_baseline` (the reference's eager PyTorch path on the same GPU) and `cpu_baseline`.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -31,6 +38,12 @@ K_LATENT, M_VIEWS, D_FEAT, H_HID, T_ITERS, N_CLASSES = 3, 12, 4096, 1024, 10, 40
 # Reference-algorithm GEMM FLOPs per object, fwd+bwd incl. head, counted with torch's flop counter on the
 # reference's own code (SURVEY.md 8d / BASELINE.md 2).
 ALG_FLOPS_PER_OBJECT = 39.681e9
+METRIC = "VMM EM objects/sec fwd+bwd (12x4096, K=3, 10 iters)"
+
+
+def nem_fwd_flops(K, T, M=M_VIEWS):
+    """Reference-algorithm forward FLOPs of the NEM per object: T * 2K * (16,777,216 M + 19,922,944)."""
+    return T * 2 * K * (16777216 * M + 19922944)
 
 
 def peaks():
@@ -41,6 +54,31 @@ def peaks():
                     source="measured")
     except Exception:
         return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+def kernel_source_hash():
+    """Identity of the code a committed ncu capture belongs to: the CUDA sources + the preset table."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "multi_view_sort_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    with open(os.path.join(ROOT, "multi_view_sort_b200", "functional.py"), "rb") as f:
+        h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(precision, batch):
+    """dram bytes of all contraction launches of one step from the committed ncu capture - ONLY when the capture was taken
+    on these kernel sources, this preset and this batch (profiles/gemm_traffic.json is keyed by all three)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("precision") == precision and tr.get("batch") == batch and tr.get("source_hash") == kernel_source_hash():
+            return tr["dram_bytes_per_step"]
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -80,14 +118,18 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def build_models(precision, device):
+def build_models(precision, device, K=K_LATENT, T=T_ITERS):
     import torch
     from multi_view_sort_b200 import NEM, Multi_View_Net
     torch.manual_seed(10)
-    nem = NEM(nclasses=N_CLASSES, view_num=M_VIEWS, k=K_LATENT, input_dim=D_FEAT, rnn_hidden_size=H_HID, iter_num=T_ITERS,
+    nem = NEM(nclasses=N_CLASSES, view_num=M_VIEWS, k=K, input_dim=D_FEAT, rnn_hidden_size=H_HID, iter_num=T,
               init_type="bin_uniform", gamma_prior_loss=1, e_sigma=0.1, precision=precision)
-    head = Multi_View_Net(None, "vggm", nclasses=N_CLASSES, k=K_LATENT, rnn_hidden_size=H_HID, precision=precision)
+    head = Multi_View_Net(None, "vggm", nclasses=N_CLASSES, k=K, rnn_hidden_size=H_HID, precision=precision)
     return nem.to(device), head.to(device)
+
+
+ORACLE_CFG = dict(nclasses=N_CLASSES, M=M_VIEWS, K=K_LATENT, D=D_FEAT, H=H_HID, T=T_ITERS, stop_gamma_grad=0,
+                  if_gamma_prior=1, sigma=0.1, if_sort=1, if_pooling=0)
 
 
 def cpu_oracle_rate(batch=8, reps=3, fwd_bwd=True):
@@ -95,10 +137,8 @@ def cpu_oracle_rate(batch=8, reps=3, fwd_bwd=True):
     import torch
     from oracle import nem_oracle as O
     from oracle.make_golden import seeded_models
-    cfg = dict(nclasses=N_CLASSES, M=M_VIEWS, K=K_LATENT, D=D_FEAT, H=H_HID, T=T_ITERS, stop_gamma_grad=0,
-               if_gamma_prior=1, sigma=0.1, if_sort=1, if_pooling=0)
     torch.set_num_threads(os.cpu_count() or 1)
-    nem, head = seeded_models(cfg)
+    nem, head = seeded_models(ORACLE_CFG)
     pn = {k: v for k, v in nem.named_parameters()}
     ph = {k: v for k, v in head.named_parameters()}
     x, y = O.make_inputs(batch, M_VIEWS, D_FEAT, N_CLASSES, seed=10)
@@ -127,10 +167,8 @@ def run_reference(args):
     import torch
     from oracle import nem_oracle as O
     from oracle.make_golden import seeded_models
-    cfg = dict(nclasses=N_CLASSES, M=M_VIEWS, K=K_LATENT, D=D_FEAT, H=H_HID, T=T_ITERS, stop_gamma_grad=0,
-               if_gamma_prior=1, sigma=0.1, if_sort=1, if_pooling=0)
     torch.set_num_threads(os.cpu_count() or 1)
-    nem, head = seeded_models(cfg)
+    nem, head = seeded_models(ORACLE_CFG)
     params = list(nem.parameters()) + list(head.parameters())
     opt = torch.optim.Adam(params, lr=5e-5, weight_decay=1e-4)
     pn = {k: v for k, v in nem.named_parameters()}
@@ -152,7 +190,7 @@ def run_reference(args):
     val = batch * steps / dt
     cores = torch.get_num_threads()
     print(json.dumps({
-        "impl": "reference", "metric": "VMM EM objects/sec fwd+bwd (12x4096, K=3, 10 iters)", "value": val,
+        "impl": "reference", "metric": METRIC, "value": val,
         "unit": "objects/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1] shape (12 views x 4096-d, K=3, T=10, head + CE + Adam); bounded sample of 8 "
@@ -166,37 +204,148 @@ def run_reference(args):
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", help="bf16 (bf16 features, 1e-2 parity), fp32 (1e-4 parity), bf16_fast")
-    ap.add_argument("--batch", type=int, default=4096, help="objects per GPU per step")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-optimizer", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+# ---- the reference's own eager PyTorch path on the B200 ("what you'd get without this work") ----
+def eager_gpu_rates(dev, steps=3, warmup=2, batch=256, variants=("fp32", "tf32", "bf16_autocast")):
+    """Oracle port (bit-identical to the reference on CPU) moved to the GPU: torch eager kernels (cuBLAS / ATen), autograd,
+    torch.optim.Adam; micro-batches of `batch` objects (the autograd tape is 124.7 MB per object - 4096 do not fit).  Same
+    step definition as ours: EM fwd (T = 10) + head + CE + NEM loss + backward + Adam, features resident in HBM.
+    None of this library's kernels run here."""
+    import torch
+    from oracle import nem_oracle as O
+    from oracle.make_golden import seeded_models
+    out = {}
+    x, y = O.make_inputs(batch, M_VIEWS, D_FEAT, N_CLASSES, seed=10)
+    x, y = x.to(dev), y.to(dev)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    for v in variants:
+        nem, head = seeded_models(ORACLE_CFG)
+        nem, head = nem.to(dev), head.to(dev)
+        pn = {k: p for k, p in nem.named_parameters()}
+        ph = {k: p for k, p in head.named_parameters()}
+        opt = torch.optim.Adam(list(pn.values()) + list(ph.values()), lr=5e-5, weight_decay=1e-4)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = (v == "tf32")
 
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(v == "bf16_autocast")):
+                r = O.train_step(pn, ph, x, y, K_LATENT, T_ITERS, 0.1, 1, 0, 1, 0)
+            r["loss"].backward()
+            opt.step()
+
+        try:
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[v] = dict(value=batch / (ms * 1e-3), unit="objects/s", ms_per_step=ms, micro_batch=batch,
+                          peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 1))
+        except Exception as e:       # e.g. out of memory on a shared box: report, do not fail the bench
+            out[v] = dict(value=None, error=str(e).splitlines()[0][:200])
+        del nem, head, pn, ph, opt
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["note"] = ("oracle port of the reference (train_nem.py / Trainer.py:160-219) run eagerly on this GPU: fp32 = "
+                   "allow_tf32 False (the reference's arithmetic), tf32 = allow_tf32 True, bf16_autocast = torch.autocast; "
+                   f"{steps} steps of {batch} objects after {warmup} warm-up, inputs resident")
+    return out
+
+
+def run_eager_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    r = eager_gpu_rates(dev, steps=args.steps, warmup=max(args.warmup, 2), batch=256)
+    best = r.get("fp32", {})
+    print(json.dumps({"impl": "eager_gpu", "metric": METRIC, "value": best.get("value"), "unit": "objects/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": best.get("ms_per_step"),
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "configs[1] shape, micro-batch 256 (torch eager, cuBLAS sgemm without TF32)"},
+                      "variants": r, "gpu_launches": 0}))
+
+
+# ---- BASELINE configs[4]: forward-only sweep ---------------------------------------------------------------------------
+def run_infer_sweep(args):
+    """1M synthetic objects (12 views x 4096-d, bf16 features) generated on the device in chunks, forward only (EM + head
+    logits), K in {2,3,4,6} x T in {3,10}; objects are sharded over the ranks, no collective on the data path."""
     import torch
     import torch.distributed as dist
-    from multi_view_sort_b200._lib import lib
-    from multi_view_sort_b200.dist import GradBucket
-    from multi_view_sort_b200.functional import cross_entropy
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU path)")
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-    xdtype = torch.float32 if args.precision.startswith("fp32") else torch.bfloat16
-    nem, head = build_models(args.precision, dev)
+    total = args.objects
+    chunk = args.chunk
+    mine = total // world + (1 if rank < total % world else 0)
+    pk = peaks()
+    cells = []
+    for K in (2, 3, 4, 6):
+        for T in (3, 10):
+            nem, head = build_models(args.precision, dev, K=K, T=T)
+            nem.eval(); head.eval()
+            gen = torch.Generator(device=dev).manual_seed(1000 * rank + 17 * K + T)
+            ms, done, first = 0.0, 0, True
+            with torch.no_grad():
+                while done < mine:
+                    n = min(chunk, mine - done)
+                    x = torch.relu(torch.randn(n, M_VIEWS, D_FEAT, device=dev, generator=gen)).bfloat16()   # untimed
+                    if first:                                  # warm-up on the first chunk (weight planes, allocator)
+                        for _ in range(2):
+                            head(*nem.run_em(x, T)[:2])
+                        first = False
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    h, gamma, _, _, _ = nem.run_em(x, T)
+                    logits = head(h, gamma)
+                    e1.record()
+                    e1.synchronize()
+                    ms += e0.elapsed_time(e1)
+                    done += n
+                    del x, h, gamma, logits
+            t = torch.tensor([ms], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rate = total / (t.item() * 1e-3)
+            alg = nem_fwd_flops(K, T) * total / (t.item() * 1e-3) / 1e12 / world
+            cells.append(dict(K=K, T=T, objects_per_s=rate, ms=t.item(), alg_tflops_per_gpu=alg,
+                              frac_of_sustained_peak=alg / pk["bf16_sustained"]))
+            del nem, head
+            torch.cuda.empty_cache()
+    if rank == 0:
+        k3 = next(c for c in cells if c["K"] == 3 and c["T"] == 10)
+        print(json.dumps({"metric": "VMM EM inference objects/sec (12x4096, forward only)", "value": k3["objects_per_s"],
+                          "unit": "objects/s", "n_gpus": world, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"BASELINE configs[4]: {total} objects generated on-device in chunks of {chunk}, "
+                                                 "forward EM + head, K in {2,3,4,6} x T in {3,10}; value = the K=3, T=10 cell",
+                                     "precision": args.precision, "objects": total, "chunk": chunk},
+                          "cells": cells}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_preset(precision, B, args, dev, rank, world, local, profile_gemm=True):
+    """value / e2e / roofline of one precision preset at batch B per rank."""
+    import torch
+    import torch.distributed as dist
+    from multi_view_sort_b200._lib import lib
+    from multi_view_sort_b200.dist import GradBucket
+    from multi_view_sort_b200.features import DevicePrefetcher
+    from multi_view_sort_b200.functional import cross_entropy
+
+    xdtype = torch.float32 if precision.startswith("fp32") else torch.bfloat16
+    nem, head = build_models(precision, dev)
     params = list(nem.parameters()) + list(head.parameters())
     opt = torch.optim.Adam(params, lr=5e-5, weight_decay=1e-4, fused=True)
     bucket = GradBucket(params)
@@ -207,12 +356,13 @@ def main():
     y_host = torch.randint(0, N_CLASSES, (B,), generator=g).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
     loss_host = torch.zeros(1).pin_memory()
+    ce_scale = 1.0 / B                                   # equal shards: the mean of the rank means is the global mean
 
     def step(x, y):
         opt.zero_grad(set_to_none=True)
         h, gamma, nem_loss, _, _ = nem.run_em(x, T_ITERS)
         logits = head(h, gamma)
-        loss = cross_entropy(logits, y) + nem_loss
+        loss = cross_entropy(logits, y, ce_scale) + nem_loss
         loss.backward()
         if world > 1:
             bucket.allreduce_mean()
@@ -259,8 +409,6 @@ def main():
     # The timed region holds K host->device copies of the step's inputs (pinned memory) and K device->host reads of
     # the loss.  Inputs go through the package's DevicePrefetcher, as in ModelNetTrainer.train_nem_mvcnn: batch i+1
     # is copied on a side stream while step i computes; batch 0 of the region is not overlapped with anything.
-    from multi_view_sort_b200.features import DevicePrefetcher
-
     feeder = DevicePrefetcher([], dev)                      # its two device buffer sets are allocated by the warm-up run
 
     def e2e_run(steps):
@@ -270,75 +418,118 @@ def main():
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()       # the caller reads the loss every step
 
-    def timed_once(fn):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sync_all()
-        return t.item()
-
     e2e_run(3)
-    ms_e2e = timed_once(lambda: e2e_run(args.steps))
+    ms_e2e = timed(lambda: e2e_run(args.steps), 1)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
     # ---- dominant kernel (tcgen05 contraction): summed launch time over one extra pass of K steps -------
-    L.vmm_gemm_profile(1)
-    timed(lambda: step(x_dev, y_dev), args.steps)
-    tot_ms, ex_fl, nl = C.c_double(), C.c_double(), C.c_longlong()
-    L.vmm_gemm_profile_read(C.byref(tot_ms), C.byref(ex_fl), C.byref(nl))
-    L.vmm_gemm_profile(0)
     pk = peaks()
-    traffic = None      # dram bytes of all contraction launches of one step, from the committed ncu capture
-    try:
-        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
-            tr = json.load(f)
-        if tr.get("precision") == args.precision and tr.get("batch") == B:
-            traffic = tr["dram_bytes_per_step"]
-    except Exception:
-        pass
-    gemm_ms_per_step = tot_ms.value / args.steps
-    alg_flops_step = ALG_FLOPS_PER_OBJECT * B
-    achieved = alg_flops_step / (gemm_ms_per_step * 1e-3) / 1e12
-    executed = ex_fl.value / (tot_ms.value * 1e-3) / 1e12 if tot_ms.value > 0 else 0.0
+    roof = None
+    if profile_gemm:
+        L.vmm_gemm_profile(1)
+        timed(lambda: step(x_dev, y_dev), args.steps)
+        tot_ms, ex_fl, nl = C.c_double(), C.c_double(), C.c_longlong()
+        L.vmm_gemm_profile_read(C.byref(tot_ms), C.byref(ex_fl), C.byref(nl))
+        L.vmm_gemm_profile(0)
+        traffic = committed_traffic(precision, B)
+        gemm_ms_per_step = tot_ms.value / args.steps
+        alg_flops_step = ALG_FLOPS_PER_OBJECT * B
+        alg_bytes_step = (110592 if xdtype == torch.bfloat16 else 208896) * B
+        achieved = alg_flops_step / (gemm_ms_per_step * 1e-3) / 1e12
+        executed = ex_fl.value / (tot_ms.value * 1e-3) / 1e12 if tot_ms.value > 0 else 0.0
+        roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_sustained"], "traffic": traffic,
+                "traffic_over_algorithmic_bytes": (traffic / alg_bytes_step) if traffic else None,
+                "kernel": "gemm_tcgen05_kernel (all contraction launches of the step)",
+                "launches_per_step": nl.value / args.steps, "kernel_ms_per_step": gemm_ms_per_step,
+                "kernel_share_of_step": gemm_ms_per_step / (ms / args.steps),
+                "executed_tflops": executed, "executed_frac": executed / pk["bf16_sustained"],
+                "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                "note": "achieved = reference-algorithm FLOPs (39.681 GFLOP/object) / summed launch time; executed counts "
+                        "every tensor-core pass the precision preset issues; traffic = dram bytes of the contraction launches "
+                        "of one step from the committed ncu capture, printed only when it was taken on these sources",
+                "step_frac": (alg_flops_step / (ms / args.steps * 1e-3) / 1e12) / pk["bf16_sustained"],
+                "hbm_frac": (alg_bytes_step / (ms / args.steps * 1e-3) / 1e9) / pk["hbm_gbs"]}
+    res = dict(value=value, ms_per_step=ms / args.steps, clocks=clocks,
+               e2e={"value": e2e_value, "unit": "objects/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size()
+                    + y_host.numel() * 8, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+               gpu_launches=int(launches), roofline=roof, features=str(xdtype).replace("torch.", ""))
+    del nem, head, opt, bucket, params, x_dev, y_dev, feeder
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager_gpu"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer_sweep"])
+    ap.add_argument("--precision", default="bf16", help="bf16 (bf16 features, 1e-2 parity), fp32 (1e-4 parity), bf16_b8, bf16_fast")
+    ap.add_argument("--batch", type=int, default=4096, help="objects per GPU per step (weak) / in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--objects", type=int, default=1000000, help="infer_sweep: objects in total")
+    ap.add_argument("--chunk", type=int, default=16384, help="infer_sweep: objects generated and processed per call")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip presets.fp32 and gpu_eager_baseline")
+    ap.add_argument("--no-optimizer", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.impl == "eager_gpu":
+        return run_eager_gpu(args)
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU path)")
+    if args.workload == "infer_sweep":
+        return run_infer_sweep(args)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.scaling == "strong":
+        assert args.batch % world == 0, "strong scaling: --batch must be divisible by the number of ranks"
+        B = args.batch // world
+    else:
+        B = args.batch
+
+    main_res = measure_preset(args.precision, B, args, dev, rank, world, local)
+    extras = {}
+    if world == 1 and not args.no_extras and args.precision == "bf16":
+        r = measure_preset("fp32", B, args, dev, rank, world, local)
+        extras["presets"] = {"fp32": {
+            "what": "fp32 features, fp16 hi/lo operand pairs forward (3 tensor-core passes), 2 bf16 planes backward: the reference's "
+                    "fp32 results to 1e-4 (tests/test_em_gpu.py::test_run_em_fp32_mode)",
+            "value": r["value"], "unit": "objects/s", "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "roofline": r["roofline"],
+            "clocks": r["clocks"], "gpu_launches": r["gpu_launches"]}}
+        extras["gpu_eager_baseline"] = eager_gpu_rates(dev)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     out = {
-        "metric": "VMM EM objects/sec fwd+bwd (12x4096, K=3, 10 iters)", "value": value, "unit": "objects/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": main_res["value"], "unit": "objects/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_step"],
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "bf16" if args.precision.startswith("bf16") else "f32 (split-bf16 tensor-core passes)",
         "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: 12 views x 4096-d features, K=3, T=10, batch 4096 objects per GPU, "
-                               "training step = EM fwd + head + CE + NEM loss + backward"
+        "config": {"workload": "BASELINE configs[1]: 12 views x 4096-d features, K=3, T=10, "
+                               + (f"batch {B} objects per GPU" if args.scaling == "weak" else f"global batch {args.batch} split over the GPUs")
+                               + ", training step = EM fwd + head + CE + NEM loss + backward"
                                + (" + NCCL grad all-reduce" if world > 1 else "") + ("" if args.no_optimizer else " + Adam"),
-                   "precision": args.precision, "features": str(xdtype).replace("torch.", ""), "batch_per_gpu": B,
+                   "precision": args.precision, "features": main_res["features"], "batch_per_gpu": B,
                    "global_batch": B * world, "l2": "inputs>L2 (tens of GB of activations per step)"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "objects/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size()
-                + y_host.numel() * 8, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16_sustained"], "traffic": traffic,
-                     "kernel": "gemm_tcgen05_kernel (all contraction launches of the step)",
-                     "launches_per_step": nl.value / args.steps, "kernel_ms_per_step": gemm_ms_per_step,
-                     "kernel_share_of_step": gemm_ms_per_step / (ms / args.steps),
-                     "executed_tflops": executed, "executed_frac": executed / pk["bf16_sustained"],
-                     "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
-                     "note": "achieved = reference-algorithm FLOPs (39.681 GFLOP/object) / summed launch time; executed counts "
-                             "every split-bf16 pass the precision mode issues",
-                     "step_frac": (alg_flops_step / (ms / args.steps * 1e-3) / 1e12) / pk["bf16_sustained"],
-                     "hbm_frac": ((110592 if xdtype == torch.bfloat16 else 208896) * B / (ms / args.steps * 1e-3) / 1e9)
-                     / pk["hbm_gbs"]},
+        "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
+        "roofline": main_res["roofline"],
     }
+    out.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], _ = cpu_oracle_rate()
     print(json.dumps(out))

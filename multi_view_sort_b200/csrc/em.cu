@@ -147,6 +147,7 @@ struct Scratch {
   Planes dpred, dv5, dv4, dgi, dgh, dv2, dg1, dxw1p, dw13p;
   float *dz, *du, *de, *da, *dxw1, *dw13, *dw1b3;
   RowF16 dv5h, dv4h, dv2h, dg1h, dgih, dghh, dpredh;     // row-scaled fp16 copies (dgrad_fp16)
+  float *dpred_gmax = nullptr, *dpred_inv_cols = nullptr;                    // dpredh carries ONE scale: the bound of max|dpred| and 1/scale per column
   long long bytes;
   Scratch(const vmm_em_config& c, void* base) {
     Dims d(c);
@@ -187,6 +188,7 @@ struct Scratch {
         dg1h.p = b.take<__half>(d.RM * E1);  dg1h.inv_scale = b.take<float>(d.RM);
         if (d.save_delta) {
           dpredh.p = b.take<__half>(d.RM * d.D); dpredh.inv_scale = b.take<float>(d.RM);
+          dpred_gmax = b.take<float>(1); dpred_inv_cols = b.take<float>(d.D);
         }
         if (d.H <= 1024) {
           dgih.p = b.take<__half>(d.R * 3 * d.H); dgih.inv_scale = b.take<float>(d.R);
@@ -623,13 +625,25 @@ int em_backward(const vmm_em_config* c, const vmm_em_params* p, const void* weig
     const bool dpred_h = d.dgh && d.save_delta && !kappa && sc.dpredh.p && cur.dmax;
     if (d.save_delta)
       VMM_TRY(estep_dpred(static_cast<int>(d.RM), d.D, cur.delta, d.save_delta, x, c->x_is_bf16, d.D, d.K, d.M, c->sigma,
-                          sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st, dpred_h ? sc.dpredh.p : nullptr,
-                          dpred_h ? sc.dpredh.inv_scale : nullptr, dpred_h ? cur.dmax : nullptr));
+                          sc.alpha, sc.beta, kappa, dpred_h ? Planes() : sc.dpred, g->dec3_b, st, dpred_h ? sc.dpredh.p : nullptr,
+                          dpred_h ? sc.dpredh.inv_scale : nullptr, dpred_h ? cur.dmax : nullptr, nullptr,
+                          dpred_h ? sc.dpred_gmax : nullptr, dpred_h ? sc.dpred_inv_cols : nullptr));
     else
       VMM_TRY(estep_backward(static_cast<int>(d.RM), d.D, E1, sel_act(d, FC_EBWD, cur.z.f), sel_w(d, FC_EBWD, w.w3.f), p->dec3_b, x,
                              c->x_is_bf16, d.D, d.K, d.M, c->sigma, sc.alpha, sc.beta, kappa, sc.dpred, g->dec3_b, st));
     // --- dec3: weight gradient; dz = dpred W3 (+ dG1_{t+1} W13, the path through the next residual)
-    VMM_TRY(linear_wgrad(sc.dpred, cur.z.b, d.RM, d.D, E1, g->dec3_w, d.chain_b, st));
+    if (dpred_h) {
+      // dW3 += dpred^T z with the globally scaled fp16 dpred and the fp16 hi plane of z: output row d scaled by 1/S
+      Planes a;
+      a.n = 1;
+      a.fmt = VMM_FMT_F16PAIR;
+      a.p[0] = reinterpret_cast<__nv_bfloat16*>(sc.dpredh.p);
+      vmm_gemm_seg s[9];
+      const int ns = make_segs(s, a, d.D, cur.z.f.first(1), E1, d.RM);
+      VMM_TRY(gemm_bf16(d.D, E1, ns, s, true, true, g->dec3_w, E1, nullptr, true, 0, 0, st, sc.dpred_inv_cols));
+    } else {
+      VMM_TRY(linear_wgrad(sc.dpred, cur.z.b, d.RM, d.D, E1, g->dec3_w, d.chain_b, st));
+    }
     {
       vmm_gemm_seg s[18];
       const bool one = (g_bwd_bits & VMM_BWD_DGRAD_SINGLE) != 0;

@@ -85,7 +85,8 @@ int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x
                 int k_latent, int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
                 const Planes& dpred, float* colsum, cudaStream_t stream, __half* dpred_h = nullptr,
                 float* inv_scale = nullptr, const float* row_dmax = nullptr,    // + row-scaled fp16 copy (kappa == nullptr only)
-                const float* add = nullptr);                                    // + an explicit dL/dpred term [rows, D]
+                const float* add = nullptr,                                     // + an explicit dL/dpred term [rows, D]
+                float* gmax = nullptr, float* inv_scale_cols = nullptr);        // ONE scale for the tensor: fp16 copy only, no bf16 plane
 int split_planes(const float* src, long long n, const Planes& out, cudaStream_t stream);
 int split_op(const float* src, long long n, const Op& out, cudaStream_t stream);   // both operand sets
 int bf16_to_f16(const void* src_bf16, long long n, void* dst_f16, cudaStream_t stream);

@@ -3,10 +3,14 @@
 // reductions by warp shuffle + smem), one thread per column for the column reductions.
 #include "stages.cuh"
 
+#include "ptx.cuh"
+
 #include <cuda_fp16.h>
 #include <math.h>
 
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 namespace vmm {
 namespace {
@@ -34,11 +38,11 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // power-of-two row scale that puts amax into [2^11, 2^12) (fp16 keeps 11 bits for everything within 2^-25 of it)
 __device__ __forceinline__ float row_scale_pow2(float amax) {
   if (!(amax > 0.f) || amax > 3.0e38f) return 1.f;
-  int e;
-  frexpf(amax, &e);                       // amax = m * 2^e, m in [0.5, 1)
-  e = 12 - e;
-  e = e > 120 ? 120 : (e < -100 ? -100 : e);
-  return ldexpf(1.f, e);
+  // amax = 1.m * 2^(eb - 127)  ->  frexp exponent e = eb - 126, scale = 2^(12 - e), clamped to [2^-100, 2^120];
+  // built from the exponent bits (a denormal amax, eb = 0, lands on the upper clamp)
+  int se = 138 - static_cast<int>((__float_as_uint(amax) >> 23) & 0xffu);
+  se = se > 120 ? 120 : (se < -100 ? -100 : se);
+  return __uint_as_float(static_cast<unsigned>(se + 127) << 23);
 }
 __device__ __forceinline__ void store_half4(__half* p, long long idx, float a, float b, float c, float d) {
   const __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
@@ -525,38 +529,90 @@ __global__ void __launch_bounds__(256, 2) ln1k_backward_rows_kernel(
 // 4t..4t+3 of every row, so dxw1 and the four column reductions (dLN gamma/beta, d bias, d w1b3) are
 // thread-private accumulators, and the 2*NR row reductions of a group share one block barrier.
 // ------------------------------------------------------------------------------------------
-template <int NR>
+// Row pipeline shared by the streaming stages below: every CTA keeps STAGES row slots in shared memory, filled by 1-D
+// bulk async copies (the TMA engine, completion on an mbarrier per slot) that thread 0 issues STAGES-1 rows ahead of
+// the row being processed.  A slot is refilled only after a __syncthreads() that follows every thread's last read of
+// it.  Loads never sit in registers while they are in flight, so the per-SM bytes in flight (what Little's law asks
+// for: ~65 KB at 6.5 TB/s) no longer depend on occupancy or on the reductions' barriers.
+template <int NR, int STAGES>
 __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
     LnDesc d, int act, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
     const float* __restrict__ d_out, long long ldd, float* __restrict__ dgamma, float* __restrict__ dxw1, Planes dg1,
     float* __restrict__ d_ln_g, float* __restrict__ d_ln_b, float* __restrict__ d_bias, float* __restrict__ d_w1b3,
     RowF16 dg1h) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  constexpr int ROWB = W1K * 4;                  // one 1024-wide fp32 row
+  constexpr int SLOT = (2 + 2 * NR) * ROWB;      // xw1 row | dxw1 row | G1 rows [NR] | incoming-gradient rows [NR]
+  __shared__ uint64_t bar[STAGES];
   __shared__ float red[2][8][2 * NR];
   __shared__ float red2[2][8][2 * NR];     // per row: sum for dgamma, max|dG1| for the row-scaled fp16 copy
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = tid * 4;
-  const int groups = d.rows / NR;
+  const int groups = d.rows / NR, G = gridDim.x;
+  const bool has_g1 = d.C != nullptr, has_dxw = dxw1 != nullptr;
+  const uint32_t slot_bytes = ROWB * (1 + (has_dxw ? 1 : 0) + (has_g1 ? NR : 0) + NR);
+  auto issue = [&](int grp, int s) {             // thread 0 only
+    uint8_t* slot = dsm + s * SLOT;
+    mbar_arrive_expect_tx(&bar[s], slot_bytes);
+    bulk_load_1d(slot, d.xw1 + static_cast<long long>(grp) * W1K, ROWB, &bar[s]);
+    if (has_dxw) bulk_load_1d(slot + ROWB, dxw1 + static_cast<long long>(grp) * W1K, ROWB, &bar[s]);
+    const int b = grp / d.mv, m = grp - b * d.mv;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const long long row = static_cast<long long>(b * NR + k) * d.mv + m;
+      if (has_g1) bulk_load_1d(slot + (2 + k) * ROWB, d.C + row * d.ldc, ROWB, &bar[s]);
+      bulk_load_1d(slot + (2 + NR + k) * ROWB, d_out + row * ldd, ROWB, &bar[s]);
+    }
+  };
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+    for (int i = 0; i < STAGES - 1; ++i)
+      if (blockIdx.x + i * G < groups) issue(blockIdx.x + i * G, i);
+  }
+  __syncthreads();
   const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c), bias = ld4(d.bias + c);
   const float4 w1b3 = d.C ? ld4(d.w1b3 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 a_g = make_float4(0.f, 0.f, 0.f, 0.f), a_b = a_g, a_bias = a_g, a_w = a_g;
-  int par = 0;
-  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x, par ^= 1) {
+  // per-row scalars (responsibility, LayerNorm statistics) of the NEXT group are fetched one group ahead
+  float gam_n[NR], mean_n[NR], rstd_n[NR];
+  auto fetch_scalars = [&](int grp) {
     const int b = grp / d.mv, m = grp - b * d.mv;
-    const float4 xw = ld4(d.xw1 + static_cast<long long>(grp) * W1K + c);
-    float4 sv[NR], dy[NR];
-    float gam[NR], mean[NR], rstd[NR], part[2 * NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
       const int row = (b * NR + k) * d.mv + m;
-      gam[k] = __ldg(d.gamma + row);
-      mean[k] = __ldg(mean_in + row);
-      rstd[k] = __ldg(rstd_in + row);
+      gam_n[k] = __ldg(d.gamma + row);
+      mean_n[k] = __ldg(mean_in + row);
+      rstd_n[k] = __ldg(rstd_in + row);
+    }
+  };
+  if (blockIdx.x < groups) fetch_scalars(blockIdx.x);
+  int par = 0, it = 0;
+  for (int grp = blockIdx.x; grp < groups; grp += G, par ^= 1, ++it) {
+    const int s = it % STAGES;
+    if (tid == 0) {
+      const int ahead = grp + (STAGES - 1) * G;
+      if (ahead < groups) issue(ahead, (it + STAGES - 1) % STAGES);
+    }
+    const int b = grp / d.mv, m = grp - b * d.mv;
+    float gam[NR], mean[NR], rstd[NR], part[2 * NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) { gam[k] = gam_n[k]; mean[k] = mean_n[k]; rstd[k] = rstd_n[k]; }
+    if (grp + G < groups) fetch_scalars(grp + G);
+    mbar_wait(&bar[s], (it / STAGES) & 1);
+    const float4* sl = reinterpret_cast<const float4*>(dsm + s * SLOT);
+    const float4 xw = sl[tid];
+    float4 dxo = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_dxw) dxo = sl[256 + tid];
+    float4 sv[NR], dy[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
       sv[k] = xw;
-      if (d.C) {
-        const float4 g1 = ld4(d.C + static_cast<long long>(row) * d.ldc + c);
+      if (has_g1) {
+        const float4 g1 = sl[(2 + k) * 256 + tid];
         sv[k] = make_float4(xw.x - g1.x - w1b3.x, xw.y - g1.y - w1b3.y, xw.z - g1.z - w1b3.z, xw.w - g1.w - w1b3.w);
       }
-      dy[k] = ld4(d_out + static_cast<long long>(row) * ldd + c);
+      dy[k] = sl[(2 + NR + k) * 256 + tid];
     }
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
@@ -577,7 +633,7 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
 #pragma unroll
       for (int j = 0; j < 2 * NR; ++j) red[par][warp][j] = part[j];
     }
-    __syncthreads();
+    __syncthreads();                     // every thread has read its part of slot s: thread 0 may refill it next iteration
     float4 accx = make_float4(0.f, 0.f, 0.f, 0.f);
     float dgam[NR], amaxk[NR];
     float4 ngk[NR];
@@ -612,12 +668,9 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
       a_bias.x += dv.x; a_bias.y += dv.y; a_bias.z += dv.z; a_bias.w += dv.w;
       a_w.x += ng.x; a_w.y += ng.y; a_w.z += ng.z; a_w.w += ng.w;
     }
-    if (dxw1) {
-      float4* px = reinterpret_cast<float4*>(dxw1 + static_cast<long long>(grp) * W1K + c);
-      float4 a = *px;
-      a.x += accx.x; a.y += accx.y; a.z += accx.z; a.w += accx.w;
-      *px = a;
-    }
+    if (has_dxw)
+      *reinterpret_cast<float4*>(dxw1 + static_cast<long long>(grp) * W1K + c) =
+          make_float4(dxo.x + accx.x, dxo.y + accx.y, dxo.z + accx.z, dxo.w + accx.w);
     if (dgamma || dg1h.p) {
 #pragma unroll
       for (int k = 0; k < NR; ++k) {
@@ -662,216 +715,275 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
 // three column reductions are thread-private accumulators; the next row is prefetched into registers before the
 // two row reductions of the current one (one barrier per row, double-buffered partials).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1) lnw4k_backward_fused_kernel(
+constexpr int LNW4K_STAGES = 5;
+__global__ void __launch_bounds__(1024, 1) lnw4k_backward_fused_kernel(
     LnDesc d, int act, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
     const float* __restrict__ d_out, long long ldd, Planes dvp, float* __restrict__ d_ln_g, float* __restrict__ d_ln_b,
     float* __restrict__ d_bias, RowF16 dvh) {
-  // 512 threads x 2 float4 (columns 4t..4t+3 and 2048+4t..): two rows are prefetched into registers ahead of the
-  // one being reduced, i.e. 64 KB in flight per SM - what Little's law asks for at ~6 TB/s and ~1.5 us of latency.
-  __shared__ float2 red[2][16];
-  __shared__ float redm[2][16];
+  // One persistent block of 1024 threads per SM, thread t owns columns 4t..4t+3 of every row it sees: the three column
+  // reductions are thread-private accumulators.  Rows arrive through a 5-slot bulk-copy pipeline (slot = the row of C
+  // + the row of the incoming gradient, 32 KB): four rows = 128 KB are in flight per SM while one is reduced.
+  extern __shared__ __align__(128) uint8_t dsm[];
+  constexpr int STAGES = LNW4K_STAGES, ROWB = 4096 * 4;
+  __shared__ uint64_t bar[STAGES];
+  __shared__ float2 red[2][32];
+  __shared__ float redm[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int G = gridDim.x;
-  float4 g[2], bb[2], bias[2], a_g[2], a_b[2], a_bias[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int c = tid * 4 + i * 2048;
-    g[i] = ld4(d.ln_g + c); bb[i] = ld4(d.ln_b + c); bias[i] = ld4(d.bias + c);
-    a_g[i] = make_float4(0.f, 0.f, 0.f, 0.f); a_b[i] = a_g[i]; a_bias[i] = a_g[i];
-  }
-  struct RowRegs { float4 v[2], go[2]; float mean, rstd; };
-  auto fetch = [&](int row, RowRegs& r) {
-    if (row < d.rows) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c = tid * 4 + i * 2048;
-        r.v[i] = ld4(d.C + static_cast<long long>(row) * d.ldc + c);
-        r.go[i] = ld4(d_out + static_cast<long long>(row) * ldd + c);
-      }
-      r.mean = __ldg(mean_in + row);
-      r.rstd = __ldg(rstd_in + row);
-    }
+  const int G = gridDim.x, c = tid * 4;
+  auto issue = [&](int row, int s) {              // thread 0 only
+    uint8_t* slot = dsm + s * 2 * ROWB;
+    mbar_arrive_expect_tx(&bar[s], 2 * ROWB);
+    bulk_load_1d(slot, d.C + static_cast<long long>(row) * d.ldc, ROWB, &bar[s]);
+    bulk_load_1d(slot + ROWB, d_out + static_cast<long long>(row) * ldd, ROWB, &bar[s]);
   };
-  RowRegs r0, r1, r2;
-  int row = blockIdx.x;
-  fetch(row, r0);
-  fetch(row + G, r1);
-  for (int par = 0; row < d.rows; row += G, par ^= 1) {
-    fetch(row + 2 * G, r2);
-    const float mean = r0.mean, rstd = r0.rstd;
-    float xh[2][4], dy[2][4];
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+    for (int i = 0; i < STAGES - 1; ++i)
+      if (blockIdx.x + i * G < d.rows) issue(blockIdx.x + i * G, i);
+  }
+  __syncthreads();
+  const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c), bias = ld4(d.bias + c);
+  float4 a_g = make_float4(0.f, 0.f, 0.f, 0.f), a_b = a_g, a_bias = a_g;
+  float mean_n = 0.f, rstd_n = 0.f;
+  if (blockIdx.x < d.rows) { mean_n = __ldg(mean_in + blockIdx.x); rstd_n = __ldg(rstd_in + blockIdx.x); }
+  int it = 0;
+  for (int row = blockIdx.x, par = 0; row < d.rows; row += G, par ^= 1, ++it) {
+    const int s = it % STAGES;
+    if (tid == 0) {
+      const int ahead = row + (STAGES - 1) * G;
+      if (ahead < d.rows) issue(ahead, (it + STAGES - 1) % STAGES);
+    }
+    const float mean = mean_n, rstd = rstd_n;
+    if (row + G < d.rows) { mean_n = __ldg(mean_in + row + G); rstd_n = __ldg(rstd_in + row + G); }
+    mbar_wait(&bar[s], (it / STAGES) & 1);
+    const float4 v = reinterpret_cast<const float4*>(dsm + s * 2 * ROWB)[tid];
+    const float4 go = reinterpret_cast<const float4*>(dsm + s * 2 * ROWB + ROWB)[tid];
+    float ds[4] = {1.f, 1.f, 1.f, 1.f};
+    if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * d.width + c, ds);
+    const float vv[4] = {v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w};
+    const float gg[4] = {g.x, g.y, g.z, g.w}, be[4] = {bb.x, bb.y, bb.z, bb.w};
+    const float oo[4] = {go.x, go.y, go.z, go.w};
+    float xh[4], dy[4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int c = tid * 4 + i * 2048;
-      float ds[4] = {1.f, 1.f, 1.f, 1.f};
-      if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * d.width + c, ds);
-      const float vv[4] = {r0.v[i].x + bias[i].x, r0.v[i].y + bias[i].y, r0.v[i].z + bias[i].z, r0.v[i].w + bias[i].w};
-      const float gg[4] = {g[i].x, g[i].y, g[i].z, g[i].w}, be[4] = {bb[i].x, bb[i].y, bb[i].z, bb[i].w};
-      const float oo[4] = {r0.go[i].x, r0.go[i].y, r0.go[i].z, r0.go[i].w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        xh[i][q] = (vv[q] - mean) * rstd;
-        dy[i][q] = oo[q] * ds[q] * act_grad_fast(act, fmaf(xh[i][q], gg[q], be[q]));
-        const float dx = dy[i][q] * gg[q];
-        s1 += dx;
-        s2 = fmaf(dx, xh[i][q], s2);
-      }
+    for (int q = 0; q < 4; ++q) {
+      xh[q] = (vv[q] - mean) * rstd;
+      dy[q] = oo[q] * ds[q] * act_grad_fast(act, fmaf(xh[q], gg[q], be[q]));
+      const float dx = dy[q] * gg[q];
+      s1 += dx;
+      s2 = fmaf(dx, xh[q], s2);
     }
     s1 = warp_sum_f(s1);
     s2 = warp_sum_f(s2);
     if (lane == 0) red[par][warp] = make_float2(s1, s2);
-    __syncthreads();
-    const float2 pr = red[par][lane & 15];
-    float c1 = pr.x, c2 = pr.y;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-    }
-    c1 *= (1.0f / 4096.f);
-    c2 *= (1.0f / 4096.f);
-    float dvv[2][4];
+    __syncthreads();                     // also: every thread has read slot s, thread 0 may refill it next iteration
+    const float2 pr = red[par][lane];
+    const float c1 = warp_sum_f(pr.x) * (1.0f / 4096.f), c2 = warp_sum_f(pr.y) * (1.0f / 4096.f);
+    float dv[4];
     float amax = 0.f;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float gg[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        dvv[i][q] = rstd * (dy[i][q] * gg[q] - c1 - xh[i][q] * c2);
-        amax = fmaxf(amax, fabsf(dvv[i][q]));
-      }
+    for (int q = 0; q < 4; ++q) {
+      dv[q] = rstd * (dy[q] * gg[q] - c1 - xh[q] * c2);
+      amax = fmaxf(amax, fabsf(dv[q]));
     }
     if (dvh.p) {                                       // row-scaled fp16 copy for the data-gradient contraction
       amax = warp_max_f(amax);
       if (lane == 0) redm[par][warp] = amax;
       __syncthreads();
-      const float sc = row_scale_pow2(warp_max_f(redm[par][lane & 15]));
+      const float sc = row_scale_pow2(warp_max_f(redm[par][lane]));
       if (tid == 0) dvh.inv_scale[row] = 1.f / sc;
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-        store_half4(dvh.p, static_cast<long long>(row) * d.width + tid * 4 + i * 2048, dvv[i][0] * sc, dvv[i][1] * sc,
-                    dvv[i][2] * sc, dvv[i][3] * sc);
+      store_half4(dvh.p, static_cast<long long>(row) * d.width + c, dv[0] * sc, dv[1] * sc, dv[2] * sc, dv[3] * sc);
     }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int c = tid * 4 + i * 2048;
-      const float* dv = dvv[i];
-      store_planes4(dvp, static_cast<long long>(row) * d.width + c, make_float4(dv[0], dv[1], dv[2], dv[3]));
-      a_g[i].x = fmaf(dy[i][0], xh[i][0], a_g[i].x); a_g[i].y = fmaf(dy[i][1], xh[i][1], a_g[i].y);
-      a_g[i].z = fmaf(dy[i][2], xh[i][2], a_g[i].z); a_g[i].w = fmaf(dy[i][3], xh[i][3], a_g[i].w);
-      a_b[i].x += dy[i][0]; a_b[i].y += dy[i][1]; a_b[i].z += dy[i][2]; a_b[i].w += dy[i][3];
-      a_bias[i].x += dv[0]; a_bias[i].y += dv[1]; a_bias[i].z += dv[2]; a_bias[i].w += dv[3];
-    }
-    r0 = r1;
-    r1 = r2;
+    store_planes4(dvp, static_cast<long long>(row) * d.width + c, make_float4(dv[0], dv[1], dv[2], dv[3]));
+    a_g.x = fmaf(dy[0], xh[0], a_g.x); a_g.y = fmaf(dy[1], xh[1], a_g.y);
+    a_g.z = fmaf(dy[2], xh[2], a_g.z); a_g.w = fmaf(dy[3], xh[3], a_g.w);
+    a_b.x += dy[0]; a_b.y += dy[1]; a_b.z += dy[2]; a_b.w += dy[3];
+    a_bias.x += dv[0]; a_bias.y += dv[1]; a_bias.z += dv[2]; a_bias.w += dv[3];
   }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int c = tid * 4 + i * 2048;
-    atomicAdd(reinterpret_cast<float4*>(d_ln_g + c), a_g[i]);
-    atomicAdd(reinterpret_cast<float4*>(d_ln_b + c), a_b[i]);
-    atomicAdd(reinterpret_cast<float4*>(d_bias + c), a_bias[i]);
-  }
+  atomicAdd(reinterpret_cast<float4*>(d_ln_g + c), a_g);
+  atomicAdd(reinterpret_cast<float4*>(d_ln_b + c), a_b);
+  atomicAdd(reinterpret_cast<float4*>(d_bias + c), a_bias);
 }
 
-// Backward rows for the wide LN_BIAS stages (4096, 1024*M): one block of width/16 threads per row, four
-// float4 per thread cached in registers between the reduction pass and the output pass.
-__global__ void __launch_bounds__(1024) lnw_backward_rows_kernel(LnDesc d, int act, const float* __restrict__ mean_in,
+// Backward rows for the wide LN_BIAS stages (4096, 1024*M): persistent blocks of width/16 threads, four float4 per
+// thread; rows arrive through a 2-slot bulk-copy pipeline (a slot = the row of C and the row of the incoming gradient),
+// so the next row is in flight while the current one is reduced and written.
+template <int MAXT, bool NEED_Y>            // NEED_Y = false: no activation (dec2), its derivative needs neither y nor beta
+__global__ void __launch_bounds__(MAXT) lnw_backward_rows_kernel(LnDesc d, int act, const float* __restrict__ mean_in,
                                                                  const float* __restrict__ rstd_in,
                                                                  const float* __restrict__ d_out, long long ldd,
                                                                  Planes dvp, float* __restrict__ c1_out,
                                                                  float* __restrict__ c2_out, RowF16 dvh) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  constexpr int STAGES = 2;
+  __shared__ uint64_t bar[STAGES];
   __shared__ float red[32];
-  const int row = blockIdx.x, tid = threadIdx.x;
-  const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
-  const long long rbase = static_cast<long long>(row) * d.width;
-  float4 xh[4], dx[4];
-  float s1 = 0.f, s2 = 0.f;
+  const int tid = threadIdx.x, G = gridDim.x, nt = blockDim.x;
+  const uint32_t rowb = static_cast<uint32_t>(d.width) * 4u;
+  auto issue = [&](int row, int s) {              // thread 0 only
+    uint8_t* slot = dsm + static_cast<size_t>(s) * 2 * rowb;
+    mbar_arrive_expect_tx(&bar[s], 2 * rowb);
+    bulk_load_1d(slot, d.C + static_cast<long long>(row) * d.ldc, rowb, &bar[s]);
+    bulk_load_1d(slot + rowb, d_out + static_cast<long long>(row) * ldd, rowb, &bar[s]);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+    if (blockIdx.x < d.rows) issue(blockIdx.x, 0);
+  }
+  __syncthreads();
+  constexpr bool need_y = NEED_Y;
+  float4 g[4], bb[NEED_Y ? 4 : 1], bias[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int c = (tid + i * blockDim.x) * 4;
-    const float4 v = ln_value4<LN_BIAS>(d, row, 0, 0.f, c, nullptr);
-    const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c);
-    const float4 go = ld4(d_out + static_cast<long long>(row) * ldd + c);
-    float ds[4] = {1.f, 1.f, 1.f, 1.f};
-    if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(rbase + c), ds);
-    xh[i] = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
-    dx[i].x = go.x * ds[0] * act_grad_fast(act, fmaf(xh[i].x, g.x, bb.x)) * g.x;
-    dx[i].y = go.y * ds[1] * act_grad_fast(act, fmaf(xh[i].y, g.y, bb.y)) * g.y;
-    dx[i].z = go.z * ds[2] * act_grad_fast(act, fmaf(xh[i].z, g.z, bb.z)) * g.z;
-    dx[i].w = go.w * ds[3] * act_grad_fast(act, fmaf(xh[i].w, g.w, bb.w)) * g.w;
-    s1 += (dx[i].x + dx[i].y) + (dx[i].z + dx[i].w);
-    s2 += (dx[i].x * xh[i].x + dx[i].y * xh[i].y) + (dx[i].z * xh[i].z + dx[i].w * xh[i].w);
+    const int c = (tid + i * nt) * 4;
+    g[i] = ld4(d.ln_g + c);
+    bias[i] = ld4(d.bias + c);
+    if (NEED_Y) bb[i] = ld4(d.ln_b + c);
   }
-  const float c1 = block_sum(s1, red) / static_cast<float>(d.width);
-  const float c2 = block_sum(s2, red) / static_cast<float>(d.width);
-  if (tid == 0) {
-    c1_out[row] = c1;
-    c2_out[row] = c2;
-  }
-  float amax = 0.f;
+  int it = 0;
+  for (int row = blockIdx.x; row < d.rows; row += G, ++it) {
+    const int s = it & 1;
+    if (tid == 0 && row + G < d.rows) issue(row + G, s ^ 1);     // slot s^1 was consumed before the barriers of iteration it-1
+    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    const long long rbase = static_cast<long long>(row) * d.width;
+    mbar_wait(&bar[s], (it >> 1) & 1);
+    const float4* sv = reinterpret_cast<const float4*>(dsm + static_cast<size_t>(s) * 2 * rowb);
+    const float4* sg = reinterpret_cast<const float4*>(dsm + static_cast<size_t>(s) * 2 * rowb + rowb);
+    float4 xh[4], dx[4];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {                        // dx now holds dv
-    dx[i] = make_float4(rstd * (dx[i].x - c1 - xh[i].x * c2), rstd * (dx[i].y - c1 - xh[i].y * c2),
-                        rstd * (dx[i].z - c1 - xh[i].z * c2), rstd * (dx[i].w - c1 - xh[i].w * c2));
-    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(dx[i].x), fabsf(dx[i].y))), fmaxf(fabsf(dx[i].z), fabsf(dx[i].w)));
-    store_planes4(dvp, rbase + (tid + i * blockDim.x) * 4, dx[i]);
-  }
-  if (dvh.p) {                                         // row-scaled fp16 copy for the data-gradient contraction
-    amax = warp_max_f(amax);
-    __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = amax;
-    __syncthreads();
-    float t = (tid & 31) < (blockDim.x >> 5) ? red[tid & 31] : 0.f;
-    const float sc = row_scale_pow2(warp_max_f(t));
-    if (tid == 0) dvh.inv_scale[row] = 1.f / sc;
+    for (int i = 0; i < 4; ++i) {
+      const int c4 = tid + i * nt;
+      const float4 v = sv[c4], go = sg[c4];
+      float ds[4] = {1.f, 1.f, 1.f, 1.f};
+      if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(rbase + c4 * 4), ds);
+      xh[i] = make_float4((v.x + bias[i].x - mean) * rstd, (v.y + bias[i].y - mean) * rstd, (v.z + bias[i].z - mean) * rstd,
+                          (v.w + bias[i].w - mean) * rstd);
+      const float4 be = bb[NEED_Y ? i : 0];
+      dx[i].x = go.x * ds[0] * (need_y ? act_grad_fast(act, fmaf(xh[i].x, g[i].x, be.x)) : 1.f) * g[i].x;
+      dx[i].y = go.y * ds[1] * (need_y ? act_grad_fast(act, fmaf(xh[i].y, g[i].y, be.y)) : 1.f) * g[i].y;
+      dx[i].z = go.z * ds[2] * (need_y ? act_grad_fast(act, fmaf(xh[i].z, g[i].z, be.z)) : 1.f) * g[i].z;
+      dx[i].w = go.w * ds[3] * (need_y ? act_grad_fast(act, fmaf(xh[i].w, g[i].w, be.w)) : 1.f) * g[i].w;
+      s1 += (dx[i].x + dx[i].y) + (dx[i].z + dx[i].w);
+      s2 += (dx[i].x * xh[i].x + dx[i].y * xh[i].y) + (dx[i].z * xh[i].z + dx[i].w * xh[i].w);
+    }
+    const float c1 = block_sum(s1, red) / static_cast<float>(d.width);      // (its barriers also release slot s)
+    const float c2 = block_sum(s2, red) / static_cast<float>(d.width);
+    if (tid == 0) {
+      c1_out[row] = c1;
+      c2_out[row] = c2;
+    }
+    float amax = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      store_half4(dvh.p, rbase + (tid + i * blockDim.x) * 4, dx[i].x * sc, dx[i].y * sc, dx[i].z * sc, dx[i].w * sc);
+    for (int i = 0; i < 4; ++i) {                        // dx now holds dv
+      dx[i] = make_float4(rstd * (dx[i].x - c1 - xh[i].x * c2), rstd * (dx[i].y - c1 - xh[i].y * c2),
+                          rstd * (dx[i].z - c1 - xh[i].z * c2), rstd * (dx[i].w - c1 - xh[i].w * c2));
+      amax = fmaxf(fmaxf(amax, fmaxf(fabsf(dx[i].x), fabsf(dx[i].y))), fmaxf(fabsf(dx[i].z), fabsf(dx[i].w)));
+      store_planes4(dvp, rbase + (tid + i * nt) * 4, dx[i]);
+    }
+    if (dvh.p) {                                         // row-scaled fp16 copy for the data-gradient contraction
+      amax = warp_max_f(amax);
+      __syncthreads();
+      if ((tid & 31) == 0) red[tid >> 5] = amax;
+      __syncthreads();
+      float t = (tid & 31) < (nt >> 5) ? red[tid & 31] : 0.f;
+      const float sc = row_scale_pow2(warp_max_f(t));
+      if (tid == 0) dvh.inv_scale[row] = 1.f / sc;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        store_half4(dvh.p, rbase + (tid + i * nt) * 4, dx[i].x * sc, dx[i].y * sc, dx[i].z * sc, dx[i].w * sc);
+    }
   }
 }
 
-// Forward for the same wide stages, same thread mapping (the generic kernel re-reads wide rows three times).
-__global__ void __launch_bounds__(1024) lnw_forward_kernel(LnDesc d, int act, Op out, float* __restrict__ mean_out,
+// Forward for the same wide stages: persistent blocks of width/16 threads, four float4 per thread, rows through a
+// bulk-copy pipeline (slot = one row of C); the LayerNorm parameters of a thread's columns stay in registers.
+__device__ __forceinline__ float elu_fwd_fast(float y) {
+  // expm1 for y <= 0: a degree-5 Taylor polynomial near zero (|error| < 3e-8 for y > -0.125), __expf(y) - 1 elsewhere
+  // (absolute error ~1e-7: the same class as the fp32 rounding of the values around it)
+  if (y > 0.f) return y;
+  if (y > -0.125f) return y * fmaf(y, fmaf(y, fmaf(y, fmaf(y, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
+  return __expf(y) - 1.f;
+}
+__device__ __forceinline__ float act_fwd_fast(int act, float y) {
+  if (act == ACT_ELU) return elu_fwd_fast(y);
+  if (act == ACT_RELU) return y > 0.f ? y : 0.f;
+  return y;
+}
+
+template <int MAXT, int STAGES, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) lnw_forward_kernel(LnDesc d, int act, Op out, float* __restrict__ mean_out,
                                                            float* __restrict__ rstd_out) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ uint64_t bar[STAGES];
   __shared__ float red[32];
-  const int row = blockIdx.x, tid = threadIdx.x;
-  float4 v[4];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[i] = ln_value4<LN_BIAS>(d, row, 0, 0.f, (tid + i * blockDim.x) * 4, nullptr);
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mean = block_sum(sum, red) / static_cast<float>(d.width);
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
-    sq += (a * a + b * b) + (e * e + f * f);
-  }
-  const float rstd = 1.0f / sqrtf(block_sum(sq, red) / static_cast<float>(d.width) + d.eps);
+  const int tid = threadIdx.x, G = gridDim.x, nt = blockDim.x;
+  const uint32_t rowb = static_cast<uint32_t>(d.width) * 4u;
+  auto issue = [&](int row, int s) {              // thread 0 only
+    mbar_arrive_expect_tx(&bar[s], rowb);
+    bulk_load_1d(dsm + static_cast<size_t>(s) * rowb, d.C + static_cast<long long>(row) * d.ldc, rowb, &bar[s]);
+  };
   if (tid == 0) {
-    mean_out[row] = mean;
-    rstd_out[row] = rstd;
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+    for (int i = 0; i < STAGES - 1; ++i)
+      if (blockIdx.x + i * G < d.rows) issue(blockIdx.x + i * G, i);
   }
-  const long long obase = static_cast<long long>(row) * d.width;
+  __syncthreads();
+  float4 bias[4], g[4], be[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int c = (tid + i * blockDim.x) * 4;
-    const float4 g = ld4(d.ln_g + c), b = ld4(d.ln_b + c);
-    float4 o;
-    o.x = act_fwd(act, fmaf((v[i].x - mean) * rstd, g.x, b.x));
-    o.y = act_fwd(act, fmaf((v[i].y - mean) * rstd, g.y, b.y));
-    o.z = act_fwd(act, fmaf((v[i].z - mean) * rstd, g.z, b.z));
-    o.w = act_fwd(act, fmaf((v[i].w - mean) * rstd, g.w, b.w));
-    if (d.drop_p > 0.f) {
-      float ds[4];
-      dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(obase + c), ds);
-      o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
+    const int c = (tid + i * nt) * 4;
+    bias[i] = ld4(d.bias + c); g[i] = ld4(d.ln_g + c); be[i] = ld4(d.ln_b + c);
+  }
+  const float inv_w = 1.0f / static_cast<float>(d.width);
+  int it = 0;
+  for (int row = blockIdx.x; row < d.rows; row += G, ++it) {
+    const int s = it % STAGES;
+    if (tid == 0) {
+      const int ahead = row + (STAGES - 1) * G;
+      if (ahead < d.rows) issue(ahead, (it + STAGES - 1) % STAGES);
     }
-    store_op4(out, obase + c, o);
+    mbar_wait(&bar[s], (it / STAGES) & 1);
+    const float4* sv = reinterpret_cast<const float4*>(dsm + static_cast<size_t>(s) * rowb);
+    float4 v[4];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = sv[tid + i * nt];
+      v[i] = make_float4(t.x + bias[i].x, t.y + bias[i].y, t.z + bias[i].z, t.w + bias[i].w);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = block_sum(sum, red) * inv_w;          // (its barriers also release slot s)
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      sq += (a * a + b * b) + (e * e + f * f);
+    }
+    const float rstd = 1.0f / sqrtf(block_sum(sq, red) * inv_w + d.eps);
+    if (tid == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+    const long long obase = static_cast<long long>(row) * d.width;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = (tid + i * nt) * 4;
+      float4 o;
+      o.x = act_fwd_fast(act, fmaf((v[i].x - mean) * rstd, g[i].x, be[i].x));
+      o.y = act_fwd_fast(act, fmaf((v[i].y - mean) * rstd, g[i].y, be[i].y));
+      o.z = act_fwd_fast(act, fmaf((v[i].z - mean) * rstd, g[i].z, be[i].z));
+      o.w = act_fwd_fast(act, fmaf((v[i].w - mean) * rstd, g[i].w, be[i].w));
+      if (d.drop_p > 0.f) {
+        float ds[4];
+        dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(obase + c), ds);
+        o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
+      }
+      store_op4(out, obase + c, o);
+    }
   }
 }
 
@@ -950,129 +1062,140 @@ __global__ void __launch_bounds__(256) gru_forward_kernel(int rows, int H, const
   store_op1(hp_out, idx, h);
 }
 
-// thread per hidden column j, blockIdx.y strides over row chunks (bias gradients need column sums)
-__global__ void __launch_bounds__(256) gru_backward_kernel(int rows, int H, int rows_per_block,
-                                                           const float* __restrict__ gi, const float* __restrict__ gh,
-                                                           const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                                                           const float* __restrict__ h_prev, const float* __restrict__ dh,
-                                                           Planes dgi, Planes dgh,
-                                                           float* __restrict__ dh_prev, float* d_b_ih, float* d_b_hh) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= H) return;
-  const int r0 = blockIdx.y * rows_per_block;
-  const int r1 = min(rows, r0 + rows_per_block);
-  const float bir = b_ih[j], biz = b_ih[H + j], bin = b_ih[2 * H + j];
-  const float bhr = b_hh[j], bhz = b_hh[H + j], bhn = b_hh[2 * H + j];
-  float s_r = 0.f, s_z = 0.f, s_in = 0.f, s_hn = 0.f;
-  for (int row = r0; row < r1; ++row) {
-    const long long g0 = static_cast<long long>(row) * 3 * H + j;
-    const long long hidx = static_cast<long long>(row) * H + j;
-    const float r = sigmoidf_((gi[g0] + bir) + (gh[g0] + bhr));
-    const float z = sigmoidf_((gi[g0 + H] + biz) + (gh[g0 + H] + bhz));
-    const float ghn = gh[g0 + 2 * H] + bhn;
-    const float n = tanhf((gi[g0 + 2 * H] + bin) + r * ghn);
-    const float hp = h_prev[hidx];
-    const float g = dh[hidx];
-    // h = (hp - n) z + n
-    const float dn = g * (1.f - z);
-    const float dz = g * (hp - n);
-    const float dn_pre = dn * (1.f - n * n);
-    const float dr_pre = dn_pre * ghn * r * (1.f - r);
-    const float dz_pre = dz * z * (1.f - z);
-    const float dhn = dn_pre * r;
-    store_planes1(dgi, g0, dr_pre);
-    store_planes1(dgi, g0 + H, dz_pre);
-    store_planes1(dgi, g0 + 2 * H, dn_pre);
-    store_planes1(dgh, g0, dr_pre);
-    store_planes1(dgh, g0 + H, dz_pre);
-    store_planes1(dgh, g0 + 2 * H, dhn);
-    dh_prev[hidx] = g * z;
-    s_r += dr_pre;
-    s_z += dz_pre;
-    s_in += dn_pre;
-    s_hn += dhn;
+// GRU backward.  Persistent blocks of H/4 threads, thread t owns hidden units 4t..4t+3 of every row it sees (the six
+// bias-gradient column sums are thread-private accumulators).  Rows arrive through a 3-slot bulk-copy pipeline (slot =
+// gi row | gh row | h_prev row | dh row = 8 H floats).  Optionally also writes the row-scaled fp16 copies of dgi / dgh
+// for the data-gradient contractions (their row maxima span all three gates).
+constexpr int GRU_STAGES = 3;
+__global__ void __launch_bounds__(256, 2) gru_backward_kernel(int rows, int H, const float* __restrict__ gi,
+                                                              const float* __restrict__ gh, const float* __restrict__ b_ih,
+                                                              const float* __restrict__ b_hh, const float* __restrict__ h_prev,
+                                                              const float* __restrict__ dh, Planes dgi, Planes dgh,
+                                                              float* __restrict__ dh_prev, float* d_b_ih, float* d_b_hh,
+                                                              RowF16 dgih, RowF16 dghh) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  constexpr int STAGES = GRU_STAGES;
+  __shared__ uint64_t bar[STAGES];
+  __shared__ float2 redm[2][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = (blockDim.x + 31) >> 5;
+  // blockIdx.y selects a tile of up to 1024 hidden units (H > 1024: several tiles per row, no fp16 copies)
+  const int G = gridDim.x, h0 = blockIdx.y * 1024, HT = min(1024, H - h0);
+  const int j = h0 + tid * 4;
+  const bool on = tid * 4 < HT;
+  const uint32_t hb = static_cast<uint32_t>(HT) * 4u;
+  const uint32_t slotb = 8 * hb;
+  auto issue = [&](int row, int s) {              // thread 0 only
+    uint8_t* slot = dsm + static_cast<size_t>(s) * slotb;
+    mbar_arrive_expect_tx(&bar[s], slotb);
+#pragma unroll
+    for (int gate = 0; gate < 3; ++gate) {
+      bulk_load_1d(slot + gate * hb, gi + static_cast<long long>(row) * 3 * H + gate * H + h0, hb, &bar[s]);
+      bulk_load_1d(slot + (3 + gate) * hb, gh + static_cast<long long>(row) * 3 * H + gate * H + h0, hb, &bar[s]);
+    }
+    bulk_load_1d(slot + 6 * hb, h_prev + static_cast<long long>(row) * H + h0, hb, &bar[s]);
+    bulk_load_1d(slot + 7 * hb, dh + static_cast<long long>(row) * H + h0, hb, &bar[s]);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+    for (int i = 0; i < STAGES - 1; ++i)
+      if (blockIdx.x + i * G < rows) issue(blockIdx.x + i * G, i);
   }
-  atomicAdd(d_b_ih + j, s_r);
-  atomicAdd(d_b_ih + H + j, s_z);
-  atomicAdd(d_b_ih + 2 * H + j, s_in);
-  atomicAdd(d_b_hh + j, s_r);
-  atomicAdd(d_b_hh + H + j, s_z);
-  atomicAdd(d_b_hh + 2 * H + j, s_hn);
-}
-
-// GRU backward, row-oriented (H <= 1024 threads, thread j owns hidden unit j of every row of its strip): same math
-// as gru_backward_kernel, plus the row-scaled fp16 copies of dgi / dgh for the data-gradient contractions - their
-// row maxima span all three gates, which a column-strip kernel cannot see.
-__global__ void __launch_bounds__(1024) gru_backward_rows_kernel(int rows, int H, int rows_per_block,
-                                                                const float* __restrict__ gi, const float* __restrict__ gh,
-                                                                const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                                                                const float* __restrict__ h_prev, const float* __restrict__ dh,
-                                                                Planes dgi, Planes dgh, float* __restrict__ dh_prev,
-                                                                float* d_b_ih, float* d_b_hh, RowF16 dgih, RowF16 dghh) {
-  __shared__ float2 redm[2][32];
-  const int j = threadIdx.x, lane = j & 31, warp = j >> 5, nw = (blockDim.x + 31) >> 5;
-  const bool on = j < H;
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(rows, r0 + rows_per_block);
-  float bir = 0.f, biz = 0.f, bin = 0.f, bhr = 0.f, bhz = 0.f, bhn = 0.f;
+  __syncthreads();
+  float4 bir = make_float4(0.f, 0.f, 0.f, 0.f), biz = bir, bin = bir, bhr = bir, bhz = bir, bhn = bir;
   if (on) {
-    bir = b_ih[j]; biz = b_ih[H + j]; bin = b_ih[2 * H + j];
-    bhr = b_hh[j]; bhz = b_hh[H + j]; bhn = b_hh[2 * H + j];
+    bir = ld4(b_ih + j); biz = ld4(b_ih + H + j); bin = ld4(b_ih + 2 * H + j);
+    bhr = ld4(b_hh + j); bhz = ld4(b_hh + H + j); bhn = ld4(b_hh + 2 * H + j);
   }
-  float s_r = 0.f, s_z = 0.f, s_in = 0.f, s_hn = 0.f;
-  int par = 0;
-  for (int row = r0; row < r1; ++row, par ^= 1) {
+  float s_r[4] = {0.f, 0.f, 0.f, 0.f}, s_z[4] = {0.f, 0.f, 0.f, 0.f}, s_in[4] = {0.f, 0.f, 0.f, 0.f}, s_hn[4] = {0.f, 0.f, 0.f, 0.f};
+  int it = 0;
+  for (int row = blockIdx.x, par = 0; row < rows; row += G, par ^= 1, ++it) {
+    const int s = it % STAGES;
+    if (tid == 0) {
+      const int ahead = row + (STAGES - 1) * G;
+      if (ahead < rows) issue(ahead, (it + STAGES - 1) % STAGES);
+    }
+    mbar_wait(&bar[s], (it / STAGES) & 1);
+    const float* sl = reinterpret_cast<const float*>(dsm + static_cast<size_t>(s) * slotb);
+    float dr[4] = {0.f, 0.f, 0.f, 0.f}, dz[4] = {0.f, 0.f, 0.f, 0.f}, dn[4] = {0.f, 0.f, 0.f, 0.f}, dhn[4] = {0.f, 0.f, 0.f, 0.f};
+    float dhp[4] = {0.f, 0.f, 0.f, 0.f};
+    float m2 = 0.f, mi = 0.f, mh = 0.f;
+    if (on) {
+      const int js = tid * 4;                        // position inside the tile
+      const float4 gir = *reinterpret_cast<const float4*>(sl + js), giz = *reinterpret_cast<const float4*>(sl + HT + js),
+                   gin = *reinterpret_cast<const float4*>(sl + 2 * HT + js);
+      const float4 ghr = *reinterpret_cast<const float4*>(sl + 3 * HT + js), ghz = *reinterpret_cast<const float4*>(sl + 4 * HT + js),
+                   ghn4 = *reinterpret_cast<const float4*>(sl + 5 * HT + js);
+      const float4 hp4 = *reinterpret_cast<const float4*>(sl + 6 * HT + js), g4 = *reinterpret_cast<const float4*>(sl + 7 * HT + js);
+      const float a_ir[4] = {gir.x + bir.x, gir.y + bir.y, gir.z + bir.z, gir.w + bir.w};
+      const float a_hr[4] = {ghr.x + bhr.x, ghr.y + bhr.y, ghr.z + bhr.z, ghr.w + bhr.w};
+      const float a_iz[4] = {giz.x + biz.x, giz.y + biz.y, giz.z + biz.z, giz.w + biz.w};
+      const float a_hz[4] = {ghz.x + bhz.x, ghz.y + bhz.y, ghz.z + bhz.z, ghz.w + bhz.w};
+      const float a_in[4] = {gin.x + bin.x, gin.y + bin.y, gin.z + bin.z, gin.w + bin.w};
+      const float a_hn[4] = {ghn4.x + bhn.x, ghn4.y + bhn.y, ghn4.z + bhn.z, ghn4.w + bhn.w};
+      const float hp[4] = {hp4.x, hp4.y, hp4.z, hp4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float r = sigmoidf_(a_ir[q] + a_hr[q]);
+        const float z = sigmoidf_(a_iz[q] + a_hz[q]);
+        const float n = tanhf(a_in[q] + r * a_hn[q]);
+        // h = (hp - n) z + n
+        const float dnq = gg[q] * (1.f - z);
+        const float dzq = gg[q] * (hp[q] - n);
+        dn[q] = dnq * (1.f - n * n);
+        dr[q] = dn[q] * a_hn[q] * r * (1.f - r);
+        dz[q] = dzq * z * (1.f - z);
+        dhn[q] = dn[q] * r;
+        dhp[q] = gg[q] * z;
+        s_r[q] += dr[q]; s_z[q] += dz[q]; s_in[q] += dn[q]; s_hn[q] += dhn[q];
+        m2 = fmaxf(m2, fmaxf(fabsf(dr[q]), fabsf(dz[q])));
+        mi = fmaxf(mi, fabsf(dn[q]));
+        mh = fmaxf(mh, fabsf(dhn[q]));
+      }
+    }
+    if (dgih.p) {
+      mi = warp_max_f(fmaxf(m2, mi));
+      mh = warp_max_f(fmaxf(m2, mh));
+      if (lane == 0) redm[par][warp] = make_float2(mi, mh);
+    }
+    __syncthreads();                     // every thread has read slot s (and the row maxima are published)
     const long long g0 = static_cast<long long>(row) * 3 * H + j;
-    const long long hidx = static_cast<long long>(row) * H + j;
-    float dr_pre = 0.f, dz_pre = 0.f, dn_pre = 0.f, dhn = 0.f;
     if (on) {
-      const float r = sigmoidf_((gi[g0] + bir) + (gh[g0] + bhr));
-      const float z = sigmoidf_((gi[g0 + H] + biz) + (gh[g0 + H] + bhz));
-      const float ghn = gh[g0 + 2 * H] + bhn;
-      const float n = tanhf((gi[g0 + 2 * H] + bin) + r * ghn);
-      const float hp = h_prev[hidx];
-      const float g = dh[hidx];
-      const float dn = g * (1.f - z);
-      const float dz = g * (hp - n);
-      dn_pre = dn * (1.f - n * n);
-      dr_pre = dn_pre * ghn * r * (1.f - r);
-      dz_pre = dz * z * (1.f - z);
-      dhn = dn_pre * r;
-      store_planes1(dgi, g0, dr_pre);
-      store_planes1(dgi, g0 + H, dz_pre);
-      store_planes1(dgi, g0 + 2 * H, dn_pre);
-      store_planes1(dgh, g0, dr_pre);
-      store_planes1(dgh, g0 + H, dz_pre);
-      store_planes1(dgh, g0 + 2 * H, dhn);
-      dh_prev[hidx] = g * z;
-      s_r += dr_pre; s_z += dz_pre; s_in += dn_pre; s_hn += dhn;
+      store_planes4(dgi, g0, make_float4(dr[0], dr[1], dr[2], dr[3]));
+      store_planes4(dgi, g0 + H, make_float4(dz[0], dz[1], dz[2], dz[3]));
+      store_planes4(dgi, g0 + 2 * H, make_float4(dn[0], dn[1], dn[2], dn[3]));
+      store_planes4(dgh, g0, make_float4(dr[0], dr[1], dr[2], dr[3]));
+      store_planes4(dgh, g0 + H, make_float4(dz[0], dz[1], dz[2], dz[3]));
+      store_planes4(dgh, g0 + 2 * H, make_float4(dhn[0], dhn[1], dhn[2], dhn[3]));
+      *reinterpret_cast<float4*>(dh_prev + static_cast<long long>(row) * H + j) = make_float4(dhp[0], dhp[1], dhp[2], dhp[3]);
     }
-    const float m2 = fmaxf(fabsf(dr_pre), fabsf(dz_pre));
-    const float mi = warp_max_f(fmaxf(m2, fabsf(dn_pre))), mh = warp_max_f(fmaxf(m2, fabsf(dhn)));
-    if (lane == 0) redm[par][warp] = make_float2(mi, mh);
-    __syncthreads();
-    const float2 t = lane < nw ? redm[par][lane] : make_float2(0.f, 0.f);
-    const float si = row_scale_pow2(warp_max_f(t.x)), sh = row_scale_pow2(warp_max_f(t.y));
-    if (j == 0) {
-      dgih.inv_scale[row] = 1.f / si;
-      dghh.inv_scale[row] = 1.f / sh;
-    }
-    if (on) {
-      dgih.p[g0] = __float2half_rn(dr_pre * si);
-      dgih.p[g0 + H] = __float2half_rn(dz_pre * si);
-      dgih.p[g0 + 2 * H] = __float2half_rn(dn_pre * si);
-      dghh.p[g0] = __float2half_rn(dr_pre * sh);
-      dghh.p[g0 + H] = __float2half_rn(dz_pre * sh);
-      dghh.p[g0 + 2 * H] = __float2half_rn(dhn * sh);
+    if (dgih.p) {
+      const float2 t = lane < nw ? redm[par][lane] : make_float2(0.f, 0.f);
+      const float si = row_scale_pow2(warp_max_f(t.x)), sh = row_scale_pow2(warp_max_f(t.y));
+      if (tid == 0) {
+        dgih.inv_scale[row] = 1.f / si;
+        dghh.inv_scale[row] = 1.f / sh;
+      }
+      if (on) {
+        store_half4(dgih.p, g0, dr[0] * si, dr[1] * si, dr[2] * si, dr[3] * si);
+        store_half4(dgih.p, g0 + H, dz[0] * si, dz[1] * si, dz[2] * si, dz[3] * si);
+        store_half4(dgih.p, g0 + 2 * H, dn[0] * si, dn[1] * si, dn[2] * si, dn[3] * si);
+        store_half4(dghh.p, g0, dr[0] * sh, dr[1] * sh, dr[2] * sh, dr[3] * sh);
+        store_half4(dghh.p, g0 + H, dz[0] * sh, dz[1] * sh, dz[2] * sh, dz[3] * sh);
+        store_half4(dghh.p, g0 + 2 * H, dhn[0] * sh, dhn[1] * sh, dhn[2] * sh, dhn[3] * sh);
+      }
     }
   }
   if (on) {
-    atomicAdd(d_b_ih + j, s_r);
-    atomicAdd(d_b_ih + H + j, s_z);
-    atomicAdd(d_b_ih + 2 * H + j, s_in);
-    atomicAdd(d_b_hh + j, s_r);
-    atomicAdd(d_b_hh + H + j, s_z);
-    atomicAdd(d_b_hh + 2 * H + j, s_hn);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      atomicAdd(d_b_ih + j + q, s_r[q]);
+      atomicAdd(d_b_ih + H + j + q, s_z[q]);
+      atomicAdd(d_b_ih + 2 * H + j + q, s_in[q]);
+      atomicAdd(d_b_hh + j + q, s_r[q]);
+      atomicAdd(d_b_hh + H + j + q, s_z[q]);
+      atomicAdd(d_b_hh + 2 * H + j + q, s_hn[q]);
+    }
   }
 }
 
@@ -1388,6 +1511,26 @@ int pick_rows_per_block(int rows, int col_blocks) {
 // as OPL bf16 residual planes, plus exact fp32 column sums (the dec3 bias gradient).
 // One thread owns 8 consecutive columns of a strip of rows; four rows are in flight per thread.
 // ------------------------------------------------------------------------------------------
+// Upper bound of max |dL/dpred| over the whole tensor: |delta * E(delta)| <= sigma * e^-1/2 for every delta, so
+// max|dpred_r| <= 0.607 sigma |alpha_r| + max|delta_r| |beta_r|; the maximum over rows lands in *gmax_bits (non-negative
+// floats order like their bit patterns; zeroed by the caller).
+__global__ void __launch_bounds__(256) dpred_bound_kernel(int rows, float sigma, const float* __restrict__ alpha,
+                                                          const float* __restrict__ beta, const float* __restrict__ row_dmax,
+                                                          unsigned* __restrict__ gmax_bits) {
+  __shared__ float red[8];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
+  if (r < rows) v = 0.62f * sigma * fabsf(alpha[r]) + row_dmax[r] * fabsf(beta[r]);
+  v = warp_max_f(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    v = warp_max_f(v);
+    if (threadIdx.x == 0 && v > 0.f && v < 3.0e38f) atomicMax(gmax_bits, __float_as_uint(v));
+  }
+}
+
 template <typename DT>
 __device__ __forceinline__ void ld_delta8(const DT* p, float (&v)[8]) {
   if constexpr (sizeof(DT) == 2) {
@@ -1414,9 +1557,18 @@ __global__ void __launch_bounds__(256) estep_dpred_kernel(int rows, int D, int r
                                                           __nv_bfloat16* __restrict__ p2, float* __restrict__ colsum,
                                                           __half* __restrict__ ph, float* __restrict__ inv_scale,
                                                           const float* __restrict__ row_dmax, float sigma,
-                                                          const float* __restrict__ add) {
+                                                          const float* __restrict__ add, const float* __restrict__ gmax,
+                                                          float* __restrict__ inv_scale_cols) {
   const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (col >= D) return;
+  // gmax != nullptr: ONE power-of-two scale for the whole tensor (from a bound of max|dpred| over all rows) - the fp16
+  // copy then serves the data-gradient AND the weight-gradient contraction (a per-row scale cannot be factored out of a
+  // reduction over rows), and no bf16 plane is written (OPL = 0)
+  const float gsc = gmax ? row_scale_pow2(__ldg(gmax)) : 0.f;
+  if (gmax && inv_scale_cols && blockIdx.y == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) inv_scale_cols[col + q] = 1.f / gsc;
+  }
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1445,7 +1597,7 @@ __global__ void __launch_bounds__(256) estep_dpred_kernel(int rows, int D, int r
       if (ph) {
         // row-scaled fp16 copy for the data-gradient contraction.  |delta * E(delta)| <= sigma * e^-1/2 for every
         // delta, so max|dpred_r| <= 0.607 sigma |alpha_r| + max|delta_r| |beta_r| (max|delta_r| from the forward pass).
-        const float sc = row_scale_pow2(0.62f * sigma * fabsf(a) + __ldg(row_dmax + r) * fabsf(b));
+        const float sc = gmax ? gsc : row_scale_pow2(0.62f * sigma * fabsf(a) + __ldg(row_dmax + r) * fabsf(b));
         if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[r] = 1.f / sc;
         store_half4(ph, static_cast<long long>(r) * D + col, out[0] * sc, out[1] * sc, out[2] * sc, out[3] * sc);
         store_half4(ph, static_cast<long long>(r) * D + col + 4, out[4] * sc, out[5] * sc, out[6] * sc, out[7] * sc);
@@ -1498,6 +1650,26 @@ __global__ void __launch_bounds__(256) estep_dpred_kernel(int rows, int D, int r
 }  // namespace
 
 // ---- host wrappers ------------------------------------------------------------------------
+// Dynamic shared memory above 48 KB is a per-device opt-in of each kernel: done once per (kernel, device).
+static int opt_in_smem(const void* kernel, int bytes) {
+  struct Seen { const void* k; int dev; int bytes; };
+  static std::mutex mu;
+  static std::vector<Seen> seen;
+  int dev = 0;
+  VMM_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  for (Seen& e : seen)
+    if (e.k == kernel && e.dev == dev) {
+      if (e.bytes >= bytes) return 0;
+      VMM_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      e.bytes = bytes;
+      return 0;
+    }
+  VMM_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  seen.push_back({kernel, dev, bytes});
+  return 0;
+}
+
 static int check_ln(const LnDesc& d, int mode) {
   VMM_REQUIRE(d.rows > 0 && d.width > 0 && d.width % 4 == 0, "LayerNorm stage: bad shape %d x %d", d.rows, d.width);
   VMM_REQUIRE(d.bias && d.ln_g && d.ln_b, "LayerNorm stage: null parameter");
@@ -1521,8 +1693,22 @@ int ln_forward(int mode, int act, const LnDesc& d, const Op& out, float* mean, f
     VMM_LAUNCHED();
     return 0;
   }
-  if (mode == LN_BIAS && d.width % 512 == 0 && d.width / 16 <= 1024) {   // block of width/16 threads per row
-    lnw_forward_kernel<<<d.rows, d.width / 16, 0, stream>>>(d, act, out, mean, rstd);
+  if (mode == LN_BIAS && d.width % 512 == 0 && d.width / 16 <= 1024 && (reinterpret_cast<uintptr_t>(d.C) & 15) == 0) {
+    // persistent blocks of width/16 threads, rows through a bulk-copy pipeline
+    const int threads = d.width / 16, rowb = d.width * 4;
+    if (threads <= 256) {                                    // 4096-wide (enc2, dec1): 4 slots of 16 KB, 3 blocks per SM
+      const int smem = 4 * rowb;
+      VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&lnw_forward_kernel<256, 4, 3>), smem));
+      lnw_forward_kernel<256, 4, 3><<<std::min(d.rows, device_sm_count() * 3), threads, smem, stream>>>(d, act, out, mean, rstd);
+    } else if (threads <= 768) {                             // 12288-wide (dec2 at M = 12): 3 slots of 48 KB, 1 block per SM
+      const int smem = 3 * rowb;
+      VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&lnw_forward_kernel<768, 3, 1>), smem));
+      lnw_forward_kernel<768, 3, 1><<<std::min(d.rows, device_sm_count()), threads, smem, stream>>>(d, act, out, mean, rstd);
+    } else {
+      const int smem = 3 * rowb;
+      VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&lnw_forward_kernel<1024, 3, 1>), smem));
+      lnw_forward_kernel<1024, 3, 1><<<std::min(d.rows, device_sm_count()), threads, smem, stream>>>(d, act, out, mean, rstd);
+    }
     VMM_LAUNCHED();
     return 0;
   }
@@ -1558,8 +1744,23 @@ int ln_backward_rows(int mode, int act, const LnDesc& d, const float* mean, cons
     VMM_LAUNCHED();
     return 0;
   }
-  if (mode == LN_BIAS && d.width % 512 == 0 && d.width / 16 <= 1024 && dv.n > 0) {
-    lnw_backward_rows_kernel<<<d.rows, d.width / 16, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2, dvh);
+  if (mode == LN_BIAS && d.width % 512 == 0 && d.width / 16 <= 1024 && dv.n > 0 && d.width * 16 <= 200 * 1024 &&
+      ((reinterpret_cast<uintptr_t>(d.C) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0) {
+    const int smem = 2 * 2 * d.width * 4;          // 2 slots x (row of C + row of the incoming gradient)
+    const int threads = d.width / 16;
+    const int per_sm = std::max(1, std::min(2048 / threads, (220 * 1024) / (smem + 1024)));
+    const int blocks = std::min(d.rows, device_sm_count() * per_sm);
+#define VMM_LNWB(MAXT, NY)                                                                                           \
+  {                                                                                                                  \
+    VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&lnw_backward_rows_kernel<MAXT, NY>), smem));                  \
+    lnw_backward_rows_kernel<MAXT, NY><<<blocks, threads, smem, stream>>>(d, act, mean, rstd, d_out, ldd, dv, c1, c2, dvh); \
+  }
+    if (threads <= 768) {
+      if (act == ACT_NONE) VMM_LNWB(768, false) else VMM_LNWB(768, true)
+    } else {
+      if (act == ACT_NONE) VMM_LNWB(1024, false) else VMM_LNWB(1024, true)
+    }
+#undef VMM_LNWB
     VMM_LAUNCHED();
     return 0;
   }
@@ -1604,8 +1805,12 @@ int lnw_backward_fused(int act, const LnDesc& d, const float* mean, const float*
   VMM_REQUIRE(mean && rstd && d_out && ldd % 4 == 0 && d_ln_g && d_ln_b && d_bias, "lnw_backward_fused: null argument");
   VMM_REQUIRE(((reinterpret_cast<uintptr_t>(d_ln_g) | reinterpret_cast<uintptr_t>(d_ln_b) |
                 reinterpret_cast<uintptr_t>(d_bias)) & 15) == 0, "lnw_backward_fused: gradient buffers must be 16-byte aligned");
+  VMM_REQUIRE(((reinterpret_cast<uintptr_t>(d.C) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0 && d.ldc % 4 == 0,
+              "lnw_backward_fused: rows must be 16-byte aligned (bulk copies)");
   const int blocks = std::min(d.rows, device_sm_count());
-  lnw4k_backward_fused_kernel<<<blocks, 512, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dv, d_ln_g, d_ln_b, d_bias, dvh);
+  constexpr int kSmem = LNW4K_STAGES * 2 * 4096 * 4;
+  VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&lnw4k_backward_fused_kernel), kSmem));
+  lnw4k_backward_fused_kernel<<<blocks, 1024, kSmem, stream>>>(d, act, mean, rstd, d_out, ldd, dv, d_ln_g, d_ln_b, d_bias, dvh);
   VMM_LAUNCHED();
   return 0;
 }
@@ -1622,16 +1827,23 @@ int enc1_backward_fused(int act, const LnDesc& d, const float* mean, const float
               "enc1_backward_fused: gradient buffers must be 16-byte aligned");
   const int groups = d.rows / K;
   const int blocks = std::min(groups, device_sm_count() * 2);
-#define VMM_ENC1B(NR)                                                                                                  \
-  enc1_backward_fused_kernel<NR><<<blocks, 256, 0, stream>>>(d, act, mean, rstd, d_out, ldd, dgamma, dxw1, dg1, d_ln_g, \
-                                                             d_ln_b, d_bias, d_w1b3, dg1h)
+  VMM_REQUIRE(d.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(d.xw1) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
+                  (!d.C || (reinterpret_cast<uintptr_t>(d.C) & 15) == 0) && (!dxw1 || (reinterpret_cast<uintptr_t>(dxw1) & 15) == 0),
+              "enc1_backward_fused: rows must be 16-byte aligned (bulk copies)");
+#define VMM_ENC1B(NR, ST)                                                                                              \
+  {                                                                                                                    \
+    constexpr int kSmem = ST * (2 + 2 * NR) * 4096;                                                                    \
+    VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&enc1_backward_fused_kernel<NR, ST>), kSmem));                   \
+    enc1_backward_fused_kernel<NR, ST><<<blocks, 256, kSmem, stream>>>(d, act, mean, rstd, d_out, ldd, dgamma, dxw1, dg1, \
+                                                                       d_ln_g, d_ln_b, d_bias, d_w1b3, dg1h);          \
+  }
   switch (K) {
-    case 1: VMM_ENC1B(1); break;
-    case 2: VMM_ENC1B(2); break;
-    case 3: VMM_ENC1B(3); break;
-    case 4: VMM_ENC1B(4); break;
-    case 5: VMM_ENC1B(5); break;
-    default: VMM_ENC1B(6); break;
+    case 1: VMM_ENC1B(1, 3); break;
+    case 2: VMM_ENC1B(2, 3); break;
+    case 3: VMM_ENC1B(3, 3); break;
+    case 4: VMM_ENC1B(4, 2); break;
+    case 5: VMM_ENC1B(5, 2); break;
+    default: VMM_ENC1B(6, 2); break;
   }
 #undef VMM_ENC1B
   VMM_LAUNCHED();
@@ -1653,20 +1865,19 @@ int gru_backward(int rows, int H, const float* gi, const float* gh, const float*
                  float* d_b_hh, cudaStream_t stream, RowF16 dgih, RowF16 dghh) {
   VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && dh && dgi.n >= 1 && dgh.n >= 1 && dh_prev &&
                   d_b_ih && d_b_hh, "gru_backward: bad argument");
-  if (dgih.p) {                                       // row-oriented variant: also writes the row-scaled fp16 copies
-    VMM_REQUIRE(H <= 1024 && dghh.p && dgih.inv_scale && dghh.inv_scale, "gru_backward: fp16 copies need H <= 1024 and both outputs");
-    const int threads = (H + 31) / 32 * 32;
-    const int rpb = std::max(1, ceil_div(rows, device_sm_count() * (2048 / threads)));
-    gru_backward_rows_kernel<<<ceil_div(rows, rpb), threads, 0, stream>>>(rows, H, rpb, gi, gh, b_ih, b_hh, h_prev, dh, dgi, dgh,
-                                                                         dh_prev, d_b_ih, d_b_hh, dgih, dghh);
-    VMM_LAUNCHED();
-    return 0;
-  }
-  const int col_blocks = ceil_div(H, 256);
-  const int rpb = pick_rows_per_block(rows, col_blocks);
-  dim3 grid(col_blocks, ceil_div(rows, rpb));
-  gru_backward_kernel<<<grid, 256, 0, stream>>>(rows, H, rpb, gi, gh, b_ih, b_hh, h_prev, dh, dgi, dgh, dh_prev, d_b_ih,
-                                                d_b_hh);
+  VMM_REQUIRE(H % 4 == 0, "gru_backward: H must be a multiple of 4");
+  VMM_REQUIRE(!dgih.p || (H <= 1024 && dghh.p && dgih.inv_scale && dghh.inv_scale),
+              "gru_backward: the fp16 copies need H <= 1024 (row maxima span the row) and come in pairs");
+  VMM_REQUIRE(((reinterpret_cast<uintptr_t>(gi) | reinterpret_cast<uintptr_t>(gh) | reinterpret_cast<uintptr_t>(h_prev) |
+                reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(b_ih) | reinterpret_cast<uintptr_t>(b_hh)) & 15) == 0,
+              "gru_backward: operands must be 16-byte aligned");
+  const int tiles = ceil_div(H, 1024), HT = std::min(H, 1024);
+  const int threads = (HT / 4 + 31) / 32 * 32;
+  const int smem = GRU_STAGES * 8 * HT * 4;
+  VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&gru_backward_kernel), smem));
+  const dim3 blocks(std::min(rows, std::max(1, device_sm_count() * 2 / tiles)), tiles);
+  gru_backward_kernel<<<blocks, threads, smem, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, dh, dgi, dgh, dh_prev, d_b_ih,
+                                                        d_b_hh, dgih, dghh);
   VMM_LAUNCHED();
   return 0;
 }
@@ -1795,13 +2006,14 @@ int act_backward(int act, long long n, const float* pre, float* grad, float drop
 int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x, int x_is_bf16, long long ldx,
                 int k_latent, int m_views, float sigma, const float* alpha, const float* beta, const float* kappa,
                 const Planes& dpred, float* colsum, cudaStream_t stream, __half* dpred_h, float* inv_scale,
-                const float* row_dmax, const float* add) {
+                const float* row_dmax, const float* add, float* gmax, float* inv_scale_cols) {
   VMM_REQUIRE(rows > 0 && D > 0 && D % 8 == 0 && delta && alpha && beta, "estep_dpred: bad argument");
+  VMM_REQUIRE(!gmax || (dpred_h && inv_scale_cols), "estep_dpred: the global scale goes with the fp16 copy and its column scales");
   VMM_REQUIRE(!add || (!dpred_h && (reinterpret_cast<uintptr_t>(add) & 15) == 0), "estep_dpred: `add` needs 16-byte alignment and no fp16 copy");
   VMM_REQUIRE(!dpred_h || (!kappa && inv_scale && row_dmax && (reinterpret_cast<uintptr_t>(dpred_h) & 15) == 0),
               "estep_dpred: the row-scaled fp16 copy needs kappa == NULL, a scale buffer and the row maxima of delta");
   VMM_REQUIRE(delta_fmt == VMM_DELTA_F16 || delta_fmt == VMM_DELTA_F32, "estep_dpred: delta_fmt must be fp16 or fp32");
-  VMM_REQUIRE(dpred.n >= 1 && dpred.n <= 3 && dpred.fmt == VMM_FMT_BF16, "estep_dpred: dpred must be 1..3 bf16 planes");
+  VMM_REQUIRE((dpred.n >= 1 || gmax) && dpred.n <= 3 && dpred.fmt == VMM_FMT_BF16, "estep_dpred: dpred must be 1..3 bf16 planes");
   for (int i = 0; i < dpred.n; ++i)
     VMM_REQUIRE(dpred.p[i] && (reinterpret_cast<uintptr_t>(dpred.p[i]) & 15) == 0, "dpred planes must be 16-byte aligned");
   VMM_REQUIRE((reinterpret_cast<uintptr_t>(delta) & 15) == 0, "delta must be 16-byte aligned");
@@ -1820,8 +2032,15 @@ int estep_dpred(int rows, int D, const void* delta, int delta_fmt, const void* x
 #define VMM_DPRED(DT, N)                                                                                            \
   estep_dpred_kernel<DT, N><<<grid, 256, 0, stream>>>(rows, D, rpb, static_cast<const DT*>(delta), alpha, beta, kappa, x,  \
                                                       x_is_bf16, ldx, km, m_views, exp_scale, dpred.p[0], dpred.p[1],   \
-                                                      dpred.p[2], colsum, dpred_h, inv_scale, row_dmax, sigma, add)
-  if (delta_fmt == VMM_DELTA_F16) {
+                                                      dpred.p[2], colsum, dpred_h, inv_scale, row_dmax, sigma, add, gmax,    \
+                                                      inv_scale_cols)
+  if (gmax) {                                          // global scale: bound first, then the fp16-only pass
+    VMM_CHECK_CUDA(cudaMemsetAsync(gmax, 0, sizeof(float), stream));
+    dpred_bound_kernel<<<ceil_div(rows, 256), 256, 0, stream>>>(rows, sigma, alpha, beta, row_dmax, reinterpret_cast<unsigned*>(gmax));
+    VMM_LAUNCHED();
+    if (delta_fmt == VMM_DELTA_F16) VMM_DPRED(__half, 0);
+    else VMM_DPRED(float, 0);
+  } else if (delta_fmt == VMM_DELTA_F16) {
     if (dpred.n == 1) VMM_DPRED(__half, 1);
     else if (dpred.n == 2) VMM_DPRED(__half, 2);
     else VMM_DPRED(__half, 3);

@@ -264,9 +264,9 @@ def run_em(p: Params, x: torch.Tensor, k: int, iters: int, sigma: float = 0.1,
         g0 = gamma0
     if gamma_prior is not None:
         gp = gamma_prior
-    dt = x.dtype
-    state = (h.to(dt), pred.to(dt), g0.to(dt))
-    gp = gp.to(dt)
+    dt, dev = x.dtype, x.device          # dev != cpu: bench.py's eager-GPU comparator; the state is built on the host and
+    state = (h.to(dev, dt), pred.to(dev, dt), g0.to(dev, dt))   # copied every step, as the reference does (train_nem.py:217)
+    gp = gp.to(dev, dt)
     xin = x.unsqueeze(1)
     hist = []
     for it in range(iters):

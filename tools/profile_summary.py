@@ -64,7 +64,9 @@ else:
     rd = sum(m.get("dram__bytes_read.sum", 0.0) for _, m in last)
     wr = sum(m.get("dram__bytes_write.sum", 0.0) for _, m in last)
     us = sum(m.get("gpu__time_duration.sum", 0.0) for _, m in last)
-    out = dict(precision=prec, batch=batch, launches_per_step=n, dram_bytes_per_step=rd + wr, dram_read_bytes=rd,
+    sys.path.insert(0, ROOT)
+    import bench
+    out = dict(precision=prec, batch=batch, source_hash=bench.kernel_source_hash(), launches_per_step=n, dram_bytes_per_step=rd + wr, dram_read_bytes=rd,
                dram_write_bytes=wr, kernel_us_under_ncu=us,
                source="ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none "
                       "-k regex:gemm_tcgen05 python tools/gemm_breakdown.py %d %s (last step of the log)" % (batch, prec))
