@@ -204,6 +204,62 @@ def _weight_cache(module) -> _WeightCache:
     return wc
 
 
+class GradArena:
+    """One flat fp32 buffer that a module's hand-written backward writes its parameter gradients into (instead of one
+    zeros_like per parameter): the gradients autograd hands to the parameters are then VIEWS of one contiguous buffer,
+    which dist.GradBucket all-reduces in place - no packing copy.  Attached to a module by GradBucket; used only when
+    every parameter's .grad is None (optimizer.zero_grad(set_to_none=True), the default), because accumulating into an
+    existing .grad that aliases the arena would add the buffer to itself."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        self.sizes = [p.numel() for p in self.params]
+        self.flat = None
+
+    def views_nozero(self):
+        out, off = [], 0
+        for p, k in zip(self.params, self.sizes):
+            out.append(self.flat[off:off + k].view(p.shape))
+            off += k
+        return out
+
+    def views(self):
+        dev = self.params[0].device
+        n = sum(self.sizes)
+        if self.flat is None or self.flat.device != dev or self.flat.numel() != n:
+            self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat.zero_()
+        out, off = [], 0
+        for p, k in zip(self.params, self.sizes):
+            out.append(self.flat[off:off + k].view(p.shape))
+            off += k
+        return out
+
+
+def _grad_buffers(module, params):
+    """-> (zeroed gradient buffers for `params`, direct).  direct: the buffers are views of the module's GradArena (one
+    is attached and every .grad is None); the backward then installs them as the parameters' .grad itself and returns
+    None to autograd, so that .grad provably aliases the arena (autograd may clone a returned gradient)."""
+    arena = module.__dict__.get("_vmm_grad_arena")
+    if (arena is not None and len(arena.params) == len(params) and all(a is p for a, p in zip(arena.params, params))
+            and all(p.grad is None for p in params)):
+        return arena.views(), True
+    return [torch.zeros_like(p) for p in params], False
+
+
+def _install(params, grads):
+    for p, g in zip(params, grads):
+        if p.requires_grad:
+            p.grad = g
+    return [None] * len(grads)
+
+
+def _after_backward(module):
+    cb = module.__dict__.get("_vmm_after_backward")
+    if cb is not None:
+        cb()
+
+
 class _EMFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, T, training, flags, x, gamma0, prior, *params):
@@ -237,7 +293,8 @@ class _EMFunction(torch.autograd.Function):
         dev = x.device
         with torch.cuda.device(dev):
             scratch = torch.empty(_bytes(lib().vmm_em_scratch_bytes, cfg), dtype=torch.uint8, device=dev)
-            grads = [torch.zeros_like(p) for p in params]
+            live = em_param_tensors(ctx.module)
+            grads, direct = _grad_buffers(ctx.module, live)
             gp, pp = _pointers(grads), _pointers(params)
             d_h = d_h.contiguous().float() if d_h is not None else None
             d_gamma = d_gamma.contiguous().float() if d_gamma is not None else None
@@ -246,6 +303,9 @@ class _EMFunction(torch.autograd.Function):
             check(lib().vmm_em_backward(C.byref(cfg), C.byref(pp), ptr(weights), ptr(x), ptr(gamma0), ptr(prior), ptr(ws),
                                         ptr(scratch), ptr(d_h), ptr(d_gamma), ptr(d_loss), C.byref(gp), stream_ptr()))
         _weight_cache(ctx.module).invalidate()          # an optimizer step follows: the planes are stale from here on
+        if direct:
+            grads = _install(live, grads)
+        _after_backward(ctx.module)
         return (None, None, None, None, None, None, None, *grads)
 
 
@@ -444,7 +504,8 @@ class _HeadFunction(torch.autograd.Function):
         cfg, dev = ctx.cfg, h.device
         with torch.cuda.device(dev):
             scratch = torch.empty(_bytes(lib().vmm_head_scratch_bytes, cfg), dtype=torch.uint8, device=dev)
-            grads = [torch.zeros_like(p) for p in params]
+            live = head_param_tensors(ctx.module)
+            grads, direct = _grad_buffers(ctx.module, live)
             gp, pp = _head_pointers(grads), _head_pointers(params)
             d_h = torch.empty_like(h)
             d_out = d_out.contiguous().float()
@@ -452,6 +513,9 @@ class _HeadFunction(torch.autograd.Function):
                                           None if ctx.want_descriptor else ptr(d_out),
                                           ptr(d_out) if ctx.want_descriptor else None, C.byref(gp), ptr(d_h), stream_ptr()))
         ctx.module.__dict__["_vmm_weight_cache"].invalidate()
+        if direct:
+            grads = _install(live, grads)
+        _after_backward(ctx.module)
         return (None, None, None, d_h, None, *grads)
 
 

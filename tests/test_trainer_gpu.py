@@ -95,3 +95,78 @@ def test_training_updates_the_prepared_weights_and_learns():
             prev = cur
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_trainer_trajectory_matches_oracle_adam(tmp_path):
+    """f1 as a trajectory: ModelNetTrainer.train_nem_mvcnn (fp32 preset, eval-mode modules so that dropout is off)
+    on a tiny in-memory loader for 3 optimizer steps against the oracle's train_step + torch.optim.Adam on the CPU
+    with the same weights, data and hyper-parameters: the logged losses of every step within 1e-4, the parameters after
+    the last step close to the oracle's in relative L2 of the update.  Also pins the
+    -if_total_loss 1 scalar (closs + mean of the T NEM losses, Trainer.py:203)."""
+    from oracle import nem_oracle as O
+    from helpers import params_of
+    from multi_view_sort_b200 import NEM, Multi_View_Net
+    from multi_view_sort_b200.trainer import ModelNetTrainer
+    import torch.nn as nn
+    cfg = dict(B=6, K=2, M=12, D=512, H=256, T=3, sigma=0.1, nclasses=10)
+    for total_loss in (0, 1):
+        torch.manual_seed(10)
+        nem = NEM(nclasses=cfg["nclasses"], view_num=cfg["M"], k=cfg["K"], input_dim=cfg["D"], rnn_hidden_size=cfg["H"],
+                  iter_num=cfg["T"], init_type="bin_uniform", gamma_prior_loss=1, e_sigma=cfg["sigma"], if_total_loss=total_loss,
+                  precision="fp32")
+        head = Multi_View_Net(None, "vggm", nclasses=cfg["nclasses"], k=cfg["K"], rnn_hidden_size=cfg["H"], precision="fp32")
+        pn, ph = params_of(nem), params_of(head)
+        start = {k: v.detach().clone() for k, v in list(pn.items()) + [("head." + k, v) for k, v in ph.items()]}
+        batches = []
+        for i in range(3):
+            x, y = O.make_inputs(cfg["B"], cfg["M"], cfg["D"], cfg["nclasses"], seed=20 + i, scale=0.5)
+            batches.append((y, x, ["obj"] * cfg["B"]))
+        # ---- oracle trajectory (CPU, torch autograd + Adam) ----
+        opt_ref = torch.optim.Adam(list(pn.values()) + list(ph.values()), lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999))
+        ref_losses = []
+        for y, x, _ in batches:
+            opt_ref.zero_grad()
+            losses = []
+            r = O.run_em(pn, x, cfg["K"], cfg["T"], cfg["sigma"], "bin_uniform", 1, 0, losses=losses)
+            out = O.head_forward(ph, r["h"], r["gamma"], cfg["K"], 1, 0)
+            closs = torch.nn.functional.cross_entropy(out, y)
+            loss = closs + (r["nem_loss"] if total_loss == 0 else torch.stack([l[0] for l in losses]).detach().mean())
+            loss.backward()
+            opt_ref.step()
+            ref_losses.append((loss.item(), closs.item(), r["nem_loss"].item()))
+        # ---- this package's trainer ----
+        # the trainer calls .train(); parity is defined with dropout off
+        nem.train = lambda mode=True: nem
+        head.train = lambda mode=True: head
+        nn.Module.eval(nem); nn.Module.eval(head)
+        nem.training = head.training = False
+        opt = torch.optim.Adam(list(nem.parameters()) + list(head.parameters()), lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999))
+        log_dir = str(tmp_path / f"traj{total_loss}")
+        os.makedirs(log_dir)
+        trainer = ModelNetTrainer((nem, head), batches, [], opt, nn.CrossEntropyLoss(), None, log_dir, num_views=cfg["M"],
+                                  class_num=cfg["nclasses"])
+        cwd = os.getcwd()
+        os.chdir(tmp_path)
+        try:
+            trainer.train_nem_mvcnn(1)
+        finally:
+            os.chdir(cwd)
+        sc = trainer.writer.scalars if trainer.writer else None
+        assert sc is not None
+        got = list(zip([v[2] for v in sc["train/train_loss"]], [v[2] for v in sc["train/c_loss"]], [v[2] for v in sc["train/nem_loss"]]))
+        assert len(got) == 3
+        for step, (a, b) in enumerate(zip(got, ref_losses)):
+            for j in range(3):
+                assert abs(a[j] - b[j]) < 1e-4 * abs(b[j]), (total_loss, step, j, a, b)
+        mine = {k: v.detach().cpu() for k, v in nem.state_dict().items()}
+        mine.update({"head." + k: v.detach().cpu() for k, v in head.state_dict().items()})
+        ref_end = dict(pn)
+        ref_end.update({"head." + k: v for k, v in ph.items()})
+        for k, v in ref_end.items():
+            moved = (v.detach() - start[k]).norm().item()
+            if moved == 0:
+                continue
+            # Adam's first updates are ~lr * sign(g): an entry whose gradient is within rounding of zero may move the
+            # other way, so the parameters are compared in relative L2 of the update, not entry-wise
+            err = (mine[k] - v.detach()).norm().item() / moved
+            assert err < 2e-2, (total_loss, k, err)
