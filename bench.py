@@ -348,7 +348,7 @@ def measure_preset(precision, B, args, dev, rank, world, local, profile_gemm=Tru
     nem, head = build_models(precision, dev)
     params = list(nem.parameters()) + list(head.parameters())
     opt = torch.optim.Adam(params, lr=5e-5, weight_decay=1e-4, fused=True)
-    bucket = GradBucket(params)
+    bucket = GradBucket(params).attach(nem, head)       # backward writes into flat arenas; head arena reduced under the EM backward
 
     # synthetic features, generated once on the host (pinned) with a per-rank seed
     g = torch.Generator().manual_seed(10 + rank)

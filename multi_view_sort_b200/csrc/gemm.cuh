@@ -91,16 +91,22 @@ struct alignas(64) GemmParams {
   void* delta_out;           // ESTEP with OPL 2 (fp16) / 3 (fp32): delta = x - pred, [M, ldo]
 };
 
-template <int BN, int NCTA = 1>
+// Staging tiles per epilogue warp: the E-step epilogue that writes an fp32 delta keeps the feature tile and the delta
+// tile apart (the TMA store of chunk c then reads its tile while chunk c+1 is staged and computed) and pays for the
+// second tile with one pipeline stage.
+__host__ __device__ constexpr int epi_bufs(int epi, int opl) { return (epi == 2 /* EPI_ESTEP */ && opl == 3) ? 2 : 1; }
+
+template <int BN, int NCTA = 1, int EPI_BUFS = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;              // this CTA's 128 rows of A
   static constexpr int B_ROWS = BN / NCTA;                 // N rows of the B tile held by this CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB, or 32 KB per CTA of a pair
-  static constexpr int STAGES = (196608 / STAGE_BYTES);    // 4, or 6 for a pair
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_BYTES * EPI_BUFS;
+  static constexpr int STAGES = (196608 + EPI_WARPS * EPI_STAGE_BYTES - EPI_BYTES) / STAGE_BYTES;   // 4 (3), or 6 (5) for a pair
   static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256: power of two
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
 };
 
 // One work item = one output tile x one contiguous range of accumulation chains [c0, c1).
@@ -156,6 +162,7 @@ __device__ __forceinline__ int st_slot(int r, int c4) { return r * 8 + (c4 ^ (r 
 template <typename XT>
 struct XRegs {
   uint4 v[sizeof(XT) == 4 ? 8 : 4];
+  float4 b[sizeof(XT) == 4 ? 1 : 2];   // b3 of the columns this lane stages (the same columns in every row it fetches)
 };
 
 // Feature-row pointers of the rows a lane fetches (constant over the chunks of one tile; the integer
@@ -176,7 +183,7 @@ __device__ __forceinline__ void x_rows(const GemmParams& p, XRows<XT>& xr, int r
     if (grow < p.M) xr.p[j] = x + (static_cast<long long>(grow / p.km) * p.mv + grow % p.mv) * p.ldx + (lane % LPR) * EPL;
   }
 }
-template <typename XT>
+template <typename XT, bool kBias>
 __device__ __forceinline__ void x_fetch(const GemmParams& p, XRegs<XT>& xr, const XRows<XT>& rows, int col0, int lane) {
   constexpr int NI = sizeof(XT) == 4 ? 8 : 4;
   constexpr int RPI = 32 / NI, LPR = 32 / RPI, EPL = 16 / sizeof(XT);
@@ -186,6 +193,14 @@ __device__ __forceinline__ void x_fetch(const GemmParams& p, XRegs<XT>& xr, cons
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (rows.p[j] && col_ok) v = __ldg(reinterpret_cast<const uint4*>(rows.p[j] + col0));
     xr.v[j] = v;
+  }
+  if constexpr (kBias) {
+#pragma unroll
+    for (int i = 0; i < EPL / 4; ++i) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + (lane % LPR) * EPL + i * 4));
+      xr.b[i] = b;
+    }
   }
 }
 
@@ -208,6 +223,71 @@ __device__ __forceinline__ void x_stage(const XRegs<XT>& xr, float4* st, int lan
       st[st_slot(r, c4 + 1)] = make_float4(bf16_bits_to_float(v.z & 0xffffu), bf16_bits_to_float(v.z >> 16),
                                            bf16_bits_to_float(v.w & 0xffffu), bf16_bits_to_float(v.w >> 16));
     }
+  }
+}
+
+// The same with b3 folded in: the staged tile holds x - b3, so that the E-step's delta = (x - b3) - acc needs no bias in
+// the row-per-lane layout (where every lane would need all 32 bias values of the chunk).
+template <typename XT>
+__device__ __forceinline__ void x_stage_sub(const XRegs<XT>& xr, float4* st, int lane) {
+  if constexpr (sizeof(XT) == 4) {
+    const float4 b = xr.b[0];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = j * 4 + (lane >> 3), c4 = lane & 7;
+      st[st_slot(r, c4)] = make_float4(__uint_as_float(xr.v[j].x) - b.x, __uint_as_float(xr.v[j].y) - b.y,
+                                       __uint_as_float(xr.v[j].z) - b.z, __uint_as_float(xr.v[j].w) - b.w);
+    }
+  } else {
+    const float4 b0 = xr.b[0], b1 = xr.b[1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = j * 8 + (lane >> 2), c4 = (lane & 3) * 2;
+      const uint4 v = xr.v[j];
+      st[st_slot(r, c4)] = make_float4(bf16_bits_to_float(v.x & 0xffffu) - b0.x, bf16_bits_to_float(v.x >> 16) - b0.y,
+                                       bf16_bits_to_float(v.y & 0xffffu) - b0.z, bf16_bits_to_float(v.y >> 16) - b0.w);
+      st[st_slot(r, c4 + 1)] = make_float4(bf16_bits_to_float(v.z & 0xffffu) - b1.x, bf16_bits_to_float(v.z >> 16) - b1.y,
+                                           bf16_bits_to_float(v.w & 0xffffu) - b1.z, bf16_bits_to_float(v.w >> 16) - b1.w);
+    }
+  }
+}
+
+// E-step chunk, fast form (all 32 columns inside N, no loss sums - every iteration but the last): per element one
+// subtraction, two multiplications, one ex2 and one addition (+ one max with kDmax); delta goes straight from the
+// registers into the warp's delta tile, which one TMA store writes while the warp moves on.  kSave: 0 none, 2 fp32.
+template <int kSave, bool kDmax>
+__device__ __forceinline__ void estep_fast_chunk(const GemmParams& p, const uint32_t (&v)[32], const float4* stx, float4* sto,
+                                                 int lane, int row0, int col0, bool& st_busy, float& sum_e, float& dmax) {
+  if constexpr (kSave == 2) {
+    if (st_busy) {                                   // the previous chunk's TMA store has read the delta tile
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
+  }
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 xv = stx[st_slot(lane, j)];
+    const float d0 = xv.x - __uint_as_float(v[4 * j]), d1 = xv.y - __uint_as_float(v[4 * j + 1]);
+    const float d2 = xv.z - __uint_as_float(v[4 * j + 2]), d3 = xv.w - __uint_as_float(v[4 * j + 3]);
+    s[0] += ex2_approx(d0 * d0 * p.exp_scale);
+    s[1] += ex2_approx(d1 * d1 * p.exp_scale);
+    s[2] += ex2_approx(d2 * d2 * p.exp_scale);
+    s[3] += ex2_approx(d3 * d3 * p.exp_scale);
+    if constexpr (kDmax) dmax = fmaxf(fmaxf(dmax, fmaxf(fabsf(d0), fabsf(d1))), fmaxf(fabsf(d2), fabsf(d3)));
+    if constexpr (kSave == 2) sto[st_slot(lane, j)] = make_float4(d0, d1, d2, d3);
+  }
+  sum_e += (s[0] + s[1]) + (s[2] + s[3]);
+  if constexpr (kSave == 2) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&p.tma_out, sto, col0, row0);
+      tma_store_commit();
+    }
+    st_busy = true;
+  } else {
+    __syncwarp();                                    // every lane has read its row before the tile is staged again
   }
 }
 
