@@ -124,7 +124,7 @@ static std::atomic<int> g_force_ncta{0};   // 0 = choose (pairs whenever M > 128
 
 template <int BN, bool A_MN, bool B_MN, int EPI, typename XT, int OPL, int NCTA>
 static int launch_one(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, NCTA>;
+  using Cfg = GemmCfg<BN, NCTA, epi_bufs(EPI, OPL)>;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, XT, OPL, NCTA>;
   // the dynamic shared-memory opt-in is a per-device attribute of the function: set it once per (kernel, device)
   static std::atomic<unsigned long long> opted_in{0ull};

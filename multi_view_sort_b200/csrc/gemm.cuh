@@ -91,10 +91,11 @@ struct alignas(64) GemmParams {
   void* delta_out;           // ESTEP with OPL 2 (fp16) / 3 (fp32): delta = x - pred, [M, ldo]
 };
 
-// Staging tiles per epilogue warp: the E-step epilogue that writes an fp32 delta keeps the feature tile and the delta
-// tile apart (the TMA store of chunk c then reads its tile while chunk c+1 is staged and computed) and pays for the
-// second tile with one pipeline stage.
-__host__ __device__ constexpr int epi_bufs(int epi, int opl) { return (epi == 2 /* EPI_ESTEP */ && opl == 3) ? 2 : 1; }
+// Staging tiles per epilogue warp: the E-step epilogue that writes an fp32 delta keeps the feature tile apart from TWO
+// delta tiles used in turn (a TMA store queues behind the producer's operand loads in the SM's TMA unit: measured, a warp
+// that reuses its only tile waits ~a chunk's worth of time for the engine to have read it) and pays with two pipeline
+// stages (4 x 32 KB for a pair: 2048 MMA cycles of operands in flight, still above the L2 latency).
+__host__ __device__ constexpr int epi_bufs(int epi, int opl) { return (epi == 2 /* EPI_ESTEP */ && opl == 3) ? 3 : 1; }
 
 template <int BN, int NCTA = 1, int EPI_BUFS = 1>
 struct GemmCfg {
@@ -252,18 +253,26 @@ __device__ __forceinline__ void x_stage_sub(const XRegs<XT>& xr, float4* st, int
   }
 }
 
+// Before delta tile `cur` (0 / 1) of this warp is written again: the TMA store that last read it must be done reading.
+// The two tiles are used in turn, so that store is normally the one before the most recent (`last` = the tile of the most
+// recent store, -1 none); after a chunk clipped away at the N edge it can be the most recent one.
+__device__ __forceinline__ void delta_tile_acquire(int cur, int last, int lane) {
+  if (last < 0) return;
+  if (lane == 0) {
+    if (last == cur) tma_store_wait_read();
+    else tma_store_wait_read_keep1();
+  }
+  __syncwarp();
+}
+
 // E-step chunk, fast form (all 32 columns inside N, no loss sums - every iteration but the last): per element one
 // subtraction, two multiplications, one ex2 and one addition (+ one max with kDmax); delta goes straight from the
 // registers into the warp's delta tile, which one TMA store writes while the warp moves on.  kSave: 0 none, 2 fp32.
 template <int kSave, bool kDmax>
 __device__ __forceinline__ void estep_fast_chunk(const GemmParams& p, const uint32_t (&v)[32], const float4* stx, float4* sto,
-                                                 int lane, int row0, int col0, bool& st_busy, float& sum_e, float& dmax) {
-  if constexpr (kSave == 2) {
-    if (st_busy) {                                   // the previous chunk's TMA store has read the delta tile
-      if (lane == 0) tma_store_wait_read();
-      __syncwarp();
-    }
-  }
+                                                 int lane, int row0, int col0, int cur_sto, int& last_sto, float& sum_e,
+                                                 float& dmax) {
+  if constexpr (kSave == 2) delta_tile_acquire(cur_sto, last_sto, lane);
   float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -285,7 +294,7 @@ __device__ __forceinline__ void estep_fast_chunk(const GemmParams& p, const uint
       tma_store_2d(&p.tma_out, sto, col0, row0);
       tma_store_commit();
     }
-    st_busy = true;
+    last_sto = cur_sto;
   } else {
     __syncwarp();                                    // every lane has read its row before the tile is staged again
   }
@@ -392,7 +401,7 @@ __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint3
 
 template <int BN, bool A_MN, bool B_MN, int EPI, typename XT, int OPL, int NCTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, NCTA>;
+  using Cfg = GemmCfg<BN, NCTA, epi_bufs(EPI, OPL)>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool kFused = (EPI == EPI_ESTEP || EPI == EPI_EBWD);
   constexpr int kSave = (EPI == EPI_ESTEP) ? OPL - 1 : 0;     // 0: no delta output, 1: fp16, 2: fp32
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   // round trip, which makes the compiler lose the address space and emit generic LD/ST for all staging traffic
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * EPI_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -554,11 +563,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int ew = warp - 2;
     const int lane_grp = warp & 3;
     const int col_half = ew >> 2;
-    float4* st = reinterpret_cast<float4*>(epi_smem + ew * EPI_STAGE_BYTES);
+    float4* st = reinterpret_cast<float4*>(epi_smem + ew * EPI_STAGE_BYTES);      // feature tile / the only tile
+    // delta tiles (fp32-delta E-step only: two per warp, used in turn; otherwise both alias st)
+    float4* sto0 = reinterpret_cast<float4*>(epi_smem + (Cfg::EPI_BYTES >= 2 * EPI_WARPS * EPI_STAGE_BYTES ? EPI_WARPS * EPI_STAGE_BYTES : 0) + ew * EPI_STAGE_BYTES);
+    float4* sto1 = reinterpret_cast<float4*>(epi_smem + (Cfg::EPI_BYTES >= 3 * EPI_WARPS * EPI_STAGE_BYTES ? 2 * EPI_WARPS * EPI_STAGE_BYTES : 0) + ew * EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
     bool st_busy = false;                      // a TMA store of this warp's staging tile may still be reading it
+    int last_sto = -1;                         // fp32-delta E-step: delta tile (0 / 1) of the most recent TMA store, -1 none
     const uint32_t tempty0 = NCTA == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;   // the leader's barriers
+    constexpr bool kXBias = (EPI == EPI_ESTEP) && kSave != 1;    // the fast E-step chunk stages x - b3
+    constexpr int XPF = sizeof(XT) == 2 ? 2 : 1;                 // feature chunks in flight ahead of the one being processed
     for (int work = worker; work < total_work; work += nworkers) {
       const WorkItem w = decode_work(p, work, NCTA, rank);
       const int row0 = w.m_blk * BM + lane_grp * 32;                 // first row of this warp
@@ -578,12 +593,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           if (p.row_kappa) kappa = p.row_kappa[grow];
         }
       }
-      XRegs<XT> xr;
+      XRegs<XT> xa, xb;
       XRows<XT> xrows;
       float4 mybias = make_float4(0.f, 0.f, 0.f, 0.f);               // b3 of this warp's 128 columns, 4 per lane
       if constexpr (kFused) {
         x_rows<XT>(p, xrows, row0, lane);
-        x_fetch<XT>(p, xr, xrows, nbase, lane);                      // overlaps the wait for the MMAs
+        x_fetch<XT, kXBias>(p, xa, xrows, nbase, lane);              // overlaps the wait for the MMAs
+        if constexpr (XPF == 2) x_fetch<XT, kXBias>(p, xb, xrows, nbase + 32, lane);
         if (nbase + lane * 4 < p.N) mybias = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + lane * 4));
       }
       const bool want_sq = kFused && (EPI == EPI_ESTEP) && p.part_sq != nullptr;   // last iteration only
@@ -606,16 +622,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           if constexpr (!kFused) {
             epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0, st_busy, groups_per_chain);
           } else {
-            if constexpr (kSave == 2) {
-              if (st_busy) {
-                if (lane == 0) tma_store_wait_read();
-                __syncwarp();
-                st_busy = false;
-              }
-            }
-            x_stage<XT>(xr, st, lane);
-            if (c + 1 < NCH) x_fetch<XT>(p, xr, xrows, col0 + 32, lane);
+            XRegs<XT>& xc = (XPF == 2 && (c & 1)) ? xb : xa;
+            float4* sto = (c & 1) ? sto1 : sto0;
+            bool fast = false;                                       // warp-uniform
+            if constexpr (kXBias) fast = (col0 + 32 <= p.N) && !want_sq && !(p.part_pp != nullptr);
+            if (fast) x_stage_sub<XT>(xc, st, lane);
+            else x_stage<XT>(xc, st, lane);
+            if (c + XPF < NCH) x_fetch<XT, kXBias>(p, xc, xrows, col0 + 32 * XPF, lane);
             __syncwarp();
+            if (fast) {
+              if constexpr (kXBias) {
+                if (want_dmax) estep_fast_chunk<kSave, true>(p, v, st, sto, lane, row0, col0, c & 1, last_sto, sum_e, dmax);
+                else estep_fast_chunk<kSave, false>(p, v, st, sto, lane, row0, col0, c & 1, last_sto, sum_e, dmax);
+              }
+            } else {
             float out[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -668,16 +688,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             } else if constexpr (kSave == 2) {
               // fp32 delta: the swizzled staging tile IS a SWIZZLE_128B box - one TMA store writes it (clipped at the
               // tensor's edges) while the warp goes on; the tile is reused only after the TMA engine has read it
+              delta_tile_acquire(c & 1, last_sto, lane);
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                st[st_slot(lane, j)] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+                sto[st_slot(lane, j)] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
-                tma_store_2d(&p.tma_out, st, col0, row0);
+                tma_store_2d(&p.tma_out, sto, col0, row0);
                 tma_store_commit();
               }
-              st_busy = true;
+              last_sto = c & 1;
             }
             if constexpr (EPI == EPI_EBWD) {
               if (p.colsum) {
@@ -721,6 +742,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 __syncwarp();
               }
             }
+            }   // slow path
           }
         }
       }

@@ -86,6 +86,8 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent group have been read out of shared memory (two staging tiles used in turn)
+__device__ __forceinline__ void tma_store_wait_read_keep1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // all but the `keep` (0..3) most recent groups have completed (their global writes are performed)
 __device__ __forceinline__ void tma_store_wait_keep(int keep) {
   switch (keep) {
