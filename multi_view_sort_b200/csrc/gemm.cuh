@@ -91,11 +91,12 @@ struct alignas(64) GemmParams {
   void* delta_out;           // ESTEP with OPL 2 (fp16) / 3 (fp32): delta = x - pred, [M, ldo]
 };
 
-// Staging tiles per epilogue warp: the E-step epilogue that writes an fp32 delta keeps the feature tile apart from TWO
-// delta tiles used in turn (a TMA store queues behind the producer's operand loads in the SM's TMA unit: measured, a warp
-// that reuses its only tile waits ~a chunk's worth of time for the engine to have read it) and pays with two pipeline
-// stages (4 x 32 KB for a pair: 2048 MMA cycles of operands in flight, still above the L2 latency).
-__host__ __device__ constexpr int epi_bufs(int epi, int opl) { return (epi == 2 /* EPI_ESTEP */ && opl == 3) ? 3 : 1; }
+// Staging tiles per epilogue warp: the E-step epilogue that writes an fp32 delta keeps the feature tile apart from the
+// delta tile (the TMA store of chunk c reads its tile while chunk c+1 is staged) and pays with one pipeline stage
+// (5 x 32 KB for a pair).  A third tile (two delta tiles used in turn, 4 stages) measured no better: 1.53 vs 1.50 ms
+// for the B = 4096 launch - the epilogue's cost is its shared-memory traffic (16 KB per 32x32 chunk against the 32 KB
+// per k-block the tensor core reads), not the wait for the TMA engine.  EPI_BUFS = 3 still works (delta_tile_acquire).
+__host__ __device__ constexpr int epi_bufs(int epi, int opl) { return (epi == 2 /* EPI_ESTEP */ && opl == 3) ? 2 : 1; }
 
 template <int BN, int NCTA = 1, int EPI_BUFS = 1>
 struct GemmCfg {
@@ -564,9 +565,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int lane_grp = warp & 3;
     const int col_half = ew >> 2;
     float4* st = reinterpret_cast<float4*>(epi_smem + ew * EPI_STAGE_BYTES);      // feature tile / the only tile
-    // delta tiles (fp32-delta E-step only: two per warp, used in turn; otherwise both alias st)
-    float4* sto0 = reinterpret_cast<float4*>(epi_smem + (Cfg::EPI_BYTES >= 2 * EPI_WARPS * EPI_STAGE_BYTES ? EPI_WARPS * EPI_STAGE_BYTES : 0) + ew * EPI_STAGE_BYTES);
-    float4* sto1 = reinterpret_cast<float4*>(epi_smem + (Cfg::EPI_BYTES >= 3 * EPI_WARPS * EPI_STAGE_BYTES ? 2 * EPI_WARPS * EPI_STAGE_BYTES : 0) + ew * EPI_STAGE_BYTES);
+    // delta tiles (fp32-delta E-step only; with a single tile per warp everything aliases st)
+    constexpr int kEpiBufs = Cfg::EPI_BYTES / (EPI_WARPS * EPI_STAGE_BYTES);
+    float4* sto0 = reinterpret_cast<float4*>(epi_smem + (kEpiBufs >= 2 ? EPI_WARPS * EPI_STAGE_BYTES : 0) + ew * EPI_STAGE_BYTES);
+    float4* sto1 = kEpiBufs >= 3 ? reinterpret_cast<float4*>(epi_smem + 2 * EPI_WARPS * EPI_STAGE_BYTES + ew * EPI_STAGE_BYTES) : sto0;
     int acc = 0;
     uint32_t acc_phase = 0;
     bool st_busy = false;                      // a TMA store of this warp's staging tile may still be reading it
@@ -623,7 +625,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0, st_busy, groups_per_chain);
           } else {
             XRegs<XT>& xc = (XPF == 2 && (c & 1)) ? xb : xa;
-            float4* sto = (c & 1) ? sto1 : sto0;
+            const int csto = kEpiBufs >= 3 ? (c & 1) : 0;          // delta tile of this chunk
+            float4* sto = csto ? sto1 : sto0;
             bool fast = false;                                       // warp-uniform
             if constexpr (kXBias) fast = (col0 + 32 <= p.N) && !want_sq && !(p.part_pp != nullptr);
             if (fast) x_stage_sub<XT>(xc, st, lane);
@@ -632,8 +635,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             __syncwarp();
             if (fast) {
               if constexpr (kXBias) {
-                if (want_dmax) estep_fast_chunk<kSave, true>(p, v, st, sto, lane, row0, col0, c & 1, last_sto, sum_e, dmax);
-                else estep_fast_chunk<kSave, false>(p, v, st, sto, lane, row0, col0, c & 1, last_sto, sum_e, dmax);
+                if (want_dmax) estep_fast_chunk<kSave, true>(p, v, st, sto, lane, row0, col0, csto, last_sto, sum_e, dmax);
+                else estep_fast_chunk<kSave, false>(p, v, st, sto, lane, row0, col0, csto, last_sto, sum_e, dmax);
               }
             } else {
             float out[32];
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             } else if constexpr (kSave == 2) {
               // fp32 delta: the swizzled staging tile IS a SWIZZLE_128B box - one TMA store writes it (clipped at the
               // tensor's edges) while the warp goes on; the tile is reused only after the TMA engine has read it
-              delta_tile_acquire(c & 1, last_sto, lane);
+              delta_tile_acquire(csto, last_sto, lane);
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 sto[st_slot(lane, j)] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
@@ -698,7 +701,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 tma_store_2d(&p.tma_out, sto, col0, row0);
                 tma_store_commit();
               }
-              last_sto = c & 1;
+              last_sto = csto;
             }
             if constexpr (EPI == EPI_EBWD) {
               if (p.colsum) {

@@ -15,9 +15,15 @@ from multi_view_sort_b200.functional import cross_entropy                  # noq
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    backend = os.environ.get("VMM_TEST_BACKEND", "nccl")
+    if backend != "nccl":
+        local = 0                                                        # single-GPU box: both ranks compute on cuda:0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group(backend)
     cfg = dict(K=2, M=12, D=512, H=256, T=3, sigma=0.1, nclasses=10)
     worst = 0.0
     for B, attach in ((8, True), (8, False), (7, True)):                 # equal shards (both bucket paths), ragged shards
@@ -58,7 +64,7 @@ def main():
             a = nem.__dict__["_vmm_grad_arena"].flat
             assert any(a.data_ptr() <= p.grad.data_ptr() < a.data_ptr() + a.numel() * 4 for p in nem.parameters() if p.grad is not None)
     if rank == 0:
-        print(f"DIST_GPU_OK world={world} worst_rel_err={worst:.2e}")
+        print(f"DIST_GPU_OK world={world} backend={backend} worst_rel_err={worst:.2e}")
     dist.destroy_process_group()
 
 

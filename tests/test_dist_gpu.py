@@ -1,6 +1,8 @@
-"""N = 2 on real GPUs: two CUDA ranks (torchrun, NCCL) on the halves of a batch + GradBucket.allreduce_mean() reproduce
-the 1-rank full-batch gradients of the whole training step (fp32 preset, 2e-5) - equal and ragged shards, with the
-gradients written straight into the flat arenas (attach) and through the packing path.  Skipped with fewer than 2 GPUs."""
+"""N = 2 on real GPUs: two CUDA ranks (torchrun) on the halves of a batch + GradBucket.allreduce_mean() reproduce the 1-rank
+full-batch gradients of the whole training step (fp32 preset, 2e-5) - equal and ragged shards, with the gradients written
+straight into the flat arenas (attach) and through the packing path.  With 2+ GPUs the ranks sit on different devices
+and exchange over NCCL; on a single-GPU box both ranks run their CUDA step on cuda:0 and exchange the CUDA buffers over
+gloo (NCCL refuses two ranks on one device) - the same GradBucket code path minus the transport."""
 import os
 import socket
 import subprocess
@@ -22,12 +24,12 @@ def _free_port():
 
 
 def test_two_cuda_ranks_equal_one_rank_full_batch():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(HERE, "dist_gpu_worker.py")]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0 and "DIST_GPU_OK" in r.stdout, r.stdout[-3000:]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
+                       env=dict(os.environ, VMM_TEST_BACKEND=backend))
+    assert r.returncode == 0 and f"DIST_GPU_OK world=2 backend={backend}" in r.stdout, r.stdout[-3000:]
 
 
 def test_grad_arena_single_rank():
