@@ -409,6 +409,10 @@ def measure_preset(precision, B, args, dev, rank, world, local, profile_gemm=Tru
     # The timed region holds K host->device copies of the step's inputs (pinned memory) and K device->host reads of
     # the loss.  Inputs go through the package's DevicePrefetcher, as in ModelNetTrainer.train_nem_mvcnn: batch i+1
     # is copied on a side stream while step i computes; batch 0 of the region is not overlapped with anything.
+    if args.value_only:
+        res = dict(value=value, ms_per_step=ms / args.steps, clocks=clocks, e2e=None, gpu_launches=int(launches), roofline=None,
+                   features=str(xdtype).replace("torch.", ""))
+        return res
     feeder = DevicePrefetcher([], dev)                      # its two device buffer sets are allocated by the warm-up run
 
     def e2e_run(steps):
@@ -474,7 +478,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N = 1: skip presets.fp32 and gpu_eager_baseline")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--value-only", action="store_true",
+                    help="profiler runs (ncu launch list): warm-up + the K timed steps only - no e2e leg, no per-launch event pass")
     args = ap.parse_args()
+    if args.value_only:
+        args.no_extras = args.no_cpu_baseline = True
     if args.impl == "reference":
         return run_reference(args)
     if args.impl == "eager_gpu":

@@ -70,6 +70,21 @@ __device__ __forceinline__ float act_grad(int act, float y) {
   return 1.f;
 }
 
+__device__ __forceinline__ float elu_fwd_fast(float y) {
+  // expm1 for y <= 0: a degree-5 Taylor polynomial near zero (|error| < 3e-8 for y > -0.125), __expf(y) - 1 elsewhere
+  // (absolute error ~1e-7: the same class as the fp32 rounding of the values around it).  Both are evaluated and
+  // selected: the values of a row straddle all three ranges, so branches would diverge in every warp.
+  const float p = y * fmaf(y, fmaf(y, fmaf(y, fmaf(y, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
+  const float e = __expf(y) - 1.f;
+  const float neg = y > -0.125f ? p : e;
+  return y > 0.f ? y : neg;
+}
+__device__ __forceinline__ float act_fwd_fast(int act, float y) {
+  if (act == ACT_ELU) return elu_fwd_fast(y);
+  if (act == ACT_RELU) return y > 0.f ? y : 0.f;
+  return y;
+}
+
 __device__ __forceinline__ void store_planes4(const Planes& P, long long idx, float4 v) {
   if (P.fmt == VMM_FMT_F16PAIR) {
     const float c[4] = {fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f),
@@ -129,6 +144,54 @@ __device__ __forceinline__ void store_op4(const Op& o, long long idx, float4 v) 
 __device__ __forceinline__ void store_op1(const Op& o, long long idx, float v) {
   store_planes1(o.f, idx, v);
   if (o.b.n > 0 && o.b.p[0] != o.f.p[0]) store_planes1(o.b, idx, v);
+}
+
+// The operand-plane layouts the forward streaming kernels are specialised for (everything else takes the generic
+// run-time path): PCFG = 10 * (fp16 planes of the forward set) + (bf16 planes of a separate gradient set).
+//   21: training, "bf16" preset  (fp16 hi + lo, one bf16 gradient plane)        22: training, "fp32" preset
+//   10: forward-only calls of the "bf16" preset (fp16 hi plane only)             0: generic
+__host__ __device__ inline int plane_cfg(const Op& o) {
+  if (o.f.fmt != VMM_FMT_F16PAIR) return 0;
+  const bool sep = o.b.n > 0 && o.b.p[0] != o.f.p[0];
+  if (sep && o.b.fmt != VMM_FMT_BF16) return 0;
+  if (o.f.n == 2 && sep && o.b.n == 1) return 21;
+  if (o.f.n == 2 && sep && o.b.n == 2) return 22;
+  if (o.f.n == 1 && !sep) return 10;
+  return 0;
+}
+template <int PCFG>
+__device__ __forceinline__ void store_cfg4(const Op& o, long long idx, float4 v) {
+  if constexpr (PCFG == 0) {
+    store_op4(o, idx, v);
+  } else {
+    constexpr int FN = PCFG / 10, BN = PCFG % 10;
+    const float c0 = fminf(fmaxf(v.x, -65504.f), 65504.f), c1 = fminf(fmaxf(v.y, -65504.f), 65504.f);
+    const float c2 = fminf(fmaxf(v.z, -65504.f), 65504.f), c3 = fminf(fmaxf(v.w, -65504.f), 65504.f);
+    const __half2 h0 = __floats2half2_rn(c0, c1), h1 = __floats2half2_rn(c2, c3);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&h0);
+    u.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(o.f.p[0] + idx) = u;
+    if constexpr (FN == 2) {
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      const __half2 l0 = __floats2half2_rn((c0 - f0.x) * 2048.f, (c1 - f0.y) * 2048.f);
+      const __half2 l1 = __floats2half2_rn((c2 - f1.x) * 2048.f, (c3 - f1.y) * 2048.f);
+      u.x = *reinterpret_cast<const uint32_t*>(&l0);
+      u.y = *reinterpret_cast<const uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(o.f.p[1] + idx) = u;
+    }
+#pragma unroll
+    for (int i = 0; i < BN; ++i) {
+      const __nv_bfloat162 b0 = __floats2bfloat162_rn(v.x, v.y), b1 = __floats2bfloat162_rn(v.z, v.w);
+      u.x = *reinterpret_cast<const uint32_t*>(&b0);
+      u.y = *reinterpret_cast<const uint32_t*>(&b1);
+      *reinterpret_cast<uint2*>(o.b.p[i] + idx) = u;
+      if (i + 1 < BN) {
+        const float2 f0 = __bfloat1622float2(b0), f1 = __bfloat1622float2(b1);
+        v = make_float4(v.x - f0.x, v.y - f0.y, v.z - f1.x, v.w - f1.y);
+      }
+    }
+  }
 }
 
 // Pre-normalisation value of 4 consecutive columns, and (LN_ENC1) the residual factor s with
@@ -380,7 +443,7 @@ __device__ __forceinline__ float act_grad_fast(int act, float y) {
   return 1.f;
 }
 
-template <int MODE>
+template <int MODE, int PCFG>
 __global__ void __launch_bounds__(256) ln1k_forward_kernel(LnDesc d, int act, Op out, float* __restrict__ mean_out,
                                                            float* __restrict__ rstd_out) {
   const int lane = threadIdx.x & 31;
@@ -417,16 +480,16 @@ __global__ void __launch_bounds__(256) ln1k_forward_kernel(LnDesc d, int act, Op
       const int c = (lane + 32 * i) * 4;
       const float4 g = ld4(d.ln_g + c), b = ld4(d.ln_b + c);
       float4 o;
-      o.x = act_fwd(act, fmaf((v[i].x - mean) * rstd, g.x, b.x));
-      o.y = act_fwd(act, fmaf((v[i].y - mean) * rstd, g.y, b.y));
-      o.z = act_fwd(act, fmaf((v[i].z - mean) * rstd, g.z, b.z));
-      o.w = act_fwd(act, fmaf((v[i].w - mean) * rstd, g.w, b.w));
+      o.x = act_fwd_fast(act, fmaf((v[i].x - mean) * rstd, g.x, b.x));
+      o.y = act_fwd_fast(act, fmaf((v[i].y - mean) * rstd, g.y, b.y));
+      o.z = act_fwd_fast(act, fmaf((v[i].z - mean) * rstd, g.z, b.z));
+      o.w = act_fwd_fast(act, fmaf((v[i].w - mean) * rstd, g.w, b.w));
       if (d.drop_p > 0.f) {
         float ds[4];
         dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(obase + c), ds);
         o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
       }
-      store_op4(out, obase + c, o);
+      store_cfg4<PCFG>(out, obase + c, o);
     }
   }
 }
@@ -900,20 +963,7 @@ __global__ void __launch_bounds__(MAXT) lnw_backward_rows_kernel(LnDesc d, int a
 
 // Forward for the same wide stages: persistent blocks of width/16 threads, four float4 per thread, rows through a
 // bulk-copy pipeline (slot = one row of C); the LayerNorm parameters of a thread's columns stay in registers.
-__device__ __forceinline__ float elu_fwd_fast(float y) {
-  // expm1 for y <= 0: a degree-5 Taylor polynomial near zero (|error| < 3e-8 for y > -0.125), __expf(y) - 1 elsewhere
-  // (absolute error ~1e-7: the same class as the fp32 rounding of the values around it)
-  if (y > 0.f) return y;
-  if (y > -0.125f) return y * fmaf(y, fmaf(y, fmaf(y, fmaf(y, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
-  return __expf(y) - 1.f;
-}
-__device__ __forceinline__ float act_fwd_fast(int act, float y) {
-  if (act == ACT_ELU) return elu_fwd_fast(y);
-  if (act == ACT_RELU) return y > 0.f ? y : 0.f;
-  return y;
-}
-
-template <int MAXT, int STAGES, int MINB>
+template <int MAXT, int STAGES, int MINB, int PCFG>
 __global__ void __launch_bounds__(MAXT, MINB) lnw_forward_kernel(LnDesc d, int act, Op out, float* __restrict__ mean_out,
                                                            float* __restrict__ rstd_out) {
   extern __shared__ __align__(128) uint8_t dsm[];
@@ -982,7 +1032,7 @@ __global__ void __launch_bounds__(MAXT, MINB) lnw_forward_kernel(LnDesc d, int a
         dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(obase + c), ds);
         o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
       }
-      store_op4(out, obase + c, o);
+      store_cfg4<PCFG>(out, obase + c, o);
     }
   }
 }
@@ -1688,27 +1738,48 @@ int ln_forward(int mode, int act, const LnDesc& d, const Op& out, float* mean, f
   VMM_REQUIRE(out.f.n >= 1 && out.f.p[0] && mean && rstd, "ln_forward: null output");
   if (d.width == W1K) {                 // warp-per-row fast path
     const int blocks = std::min(ceil_div(d.rows, 8), device_sm_count() * 16);
-    if (mode == LN_BIAS) ln1k_forward_kernel<LN_BIAS><<<blocks, 256, 0, stream>>>(d, act, out, mean, rstd);
-    else ln1k_forward_kernel<LN_ENC1><<<blocks, 256, 0, stream>>>(d, act, out, mean, rstd);
+#define VMM_LN1K(PC)                                                                                    \
+  {                                                                                                     \
+    if (mode == LN_BIAS) ln1k_forward_kernel<LN_BIAS, PC><<<blocks, 256, 0, stream>>>(d, act, out, mean, rstd); \
+    else ln1k_forward_kernel<LN_ENC1, PC><<<blocks, 256, 0, stream>>>(d, act, out, mean, rstd);                  \
+  }
+    switch (plane_cfg(out)) {
+      case 21: VMM_LN1K(21) break;
+      case 22: VMM_LN1K(22) break;
+      case 10: VMM_LN1K(10) break;
+      default: VMM_LN1K(0) break;
+    }
+#undef VMM_LN1K
     VMM_LAUNCHED();
     return 0;
   }
   if (mode == LN_BIAS && d.width % 512 == 0 && d.width / 16 <= 1024 && (reinterpret_cast<uintptr_t>(d.C) & 15) == 0) {
     // persistent blocks of width/16 threads, rows through a bulk-copy pipeline
     const int threads = d.width / 16, rowb = d.width * 4;
+#define VMM_LNWF(MAXT, ST, MINB, PC, BLOCKS)                                                                        \
+  {                                                                                                                  \
+    VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&lnw_forward_kernel<MAXT, ST, MINB, PC>), smem));              \
+    lnw_forward_kernel<MAXT, ST, MINB, PC><<<BLOCKS, threads, smem, stream>>>(d, act, out, mean, rstd);              \
+  }
+#define VMM_LNWF_CFG(MAXT, ST, MINB, BLOCKS)                                                                         \
+  switch (plane_cfg(out)) {                                                                                          \
+    case 21: VMM_LNWF(MAXT, ST, MINB, 21, BLOCKS) break;                                                             \
+    case 22: VMM_LNWF(MAXT, ST, MINB, 22, BLOCKS) break;                                                             \
+    case 10: VMM_LNWF(MAXT, ST, MINB, 10, BLOCKS) break;                                                             \
+    default: VMM_LNWF(MAXT, ST, MINB, 0, BLOCKS) break;                                                              \
+  }
     if (threads <= 256) {                                    // 4096-wide (enc2, dec1): 4 slots of 16 KB, 3 blocks per SM
       const int smem = 4 * rowb;
-      VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&lnw_forward_kernel<256, 4, 3>), smem));
-      lnw_forward_kernel<256, 4, 3><<<std::min(d.rows, device_sm_count() * 3), threads, smem, stream>>>(d, act, out, mean, rstd);
+      VMM_LNWF_CFG(256, 4, 3, std::min(d.rows, device_sm_count() * 3))
     } else if (threads <= 768) {                             // 12288-wide (dec2 at M = 12): 3 slots of 48 KB, 1 block per SM
       const int smem = 3 * rowb;
-      VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&lnw_forward_kernel<768, 3, 1>), smem));
-      lnw_forward_kernel<768, 3, 1><<<std::min(d.rows, device_sm_count()), threads, smem, stream>>>(d, act, out, mean, rstd);
+      VMM_LNWF_CFG(768, 3, 1, std::min(d.rows, device_sm_count()))
     } else {
       const int smem = 3 * rowb;
-      VMM_TRY(opt_in_smem(reinterpret_cast<const void*>(&lnw_forward_kernel<1024, 3, 1>), smem));
-      lnw_forward_kernel<1024, 3, 1><<<std::min(d.rows, device_sm_count()), threads, smem, stream>>>(d, act, out, mean, rstd);
+      VMM_LNWF_CFG(1024, 3, 1, std::min(d.rows, device_sm_count()))
     }
+#undef VMM_LNWF_CFG
+#undef VMM_LNWF
     VMM_LAUNCHED();
     return 0;
   }

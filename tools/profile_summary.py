@@ -1,6 +1,8 @@
 """Post-process ncu CSV logs into the summaries committed under profiles/.
 
     python tools/profile_summary.py launches gpurun_out/launches.csv <steps_in_log> > profiles/rNN_launch_summary.txt
+    python tools/profile_summary.py bench gpurun_out/launches.csv > profiles/rNN_launch_summary.txt   # log of `bench.py --value-only`:
+                                                    # steps are delimited by their (single) loss_forward_kernel launch
     python tools/profile_summary.py traffic gpurun_out/gemm_traffic.csv <steps_in_log> <precision> <batch>   # -> profiles/gemm_traffic.json
 """
 import collections, csv, json, os, re, sys
@@ -40,11 +42,17 @@ def short(name):
     return re.sub(r"^void ", "", name)
 
 
-if sys.argv[1] == "launches":
+if sys.argv[1] in ("launches", "bench"):
     L = per_launch(sys.argv[2])
-    steps = int(sys.argv[3])
-    n = len(L) // steps
-    last = L[-n:]                                   # the last step of the log (after warm-up)
+    if sys.argv[1] == "bench":
+        marks = [i for i, (k, _) in enumerate(L) if "loss_forward_kernel" in k]
+        steps = len(marks)
+        n = marks[-1] - marks[-2]                   # launches from one step's loss kernel to the next one's = one step
+        last = L[len(L) - n:]                       # the last step of the log (after warm-up)
+    else:
+        steps = int(sys.argv[3])
+        n = len(L) // steps
+        last = L[-n:]                               # the last step of the log (after warm-up)
     tot = sum(m.get("gpu__time_duration.sum", 0.0) for _, m in last)
     agg = collections.OrderedDict()
     for k, m in last:
