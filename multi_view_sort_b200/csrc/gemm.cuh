@@ -96,7 +96,10 @@ struct alignas(64) GemmParams {
 // (5 x 32 KB for a pair).  A third tile (two delta tiles used in turn, 4 stages) measured no better: 1.53 vs 1.50 ms
 // for the B = 4096 launch - the epilogue's cost is its shared-memory traffic (16 KB per 32x32 chunk against the 32 KB
 // per k-block the tensor core reads), not the wait for the TMA engine.  EPI_BUFS = 3 still works (delta_tile_acquire).
-__host__ __device__ constexpr int epi_bufs(int epi, int opl) { return (epi == 2 /* EPI_ESTEP */ && opl == 3) ? 2 : 1; }
+#ifndef VMM_ESTEP_BUFS
+#define VMM_ESTEP_BUFS 2   // staging tiles per epilogue warp of the fp32-delta E-step (A/B builds: 3 = two delta tiles used in turn)
+#endif
+__host__ __device__ constexpr int epi_bufs(int epi, int opl) { return (epi == 2 /* EPI_ESTEP */ && opl == 3) ? VMM_ESTEP_BUFS : 1; }
 
 template <int BN, int NCTA = 1, int EPI_BUFS = 1>
 struct GemmCfg {

@@ -129,15 +129,19 @@ def estep_backward(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, alpha, 
     return outs
 
 
-def estep_forward_save(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, delta_dtype=torch.float16):
+def estep_forward_save(z_planes, w3_planes, b3, x, k_latent, m_views, sigma, delta_dtype=torch.float16, want_sq=True, out=None):
     """estep_forward that also writes delta = x - pred (rows, D) as fp16 (saturating) or fp32.
-    Returns (part_e, part_sq, delta)."""
+    Returns (part_e, part_sq, delta).  want_sq=False: what every EM iteration but the last runs (no loss sums);
+    out: reuse a (part_e, part_sq, delta) triple."""
     rows, zk = z_planes[0].shape
     D = w3_planes[0].shape[0]
     nb = estep_num_blocks(D)
     dev = z_planes[0].device
-    pe, psq = torch.empty(rows, nb, device=dev), torch.empty(rows, nb, device=dev)
-    delta = torch.empty(rows, D, device=dev, dtype=delta_dtype)
+    if out is not None:
+        pe, psq, delta = out
+    else:
+        pe, psq = torch.empty(rows, nb, device=dev), (torch.empty(rows, nb, device=dev) if want_sq else None)
+        delta = torch.empty(rows, D, device=dev, dtype=delta_dtype)
     zc, wc = planes_c(z_planes), planes_c(w3_planes)
     check(lib().vmm_estep_forward_save(rows, D, zk, C.byref(zc), C.byref(wc), ptr(b3), ptr(x), int(x.dtype == torch.bfloat16),
                                        C.c_longlong(x.stride(-2)), int(k_latent), int(m_views), C.c_float(sigma), ptr(pe),
