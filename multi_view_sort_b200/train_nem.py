@@ -62,7 +62,7 @@ OPTIONS = [
     (("-e_sigma",), _FLT, 0.1, "standard deviation of the E-step's Gaussian"),
     (("-dataset",), _STR, "MNet40", "class list: MNet40 | MNet10 | ShapeNet"),
     # ---- additions of this implementation ----
-    (("-precision",), _STR, "fp32", "fp32 | bf16 | bf16_h | bf16_fast: tensor-core operand precision (DESIGN.md 6)"),
+    (("-precision",), _STR, "fp32", "fp32 | bf16 | bf16_b8 | bf16_fast: tensor-core operand precision (DESIGN.md 6)"),
     (("-model_path",), _STR, "", "test mode: directory that holds <name>/NEM and <name>/MV_C_Net"),
     (("-feature_out",), _STR, "", "test mode: where the descriptors are written"),
 ]
