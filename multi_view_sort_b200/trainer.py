@@ -74,6 +74,10 @@ class ModelNetTrainer(object):
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.bucket = GradBucket(list(nem.parameters()) + list(c_net.parameters()))
+        if self.world > 1:
+            # the backward passes write into flat per-module arenas that are averaged in place (the head's under the EM
+            # backward); any parameter outside them takes the bucket's packing path
+            self.bucket.attach(nem, c_net)
         self.writer = ScalarWriter(log_dir) if (log_dir is not None and self.rank == 0) else None
 
     # ------------------------------------------------------------------------------------------
