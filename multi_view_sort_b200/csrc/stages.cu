@@ -59,6 +59,11 @@ __device__ __forceinline__ float warp_max_f(float v) {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+__device__ __forceinline__ float ex2_approx_f(float x) {          // one MUFU; ex2.approx(0) = 1 exactly
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float act_fwd(int act, float y) {
   if (act == ACT_ELU) return y > 0.f ? y : expm1f(y);
   if (act == ACT_RELU) return y > 0.f ? y : 0.f;
@@ -189,6 +194,60 @@ __device__ __forceinline__ void store_cfg4(const Op& o, long long idx, float4 v)
       if (i + 1 < BN) {
         const float2 f0 = __bfloat1622float2(b0), f1 = __bfloat1622float2(b1);
         v = make_float4(v.x - f0.x, v.y - f0.y, v.z - f1.x, v.w - f1.y);
+      }
+    }
+  }
+}
+
+// ---- packed fp32x2 helpers (FADD2 / FMUL2 / FFMA2: one issue slot for two elements; IEEE round-to-nearest like the
+// scalar forms, so a formula written with them rounds exactly as its scalar spelling) ----
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// forward activation of two values; ELU as in elu_fwd_fast (polynomial near zero, exp - 1 elsewhere, both evaluated)
+__device__ __forceinline__ float2 act2_fwd(int act, float2 y) {
+  if (act == ACT_ELU) {
+    const float2 p = mul2(y, fma2(y, fma2(y, fma2(y, fma2(y, bc2(1.f / 120.f), bc2(1.f / 24.f)), bc2(1.f / 6.f)), bc2(0.5f)), bc2(1.f)));
+    const float2 t = mul2(y, bc2(1.4426950408889634f));
+    const float2 e = add2(make_float2(ex2_approx_f(t.x), ex2_approx_f(t.y)), bc2(-1.f));
+    const float nx = y.x > -0.125f ? p.x : e.x, ny = y.y > -0.125f ? p.y : e.y;
+    return make_float2(y.x > 0.f ? y.x : nx, y.y > 0.f ? y.y : ny);
+  }
+  if (act == ACT_RELU) return make_float2(y.x > 0.f ? y.x : 0.f, y.y > 0.f ? y.y : 0.f);
+  return y;
+}
+// store_cfg4 on two packed pairs (columns idx .. idx+3)
+template <int PCFG>
+__device__ __forceinline__ void store_cfg4p(const Op& o, long long idx, float2 lo, float2 hi) {
+  if constexpr (PCFG == 0) {
+    store_op4(o, idx, make_float4(lo.x, lo.y, hi.x, hi.y));
+  } else {
+    constexpr int FN = PCFG / 10, BN = PCFG % 10;
+    const float2 c0 = make_float2(fminf(fmaxf(lo.x, -65504.f), 65504.f), fminf(fmaxf(lo.y, -65504.f), 65504.f));
+    const float2 c1 = make_float2(fminf(fmaxf(hi.x, -65504.f), 65504.f), fminf(fmaxf(hi.y, -65504.f), 65504.f));
+    const __half2 h0 = __float22half2_rn(c0), h1 = __float22half2_rn(c1);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&h0);
+    u.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(o.f.p[0] + idx) = u;
+    if constexpr (FN == 2) {
+      const float2 m2048 = bc2(2048.f), neg1 = bc2(-1.f);
+      const __half2 l0 = __float22half2_rn(mul2(fma2(__half22float2(h0), neg1, c0), m2048));
+      const __half2 l1 = __float22half2_rn(mul2(fma2(__half22float2(h1), neg1, c1), m2048));
+      u.x = *reinterpret_cast<const uint32_t*>(&l0);
+      u.y = *reinterpret_cast<const uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(o.f.p[1] + idx) = u;
+    }
+#pragma unroll
+    for (int i = 0; i < BN; ++i) {
+      const __nv_bfloat162 b0 = __float22bfloat162_rn(lo), b1 = __float22bfloat162_rn(hi);
+      u.x = *reinterpret_cast<const uint32_t*>(&b0);
+      u.y = *reinterpret_cast<const uint32_t*>(&b1);
+      *reinterpret_cast<uint2*>(o.b.p[i] + idx) = u;
+      if (i + 1 < BN) {
+        lo = fma2(__bfloat1622float2(b0), bc2(-1.f), lo);
+        hi = fma2(__bfloat1622float2(b1), bc2(-1.f), hi);
       }
     }
   }
@@ -446,8 +505,11 @@ __device__ __forceinline__ float act_grad_fast(int act, float y) {
 template <int MODE, int PCFG>
 __global__ void __launch_bounds__(256) ln1k_forward_kernel(LnDesc d, int act, Op out, float* __restrict__ mean_out,
                                                            float* __restrict__ rstd_out) {
+  // one warp per row; a lane's 8 float4 live in registers as packed pairs (fp32x2 arithmetic: the kernel is issue-bound)
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  const bool has_g1 = MODE == LN_ENC1 && d.C != nullptr;
+  const bool drop = d.drop_p > 0.f;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < d.rows; row += gridDim.x * wpb) {
     float gam = 0.f;
     long long xrow = 0;
@@ -455,41 +517,58 @@ __global__ void __launch_bounds__(256) ln1k_forward_kernel(LnDesc d, int act, Op
       gam = __ldg(d.gamma + row);
       xrow = static_cast<long long>(row / d.km) * d.mv + row % d.mv;
     }
-    float4 v[W1K_V];
-    float sum = 0.f;
+    float2 v_lo[W1K_V], v_hi[W1K_V];
+    float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < W1K_V; ++i) {
-      v[i] = ln_value4<MODE>(d, row, xrow, gam, (lane + 32 * i) * 4, nullptr);
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      const int c = (lane + 32 * i) * 4;
+      const float4 b = ld4(d.bias + c);
+      if (MODE == LN_BIAS) {
+        const float4 t = ld4(d.C + static_cast<long long>(row) * d.ldc + c);
+        v_lo[i] = add2(make_float2(t.x, t.y), make_float2(b.x, b.y));
+        v_hi[i] = add2(make_float2(t.z, t.w), make_float2(b.z, b.w));
+      } else {
+        const float4 xw = ld4(d.xw1 + xrow * d.width + c);
+        float2 s_lo = make_float2(xw.x, xw.y), s_hi = make_float2(xw.z, xw.w);
+        if (has_g1) {                                   // s = xw1 - G1 - w1b3, in ln_value4's order
+          const float4 g1 = ld4(d.C + static_cast<long long>(row) * d.ldc + c), w = ld4(d.w1b3 + c);
+          s_lo = fma2(make_float2(w.x, w.y), bc2(-1.f), fma2(make_float2(g1.x, g1.y), bc2(-1.f), s_lo));
+          s_hi = fma2(make_float2(w.z, w.w), bc2(-1.f), fma2(make_float2(g1.z, g1.w), bc2(-1.f), s_hi));
+        }
+        v_lo[i] = fma2(bc2(gam), s_lo, make_float2(b.x, b.y));
+        v_hi[i] = fma2(bc2(gam), s_hi, make_float2(b.z, b.w));
+      }
+      sum2 = add2(sum2, add2(v_lo[i], v_hi[i]));
     }
-    const float mean = warp_sum_f(sum) * (1.0f / W1K);
-    float sq = 0.f;
+    const float mean = warp_sum_f(sum2.x + sum2.y) * (1.0f / W1K);
+    const float2 nm = bc2(-mean);
+    float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < W1K_V; ++i) {
-      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
-      sq += (a * a + b * b) + (e * e + f * f);
+      const float2 a = add2(v_lo[i], nm), e = add2(v_hi[i], nm);
+      sq2 = fma2(e, e, fma2(a, a, sq2));
     }
-    const float rstd = 1.0f / sqrtf(warp_sum_f(sq) * (1.0f / W1K) + d.eps);
+    const float rstd = 1.0f / sqrtf(warp_sum_f(sq2.x + sq2.y) * (1.0f / W1K) + d.eps);
     if (lane == 0) {
       mean_out[row] = mean;
       rstd_out[row] = rstd;
     }
+    const float2 rs = bc2(rstd);
     const long long obase = static_cast<long long>(row) * W1K;
 #pragma unroll
     for (int i = 0; i < W1K_V; ++i) {
       const int c = (lane + 32 * i) * 4;
       const float4 g = ld4(d.ln_g + c), b = ld4(d.ln_b + c);
-      float4 o;
-      o.x = act_fwd_fast(act, fmaf((v[i].x - mean) * rstd, g.x, b.x));
-      o.y = act_fwd_fast(act, fmaf((v[i].y - mean) * rstd, g.y, b.y));
-      o.z = act_fwd_fast(act, fmaf((v[i].z - mean) * rstd, g.z, b.z));
-      o.w = act_fwd_fast(act, fmaf((v[i].w - mean) * rstd, g.w, b.w));
-      if (d.drop_p > 0.f) {
+      // act((v - mean) * rstd * g + b): the same operation order as the scalar kernels and the backward passes
+      float2 o_lo = act2_fwd(act, fma2(mul2(add2(v_lo[i], nm), rs), make_float2(g.x, g.y), make_float2(b.x, b.y)));
+      float2 o_hi = act2_fwd(act, fma2(mul2(add2(v_hi[i], nm), rs), make_float2(g.z, g.w), make_float2(b.z, b.w)));
+      if (drop) {
         float ds[4];
         dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(obase + c), ds);
-        o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
+        o_lo = mul2(o_lo, make_float2(ds[0], ds[1]));
+        o_hi = mul2(o_hi, make_float2(ds[2], ds[3]));
       }
-      store_cfg4<PCFG>(out, obase + c, o);
+      store_cfg4p<PCFG>(out, obase + c, o_lo, o_hi);
     }
   }
 }
@@ -607,8 +686,9 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
   constexpr int ROWB = W1K * 4;                  // one 1024-wide fp32 row
   constexpr int SLOT = (2 + 2 * NR) * ROWB;      // xw1 row | dxw1 row | G1 rows [NR] | incoming-gradient rows [NR]
   __shared__ uint64_t bar[STAGES];
-  __shared__ float red[2][8][2 * NR];
-  __shared__ float red2[2][8][2 * NR];     // per row: sum for dgamma, max|dG1| for the row-scaled fp16 copy
+  // per-warp partials of the row reductions, value-major ([value][warp]: a reader sums one value with two 16-byte loads)
+  __shared__ __align__(16) float red[2][2 * NR][8];
+  __shared__ __align__(16) float red2[2][2 * NR][8];   // per row: sum for dgamma, max|dG1| for the row-scaled fp16 copy
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = tid * 4;
   const int groups = d.rows / NR, G = gridDim.x;
@@ -634,9 +714,19 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
       if (blockIdx.x + i * G < groups) issue(blockIdx.x + i * G, i);
   }
   __syncthreads();
-  const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c), bias = ld4(d.bias + c);
-  const float4 w1b3 = d.C ? ld4(d.w1b3 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 a_g = make_float4(0.f, 0.f, 0.f, 0.f), a_b = a_g, a_bias = a_g, a_w = a_g;
+  // A thread's four columns are held as two float2: the arithmetic below is packed fp32x2 (FADD2 / FMUL2 / FFMA2 issue
+  // ONE instruction for two elements at the FP32 pipe's full rate - measured, tools/micro/ffma2_bench.cu - and this
+  // kernel is bound by instruction issue, not by the pipe or by bandwidth).
+  const float4 g4 = ld4(d.ln_g + c), bb4 = ld4(d.ln_b + c), bias4 = ld4(d.bias + c);
+  const float4 w1b34 = d.C ? ld4(d.w1b3 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float2 g_lo = make_float2(g4.x, g4.y), g_hi = make_float2(g4.z, g4.w);
+  const float2 bb_lo = make_float2(bb4.x, bb4.y), bb_hi = make_float2(bb4.z, bb4.w);
+  const float2 bias_lo = make_float2(bias4.x, bias4.y), bias_hi = make_float2(bias4.z, bias4.w);
+  const float2 nw_lo = make_float2(-w1b34.x, -w1b34.y), nw_hi = make_float2(-w1b34.z, -w1b34.w);
+  const float2 zero2 = make_float2(0.f, 0.f), neg1 = make_float2(-1.f, -1.f);
+  float2 a_g_lo = zero2, a_g_hi = zero2, a_b_lo = zero2, a_b_hi = zero2, a_bias_lo = zero2, a_bias_hi = zero2;
+  float2 a_w_lo = zero2, a_w_hi = zero2;
+  const bool elu = act == ACT_ELU, drop = d.drop_p > 0.f;
   // per-row scalars (responsibility, LayerNorm statistics) of the NEXT group are fetched one group ahead
   float gam_n[NR], mean_n[NR], rstd_n[NR];
   auto fetch_scalars = [&](int grp) {
@@ -667,107 +757,146 @@ __global__ void __launch_bounds__(256, 2) enc1_backward_fused_kernel(
     const float4 xw = sl[tid];
     float4 dxo = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_dxw) dxo = sl[256 + tid];
-    float4 sv[NR], dy[NR];
+    float2 xb_lo = make_float2(xw.x, xw.y), xb_hi = make_float2(xw.z, xw.w);      // xw1 - w1b3
+    if (has_g1) {
+      xb_lo = __fadd2_rn(xb_lo, nw_lo);
+      xb_hi = __fadd2_rn(xb_hi, nw_hi);
+    }
+    float2 sv_lo[NR], sv_hi[NR], dy_lo[NR], dy_hi[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-      sv[k] = xw;
+      sv_lo[k] = xb_lo;
+      sv_hi[k] = xb_hi;
       if (has_g1) {
         const float4 g1 = sl[(2 + k) * 256 + tid];
-        sv[k] = make_float4(xw.x - g1.x - w1b3.x, xw.y - g1.y - w1b3.y, xw.z - g1.z - w1b3.z, xw.w - g1.w - w1b3.w);
+        sv_lo[k] = __ffma2_rn(make_float2(g1.x, g1.y), neg1, xb_lo);              // s = xw1 - G1 - w1b3
+        sv_hi[k] = __ffma2_rn(make_float2(g1.z, g1.w), neg1, xb_hi);
       }
-      dy[k] = sl[(2 + NR + k) * 256 + tid];
+      const float4 t = sl[(2 + NR + k) * 256 + tid];
+      dy_lo[k] = make_float2(t.x, t.y);
+      dy_hi[k] = make_float2(t.z, t.w);
     }
+    // xhat = (gamma * s + bias - mean) * rstd = s * (gamma * rstd) + (bias * rstd - mean * rstd)
+#define VMM_ENC1_XHAT(k)                                                                             \
+    const float2 ak = make_float2(gam[k] * rstd[k], gam[k] * rstd[k]);                               \
+    const float2 rk = make_float2(rstd[k], rstd[k]), nmr = make_float2(-mean[k] * rstd[k], -mean[k] * rstd[k]); \
+    const float2 xh_lo = __ffma2_rn(sv_lo[k], ak, __ffma2_rn(bias_lo, rk, nmr));                     \
+    const float2 xh_hi = __ffma2_rn(sv_hi[k], ak, __ffma2_rn(bias_hi, rk, nmr));
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
       const int row = (b * NR + k) * d.mv + m;
-      float ds[4] = {1.f, 1.f, 1.f, 1.f};
-      if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * W1K + c, ds);
-      const float xh0 = (fmaf(gam[k], sv[k].x, bias.x) - mean[k]) * rstd[k], xh1 = (fmaf(gam[k], sv[k].y, bias.y) - mean[k]) * rstd[k];
-      const float xh2 = (fmaf(gam[k], sv[k].z, bias.z) - mean[k]) * rstd[k], xh3 = (fmaf(gam[k], sv[k].w, bias.w) - mean[k]) * rstd[k];
-      dy[k].x *= ds[0] * act_grad_fast(act, fmaf(xh0, g.x, bb.x));
-      dy[k].y *= ds[1] * act_grad_fast(act, fmaf(xh1, g.y, bb.y));
-      dy[k].z *= ds[2] * act_grad_fast(act, fmaf(xh2, g.z, bb.z));
-      dy[k].w *= ds[3] * act_grad_fast(act, fmaf(xh3, g.w, bb.w));
-      const float dx0 = dy[k].x * g.x, dx1 = dy[k].y * g.y, dx2 = dy[k].z * g.z, dx3 = dy[k].w * g.w;
-      part[2 * k] = warp_sum_f((dx0 + dx1) + (dx2 + dx3));
-      part[2 * k + 1] = warp_sum_f((dx0 * xh0 + dx1 * xh1) + (dx2 * xh2 + dx3 * xh3));
+      VMM_ENC1_XHAT(k)
+      const float2 y_lo = __ffma2_rn(xh_lo, g_lo, bb_lo), y_hi = __ffma2_rn(xh_hi, g_hi, bb_hi);
+      float2 f_lo, f_hi;                                       // d act / dy (x the dropout scale)
+      if (elu) {
+        // ELU' = exp(min(y, 0)): exactly 1 for y >= 0 (ex2.approx(0) = 1), __expf(y) below - no select, no branch
+        const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+        const float2 t_lo = __fmul2_rn(make_float2(fminf(y_lo.x, 0.f), fminf(y_lo.y, 0.f)), l2e);
+        const float2 t_hi = __fmul2_rn(make_float2(fminf(y_hi.x, 0.f), fminf(y_hi.y, 0.f)), l2e);
+        f_lo = make_float2(ex2_approx_f(t_lo.x), ex2_approx_f(t_lo.y));
+        f_hi = make_float2(ex2_approx_f(t_hi.x), ex2_approx_f(t_hi.y));
+      } else {
+        f_lo = make_float2(act_grad_fast(act, y_lo.x), act_grad_fast(act, y_lo.y));
+        f_hi = make_float2(act_grad_fast(act, y_hi.x), act_grad_fast(act, y_hi.y));
+      }
+      if (drop) {
+        float ds[4];
+        dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * W1K + c, ds);
+        f_lo = __fmul2_rn(f_lo, make_float2(ds[0], ds[1]));
+        f_hi = __fmul2_rn(f_hi, make_float2(ds[2], ds[3]));
+      }
+      dy_lo[k] = __fmul2_rn(dy_lo[k], f_lo);
+      dy_hi[k] = __fmul2_rn(dy_hi[k], f_hi);
+      const float2 dx_lo = __fmul2_rn(dy_lo[k], g_lo), dx_hi = __fmul2_rn(dy_hi[k], g_hi);
+      const float2 s1 = __fadd2_rn(dx_lo, dx_hi);
+      const float2 s2 = __ffma2_rn(dx_hi, xh_hi, __fmul2_rn(dx_lo, xh_lo));
+      part[2 * k] = warp_sum_f(s1.x + s1.y);
+      part[2 * k + 1] = warp_sum_f(s2.x + s2.y);
     }
     if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 2 * NR; ++j) red[par][warp][j] = part[j];
+      for (int j = 0; j < 2 * NR; ++j) red[par][j][warp] = part[j];
     }
     __syncthreads();                     // every thread has read its part of slot s: thread 0 may refill it next iteration
-    float4 accx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 accx_lo = zero2, accx_hi = zero2;
     float dgam[NR], amaxk[NR];
-    float4 ngk[NR];
+    float2 ng_lo[NR], ng_hi[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-      float c1 = 0.f, c2 = 0.f;
+      float cc[2];
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        c1 += red[par][w][2 * k];
-        c2 += red[par][w][2 * k + 1];
+      for (int j = 0; j < 2; ++j) {
+        const float4 p0 = *reinterpret_cast<const float4*>(&red[par][2 * k + j][0]);
+        const float4 p1 = *reinterpret_cast<const float4*>(&red[par][2 * k + j][4]);
+        const float2 t = __fadd2_rn(__fadd2_rn(make_float2(p0.x, p0.y), make_float2(p0.z, p0.w)),
+                                    __fadd2_rn(make_float2(p1.x, p1.y), make_float2(p1.z, p1.w)));
+        cc[j] = (t.x + t.y) * (1.0f / W1K);
       }
-      c1 *= (1.0f / W1K);
-      c2 *= (1.0f / W1K);
       const int row = (b * NR + k) * d.mv + m;
-      const float xh[4] = {(fmaf(gam[k], sv[k].x, bias.x) - mean[k]) * rstd[k], (fmaf(gam[k], sv[k].y, bias.y) - mean[k]) * rstd[k],
-                           (fmaf(gam[k], sv[k].z, bias.z) - mean[k]) * rstd[k], (fmaf(gam[k], sv[k].w, bias.w) - mean[k]) * rstd[k]};
-      float4 dv;
-      dv.x = rstd[k] * (dy[k].x * g.x - c1 - xh[0] * c2);
-      dv.y = rstd[k] * (dy[k].y * g.y - c1 - xh[1] * c2);
-      dv.z = rstd[k] * (dy[k].z * g.z - c1 - xh[2] * c2);
-      dv.w = rstd[k] * (dy[k].w * g.w - c1 - xh[3] * c2);
-      dgam[k] = (dv.x * sv[k].x + dv.y * sv[k].y) + (dv.z * sv[k].z + dv.w * sv[k].w);
-      accx.x = fmaf(gam[k], dv.x, accx.x); accx.y = fmaf(gam[k], dv.y, accx.y);
-      accx.z = fmaf(gam[k], dv.z, accx.z); accx.w = fmaf(gam[k], dv.w, accx.w);
-      const float4 ng = make_float4(-gam[k] * dv.x, -gam[k] * dv.y, -gam[k] * dv.z, -gam[k] * dv.w);
-      if (dg1.n) store_planes4(dg1, static_cast<long long>(row) * W1K + c, ng);
-      ngk[k] = ng;
-      amaxk[k] = fmaxf(fmaxf(fabsf(ng.x), fabsf(ng.y)), fmaxf(fabsf(ng.z), fabsf(ng.w)));
-      a_g.x = fmaf(dy[k].x, xh[0], a_g.x); a_g.y = fmaf(dy[k].y, xh[1], a_g.y);
-      a_g.z = fmaf(dy[k].z, xh[2], a_g.z); a_g.w = fmaf(dy[k].w, xh[3], a_g.w);
-      a_b.x += dy[k].x; a_b.y += dy[k].y; a_b.z += dy[k].z; a_b.w += dy[k].w;
-      a_bias.x += dv.x; a_bias.y += dv.y; a_bias.z += dv.z; a_bias.w += dv.w;
-      a_w.x += ng.x; a_w.y += ng.y; a_w.z += ng.z; a_w.w += ng.w;
+      VMM_ENC1_XHAT(k)
+      // dv = rstd * (dy * g - c1 - xhat * c2)
+      const float2 rc1 = make_float2(-rstd[k] * cc[0], -rstd[k] * cc[0]), rc2 = make_float2(-rstd[k] * cc[1], -rstd[k] * cc[1]);
+      const float2 dx_lo = __fmul2_rn(dy_lo[k], g_lo), dx_hi = __fmul2_rn(dy_hi[k], g_hi);
+      const float2 dv_lo = __ffma2_rn(dx_lo, rk, __ffma2_rn(xh_lo, rc2, rc1));
+      const float2 dv_hi = __ffma2_rn(dx_hi, rk, __ffma2_rn(xh_hi, rc2, rc1));
+      const float2 t = __ffma2_rn(dv_hi, sv_hi[k], __fmul2_rn(dv_lo, sv_lo[k]));
+      dgam[k] = t.x + t.y;
+      const float2 gk = make_float2(gam[k], gam[k]), ngk = make_float2(-gam[k], -gam[k]);
+      accx_lo = __ffma2_rn(dv_lo, gk, accx_lo);
+      accx_hi = __ffma2_rn(dv_hi, gk, accx_hi);
+      ng_lo[k] = __fmul2_rn(dv_lo, ngk);
+      ng_hi[k] = __fmul2_rn(dv_hi, ngk);
+      if (dg1.n) store_planes4(dg1, static_cast<long long>(row) * W1K + c, make_float4(ng_lo[k].x, ng_lo[k].y, ng_hi[k].x, ng_hi[k].y));
+      amaxk[k] = fmaxf(fmaxf(fabsf(ng_lo[k].x), fabsf(ng_lo[k].y)), fmaxf(fabsf(ng_hi[k].x), fabsf(ng_hi[k].y)));
+      a_g_lo = __ffma2_rn(dy_lo[k], xh_lo, a_g_lo);
+      a_g_hi = __ffma2_rn(dy_hi[k], xh_hi, a_g_hi);
+      a_b_lo = __fadd2_rn(a_b_lo, dy_lo[k]);
+      a_b_hi = __fadd2_rn(a_b_hi, dy_hi[k]);
+      a_bias_lo = __fadd2_rn(a_bias_lo, dv_lo);
+      a_bias_hi = __fadd2_rn(a_bias_hi, dv_hi);
     }
+#undef VMM_ENC1_XHAT
+    a_w_lo = __ffma2_rn(accx_lo, neg1, a_w_lo);          // column sums of dG1 = -gamma * dv: minus this group's dxw1 part
+    a_w_hi = __ffma2_rn(accx_hi, neg1, a_w_hi);
     if (has_dxw)
       *reinterpret_cast<float4*>(dxw1 + static_cast<long long>(grp) * W1K + c) =
-          make_float4(dxo.x + accx.x, dxo.y + accx.y, dxo.z + accx.z, dxo.w + accx.w);
+          make_float4(dxo.x + accx_lo.x, dxo.y + accx_lo.y, dxo.z + accx_hi.x, dxo.w + accx_hi.y);
     if (dgamma || dg1h.p) {
 #pragma unroll
       for (int k = 0; k < NR; ++k) {
         const float t = warp_sum_f(dgam[k]), mx = warp_max_f(amaxk[k]);
         if (lane == 0) {
-          red2[par][warp][2 * k] = t;
-          red2[par][warp][2 * k + 1] = mx;
+          red2[par][2 * k][warp] = t;
+          red2[par][2 * k + 1][warp] = mx;
         }
       }
       __syncthreads();
       if (dgamma && tid < NR) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += red2[par][w][2 * tid];
+        for (int w = 0; w < 8; ++w) t += red2[par][2 * tid][w];
         dgamma[(b * NR + tid) * d.mv + m] = t;
       }
       if (dg1h.p) {                                  // row-scaled fp16 copy of dG1 for the data-gradient contraction
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
-          float mx = 0.f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red2[par][w][2 * k + 1]);
+          const float4 p0 = *reinterpret_cast<const float4*>(&red2[par][2 * k + 1][0]);
+          const float4 p1 = *reinterpret_cast<const float4*>(&red2[par][2 * k + 1][4]);
+          const float mx = fmaxf(fmaxf(fmaxf(p0.x, p0.y), fmaxf(p0.z, p0.w)), fmaxf(fmaxf(p1.x, p1.y), fmaxf(p1.z, p1.w)));
           const float sc = row_scale_pow2(mx);
+          const float2 sc2 = make_float2(sc, sc);
           const int row = (b * NR + k) * d.mv + m;
           if (tid == 0) dg1h.inv_scale[row] = 1.f / sc;
-          store_half4(dg1h.p, static_cast<long long>(row) * W1K + c, ngk[k].x * sc, ngk[k].y * sc, ngk[k].z * sc, ngk[k].w * sc);
+          const float2 h_lo = __fmul2_rn(ng_lo[k], sc2), h_hi = __fmul2_rn(ng_hi[k], sc2);
+          store_half4(dg1h.p, static_cast<long long>(row) * W1K + c, h_lo.x, h_lo.y, h_hi.x, h_hi.y);
         }
       }
     }
   }
-  atomicAdd(reinterpret_cast<float4*>(d_ln_g + c), a_g);
-  atomicAdd(reinterpret_cast<float4*>(d_ln_b + c), a_b);
-  atomicAdd(reinterpret_cast<float4*>(d_bias + c), a_bias);
-  if (d_w1b3) atomicAdd(reinterpret_cast<float4*>(d_w1b3 + c), a_w);
+  atomicAdd(reinterpret_cast<float4*>(d_ln_g + c), make_float4(a_g_lo.x, a_g_lo.y, a_g_hi.x, a_g_hi.y));
+  atomicAdd(reinterpret_cast<float4*>(d_ln_b + c), make_float4(a_b_lo.x, a_b_lo.y, a_b_hi.x, a_b_hi.y));
+  atomicAdd(reinterpret_cast<float4*>(d_bias + c), make_float4(a_bias_lo.x, a_bias_lo.y, a_bias_hi.x, a_bias_hi.y));
+  if (d_w1b3) atomicAdd(reinterpret_cast<float4*>(d_w1b3 + c), make_float4(a_w_lo.x, a_w_lo.y, a_w_hi.x, a_w_hi.y));
 }
 
 
@@ -998,41 +1127,43 @@ __global__ void __launch_bounds__(MAXT, MINB) lnw_forward_kernel(LnDesc d, int a
     }
     mbar_wait(&bar[s], (it / STAGES) & 1);
     const float4* sv = reinterpret_cast<const float4*>(dsm + static_cast<size_t>(s) * rowb);
-    float4 v[4];
-    float sum = 0.f;
+    float2 v_lo[4], v_hi[4];
+    float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 t = sv[tid + i * nt];
-      v[i] = make_float4(t.x + bias[i].x, t.y + bias[i].y, t.z + bias[i].z, t.w + bias[i].w);
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      v_lo[i] = add2(make_float2(t.x, t.y), make_float2(bias[i].x, bias[i].y));
+      v_hi[i] = add2(make_float2(t.z, t.w), make_float2(bias[i].z, bias[i].w));
+      sum2 = add2(sum2, add2(v_lo[i], v_hi[i]));
     }
-    const float mean = block_sum(sum, red) * inv_w;          // (its barriers also release slot s)
-    float sq = 0.f;
+    const float mean = block_sum(sum2.x + sum2.y, red) * inv_w;          // (its barriers also release slot s)
+    const float2 nm = bc2(-mean);
+    float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
-      sq += (a * a + b * b) + (e * e + f * f);
+      const float2 a = add2(v_lo[i], nm), e = add2(v_hi[i], nm);
+      sq2 = fma2(e, e, fma2(a, a, sq2));
     }
-    const float rstd = 1.0f / sqrtf(block_sum(sq, red) * inv_w + d.eps);
+    const float rstd = 1.0f / sqrtf(block_sum(sq2.x + sq2.y, red) * inv_w + d.eps);
     if (tid == 0) {
       mean_out[row] = mean;
       rstd_out[row] = rstd;
     }
+    const float2 rs = bc2(rstd);
     const long long obase = static_cast<long long>(row) * d.width;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = (tid + i * nt) * 4;
-      float4 o;
-      o.x = act_fwd_fast(act, fmaf((v[i].x - mean) * rstd, g[i].x, be[i].x));
-      o.y = act_fwd_fast(act, fmaf((v[i].y - mean) * rstd, g[i].y, be[i].y));
-      o.z = act_fwd_fast(act, fmaf((v[i].z - mean) * rstd, g[i].z, be[i].z));
-      o.w = act_fwd_fast(act, fmaf((v[i].w - mean) * rstd, g[i].w, be[i].w));
+      // act((v - mean) * rstd * g + b): the operation order the backward passes recompute the ReLU decision with
+      float2 o_lo = act2_fwd(act, fma2(mul2(add2(v_lo[i], nm), rs), make_float2(g[i].x, g[i].y), make_float2(be[i].x, be[i].y)));
+      float2 o_hi = act2_fwd(act, fma2(mul2(add2(v_hi[i], nm), rs), make_float2(g[i].z, g[i].w), make_float2(be[i].z, be[i].w)));
       if (d.drop_p > 0.f) {
         float ds[4];
         dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(obase + c), ds);
-        o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
+        o_lo = mul2(o_lo, make_float2(ds[0], ds[1]));
+        o_hi = mul2(o_hi, make_float2(ds[2], ds[3]));
       }
-      store_cfg4<PCFG>(out, obase + c, o);
+      store_cfg4p<PCFG>(out, obase + c, o_lo, o_hi);
     }
   }
 }
