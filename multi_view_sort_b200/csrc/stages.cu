@@ -935,8 +935,13 @@ __global__ void __launch_bounds__(1024, 1) lnw4k_backward_fused_kernel(
       if (blockIdx.x + i * G < d.rows) issue(blockIdx.x + i * G, i);
   }
   __syncthreads();
-  const float4 g = ld4(d.ln_g + c), bb = ld4(d.ln_b + c), bias = ld4(d.bias + c);
-  float4 a_g = make_float4(0.f, 0.f, 0.f, 0.f), a_b = a_g, a_bias = a_g;
+  // a thread's four columns as two packed pairs (fp32x2 arithmetic: the kernel is issue-bound)
+  const float4 g4 = ld4(d.ln_g + c), bb4 = ld4(d.ln_b + c), bias4 = ld4(d.bias + c);
+  const float2 g_lo = make_float2(g4.x, g4.y), g_hi = make_float2(g4.z, g4.w);
+  const float2 be_lo = make_float2(bb4.x, bb4.y), be_hi = make_float2(bb4.z, bb4.w);
+  const float2 bias_lo = make_float2(bias4.x, bias4.y), bias_hi = make_float2(bias4.z, bias4.w);
+  float2 a_g_lo = make_float2(0.f, 0.f), a_g_hi = a_g_lo, a_b_lo = a_g_lo, a_b_hi = a_g_lo, a_bias_lo = a_g_lo, a_bias_hi = a_g_lo;
+  const bool drop = d.drop_p > 0.f;
   float mean_n = 0.f, rstd_n = 0.f;
   if (blockIdx.x < d.rows) { mean_n = __ldg(mean_in + blockIdx.x); rstd_n = __ldg(rstd_in + blockIdx.x); }
   int it = 0;
@@ -951,51 +956,61 @@ __global__ void __launch_bounds__(1024, 1) lnw4k_backward_fused_kernel(
     mbar_wait(&bar[s], (it / STAGES) & 1);
     const float4 v = reinterpret_cast<const float4*>(dsm + s * 2 * ROWB)[tid];
     const float4 go = reinterpret_cast<const float4*>(dsm + s * 2 * ROWB + ROWB)[tid];
-    float ds[4] = {1.f, 1.f, 1.f, 1.f};
-    if (d.drop_p > 0.f) dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * d.width + c, ds);
-    const float vv[4] = {v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w};
-    const float gg[4] = {g.x, g.y, g.z, g.w}, be[4] = {bb.x, bb.y, bb.z, bb.w};
-    const float oo[4] = {go.x, go.y, go.z, go.w};
-    float xh[4], dy[4];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      xh[q] = (vv[q] - mean) * rstd;
-      dy[q] = oo[q] * ds[q] * act_grad_fast(act, fmaf(xh[q], gg[q], be[q]));
-      const float dx = dy[q] * gg[q];
-      s1 += dx;
-      s2 = fmaf(dx, xh[q], s2);
+    // xhat = ((v + bias) - mean) * rstd and y = xhat * g + beta in the forward pass's operation order: the ReLU decision
+    // recomputed here is bit-identical to the one the forward pass took
+    const float2 nm = bc2(-mean), rs = bc2(rstd);
+    const float2 xh_lo = mul2(add2(add2(make_float2(v.x, v.y), bias_lo), nm), rs);
+    const float2 xh_hi = mul2(add2(add2(make_float2(v.z, v.w), bias_hi), nm), rs);
+    const float2 y_lo = fma2(xh_lo, g_lo, be_lo), y_hi = fma2(xh_hi, g_hi, be_hi);
+    float2 f_lo = make_float2(act_grad_fast(act, y_lo.x), act_grad_fast(act, y_lo.y));
+    float2 f_hi = make_float2(act_grad_fast(act, y_hi.x), act_grad_fast(act, y_hi.y));
+    if (drop) {
+      float ds[4];
+      dropout_scale4(d.drop_p, d.drop_seed, static_cast<unsigned long long>(row) * d.width + c, ds);
+      f_lo = mul2(f_lo, make_float2(ds[0], ds[1]));
+      f_hi = mul2(f_hi, make_float2(ds[2], ds[3]));
     }
-    s1 = warp_sum_f(s1);
-    s2 = warp_sum_f(s2);
-    if (lane == 0) red[par][warp] = make_float2(s1, s2);
+    const float2 dy_lo = mul2(make_float2(go.x, go.y), f_lo), dy_hi = mul2(make_float2(go.z, go.w), f_hi);
+    const float2 dx_lo = mul2(dy_lo, g_lo), dx_hi = mul2(dy_hi, g_hi);
+    const float2 t1 = add2(dx_lo, dx_hi), t2 = fma2(dx_hi, xh_hi, mul2(dx_lo, xh_lo));
+    // the two row sums together: lanes < 16 end up with s1, lanes >= 16 with s2 (one exchange, then a 16-lane butterfly)
+    float s1 = t1.x + t1.y, s2 = t2.x + t2.y;
+    {
+      const bool upper = lane >= 16;
+      const float give = upper ? s1 : s2, keep = upper ? s2 : s1;
+      float r = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+      if (lane == 0) red[par][warp].x = r;
+      if (lane == 16) red[par][warp].y = r;
+    }
     __syncthreads();                     // also: every thread has read slot s, thread 0 may refill it next iteration
     const float2 pr = red[par][lane];
     const float c1 = warp_sum_f(pr.x) * (1.0f / 4096.f), c2 = warp_sum_f(pr.y) * (1.0f / 4096.f);
-    float dv[4];
-    float amax = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      dv[q] = rstd * (dy[q] * gg[q] - c1 - xh[q] * c2);
-      amax = fmaxf(amax, fabsf(dv[q]));
-    }
+    // dv = rstd * (dy * g - c1 - xhat * c2)
+    const float2 rc1 = bc2(-rstd * c1), rc2 = bc2(-rstd * c2);
+    const float2 dv_lo = fma2(dx_lo, rs, fma2(xh_lo, rc2, rc1)), dv_hi = fma2(dx_hi, rs, fma2(xh_hi, rc2, rc1));
     if (dvh.p) {                                       // row-scaled fp16 copy for the data-gradient contraction
+      float amax = fmaxf(fmaxf(fabsf(dv_lo.x), fabsf(dv_lo.y)), fmaxf(fabsf(dv_hi.x), fabsf(dv_hi.y)));
       amax = warp_max_f(amax);
       if (lane == 0) redm[par][warp] = amax;
       __syncthreads();
       const float sc = row_scale_pow2(warp_max_f(redm[par][lane]));
       if (tid == 0) dvh.inv_scale[row] = 1.f / sc;
-      store_half4(dvh.p, static_cast<long long>(row) * d.width + c, dv[0] * sc, dv[1] * sc, dv[2] * sc, dv[3] * sc);
+      const float2 h_lo = mul2(dv_lo, bc2(sc)), h_hi = mul2(dv_hi, bc2(sc));
+      store_half4(dvh.p, static_cast<long long>(row) * d.width + c, h_lo.x, h_lo.y, h_hi.x, h_hi.y);
     }
-    store_planes4(dvp, static_cast<long long>(row) * d.width + c, make_float4(dv[0], dv[1], dv[2], dv[3]));
-    a_g.x = fmaf(dy[0], xh[0], a_g.x); a_g.y = fmaf(dy[1], xh[1], a_g.y);
-    a_g.z = fmaf(dy[2], xh[2], a_g.z); a_g.w = fmaf(dy[3], xh[3], a_g.w);
-    a_b.x += dy[0]; a_b.y += dy[1]; a_b.z += dy[2]; a_b.w += dy[3];
-    a_bias.x += dv[0]; a_bias.y += dv[1]; a_bias.z += dv[2]; a_bias.w += dv[3];
+    store_planes4(dvp, static_cast<long long>(row) * d.width + c, make_float4(dv_lo.x, dv_lo.y, dv_hi.x, dv_hi.y));
+    a_g_lo = fma2(dy_lo, xh_lo, a_g_lo);
+    a_g_hi = fma2(dy_hi, xh_hi, a_g_hi);
+    a_b_lo = add2(a_b_lo, dy_lo);
+    a_b_hi = add2(a_b_hi, dy_hi);
+    a_bias_lo = add2(a_bias_lo, dv_lo);
+    a_bias_hi = add2(a_bias_hi, dv_hi);
   }
-  atomicAdd(reinterpret_cast<float4*>(d_ln_g + c), a_g);
-  atomicAdd(reinterpret_cast<float4*>(d_ln_b + c), a_b);
-  atomicAdd(reinterpret_cast<float4*>(d_bias + c), a_bias);
+  atomicAdd(reinterpret_cast<float4*>(d_ln_g + c), make_float4(a_g_lo.x, a_g_lo.y, a_g_hi.x, a_g_hi.y));
+  atomicAdd(reinterpret_cast<float4*>(d_ln_b + c), make_float4(a_b_lo.x, a_b_lo.y, a_b_hi.x, a_b_hi.y));
+  atomicAdd(reinterpret_cast<float4*>(d_bias + c), make_float4(a_bias_lo.x, a_bias_lo.y, a_bias_hi.x, a_bias_hi.y));
 }
 
 // Backward rows for the wide LN_BIAS stages (4096, 1024*M): persistent blocks of width/16 threads, four float4 per
@@ -1241,6 +1256,41 @@ __global__ void __launch_bounds__(256) gru_forward_kernel(int rows, int H, const
   const float h = (hp - n) * z + n;
   h_new[idx] = h;
   store_op1(hp_out, idx, h);
+}
+
+// The same for four consecutive hidden units per thread (H % 4 == 0): 16-byte accesses, one row/column split per four
+// elements, gate arithmetic per element exactly as above (the backward pass recomputes the gates with the same formulas).
+template <int PCFG>
+__global__ void __launch_bounds__(256) gru_forward4_kernel(int rows, int H, const float* __restrict__ gi,
+                                                           const float* __restrict__ gh, const float* __restrict__ b_ih,
+                                                           const float* __restrict__ b_hh,
+                                                           const float* __restrict__ h_prev, float* __restrict__ h_new,
+                                                           Op hp_out) {
+  const int h4 = H >> 2;
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= static_cast<long long>(rows) * h4) return;
+  const int row = static_cast<int>(q / h4), j = static_cast<int>(q - static_cast<long long>(row) * h4) * 4;
+  const long long g0 = static_cast<long long>(row) * 3 * H + j, idx = static_cast<long long>(row) * H + j;
+  const float4 ir = ld4(gi + g0), iz = ld4(gi + g0 + H), in_ = ld4(gi + g0 + 2 * H);
+  const float4 hr = ld4(gh + g0), hz = ld4(gh + g0 + H), hn = ld4(gh + g0 + 2 * H);
+  const float4 bir = ld4(b_ih + j), biz = ld4(b_ih + H + j), bin = ld4(b_ih + 2 * H + j);
+  const float4 bhr = ld4(b_hh + j), bhz = ld4(b_hh + H + j), bhn = ld4(b_hh + 2 * H + j);
+  const float4 hp = ld4(h_prev + idx);
+  const float a_ir[4] = {ir.x, ir.y, ir.z, ir.w}, a_iz[4] = {iz.x, iz.y, iz.z, iz.w}, a_in[4] = {in_.x, in_.y, in_.z, in_.w};
+  const float a_hr[4] = {hr.x, hr.y, hr.z, hr.w}, a_hz[4] = {hz.x, hz.y, hz.z, hz.w}, a_hn[4] = {hn.x, hn.y, hn.z, hn.w};
+  const float c_ir[4] = {bir.x, bir.y, bir.z, bir.w}, c_iz[4] = {biz.x, biz.y, biz.z, biz.w}, c_in[4] = {bin.x, bin.y, bin.z, bin.w};
+  const float c_hr[4] = {bhr.x, bhr.y, bhr.z, bhr.w}, c_hz[4] = {bhz.x, bhz.y, bhz.z, bhz.w}, c_hn[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
+  const float a_hp[4] = {hp.x, hp.y, hp.z, hp.w};
+  float h[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float r = sigmoidf_((a_ir[e] + c_ir[e]) + (a_hr[e] + c_hr[e]));
+    const float z = sigmoidf_((a_iz[e] + c_iz[e]) + (a_hz[e] + c_hz[e]));
+    const float n = tanhf((a_in[e] + c_in[e]) + r * (a_hn[e] + c_hn[e]));
+    h[e] = (a_hp[e] - n) * z + n;
+  }
+  *reinterpret_cast<float4*>(h_new + idx) = make_float4(h[0], h[1], h[2], h[3]);
+  store_cfg4p<PCFG>(hp_out, idx, make_float2(h[0], h[1]), make_float2(h[2], h[3]));
 }
 
 // GRU backward.  Persistent blocks of H/4 threads, thread t owns hidden units 4t..4t+3 of every row it sees (the six
@@ -2056,8 +2106,20 @@ int gru_forward(int rows, int H, const float* gi, const float* gh, const float* 
                 const float* h_prev, float* h_new, const Op& hp, cudaStream_t stream) {
   VMM_REQUIRE(rows > 0 && H > 0 && gi && gh && b_ih && b_hh && h_prev && h_new && hp.f.n >= 1, "gru_forward: bad argument");
   const long long n = static_cast<long long>(rows) * H;
-  gru_forward_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, h_new,
-                                                                                 hp);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(gi) | reinterpret_cast<uintptr_t>(gh) | reinterpret_cast<uintptr_t>(b_ih) |
+                       reinterpret_cast<uintptr_t>(b_hh) | reinterpret_cast<uintptr_t>(h_prev) | reinterpret_cast<uintptr_t>(h_new);
+  if (H % 4 == 0 && (al & 15) == 0) {              // four hidden units per thread, 16-byte accesses
+    const unsigned blocks = static_cast<unsigned>((n / 4 + 255) / 256);
+    switch (plane_cfg(hp)) {
+      case 21: gru_forward4_kernel<21><<<blocks, 256, 0, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, h_new, hp); break;
+      case 22: gru_forward4_kernel<22><<<blocks, 256, 0, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, h_new, hp); break;
+      case 10: gru_forward4_kernel<10><<<blocks, 256, 0, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, h_new, hp); break;
+      default: gru_forward4_kernel<0><<<blocks, 256, 0, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, h_new, hp); break;
+    }
+  } else {
+    gru_forward_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(rows, H, gi, gh, b_ih, b_hh, h_prev, h_new,
+                                                                                   hp);
+  }
   VMM_LAUNCHED();
   return 0;
 }
