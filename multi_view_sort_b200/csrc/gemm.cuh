@@ -269,28 +269,32 @@ __device__ __forceinline__ void delta_tile_acquire(int cur, int last, int lane) 
   __syncwarp();
 }
 
-// E-step chunk, fast form (all 32 columns inside N, no loss sums - every iteration but the last): per element one
+// E-step chunk, fast form (all 32 columns inside N; kSq: also the sum of delta^2 the last iteration's loss needs; a launch
+// that wants the sum of pred^2 takes the general form below): per element one
 // subtraction, two multiplications, one ex2 and one addition (+ one max with kDmax); delta goes straight from the
 // registers into the warp's delta tile, which one TMA store writes while the warp moves on.  kSave: 0 none, 2 fp32.
-template <int kSave, bool kDmax>
+template <int kSave, bool kDmax, bool kSq>
 __device__ __forceinline__ void estep_fast_chunk(const GemmParams& p, const uint32_t (&v)[32], const float4* stx, float4* sto,
                                                  int lane, int row0, int col0, int cur_sto, int& last_sto, float& sum_e,
-                                                 float& dmax) {
+                                                 float& sum_sq, float& dmax) {
   if constexpr (kSave == 2) delta_tile_acquire(cur_sto, last_sto, lane);
-  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 xv = stx[st_slot(lane, j)];
     const float d0 = xv.x - __uint_as_float(v[4 * j]), d1 = xv.y - __uint_as_float(v[4 * j + 1]);
     const float d2 = xv.z - __uint_as_float(v[4 * j + 2]), d3 = xv.w - __uint_as_float(v[4 * j + 3]);
-    s[0] += ex2_approx(d0 * d0 * p.exp_scale);
-    s[1] += ex2_approx(d1 * d1 * p.exp_scale);
-    s[2] += ex2_approx(d2 * d2 * p.exp_scale);
-    s[3] += ex2_approx(d3 * d3 * p.exp_scale);
+    const float dd0 = d0 * d0, dd1 = d1 * d1, dd2 = d2 * d2, dd3 = d3 * d3;
+    s[0] += ex2_approx(dd0 * p.exp_scale);
+    s[1] += ex2_approx(dd1 * p.exp_scale);
+    s[2] += ex2_approx(dd2 * p.exp_scale);
+    s[3] += ex2_approx(dd3 * p.exp_scale);
+    if constexpr (kSq) { q[0] += dd0; q[1] += dd1; q[2] += dd2; q[3] += dd3; }
     if constexpr (kDmax) dmax = fmaxf(fmaxf(dmax, fmaxf(fabsf(d0), fabsf(d1))), fmaxf(fabsf(d2), fabsf(d3)));
     if constexpr (kSave == 2) sto[st_slot(lane, j)] = make_float4(d0, d1, d2, d3);
   }
   sum_e += (s[0] + s[1]) + (s[2] + s[3]);
+  if constexpr (kSq) sum_sq += (q[0] + q[1]) + (q[2] + q[3]);
   if constexpr (kSave == 2) {
     fence_proxy_async();
     __syncwarp();
@@ -631,15 +635,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             const int csto = kEpiBufs >= 3 ? (c & 1) : 0;          // delta tile of this chunk
             float4* sto = csto ? sto1 : sto0;
             bool fast = false;                                       // warp-uniform
-            if constexpr (kXBias) fast = (col0 + 32 <= p.N) && !want_sq && !(p.part_pp != nullptr);
+            if constexpr (kXBias) fast = (col0 + 32 <= p.N) && p.part_pp == nullptr;
             if (fast) x_stage_sub<XT>(xc, st, lane);
             else x_stage<XT>(xc, st, lane);
             if (c + XPF < NCH) x_fetch<XT, kXBias>(p, xc, xrows, col0 + 32 * XPF, lane);
             __syncwarp();
             if (fast) {
               if constexpr (kXBias) {
-                if (want_dmax) estep_fast_chunk<kSave, true>(p, v, st, sto, lane, row0, col0, csto, last_sto, sum_e, dmax);
-                else estep_fast_chunk<kSave, false>(p, v, st, sto, lane, row0, col0, csto, last_sto, sum_e, dmax);
+                if (want_sq) {
+                  if (want_dmax) estep_fast_chunk<kSave, true, true>(p, v, st, sto, lane, row0, col0, csto, last_sto, sum_e, sum_sq, dmax);
+                  else estep_fast_chunk<kSave, false, true>(p, v, st, sto, lane, row0, col0, csto, last_sto, sum_e, sum_sq, dmax);
+                } else {
+                  if (want_dmax) estep_fast_chunk<kSave, true, false>(p, v, st, sto, lane, row0, col0, csto, last_sto, sum_e, sum_sq, dmax);
+                  else estep_fast_chunk<kSave, false, false>(p, v, st, sto, lane, row0, col0, csto, last_sto, sum_e, sum_sq, dmax);
+                }
               }
             } else {
             float out[32];

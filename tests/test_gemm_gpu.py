@@ -188,7 +188,12 @@ def test_estep_saved_delta_backward(B, K, Mv, D, zk, ddt, out_planes, xdt, use_k
     pe0, psq0, _ = ops.estep_forward(zp, wp, b3, x, K, Mv, sigma, want_sq=True)
     pe, psq, delta = ops.estep_forward_save(zp, wp, b3, x, K, Mv, sigma, delta_dtype=ddt)
     torch.cuda.synchronize()
-    assert torch.equal(pe, pe0) and torch.equal(psq, psq0)          # saving delta does not change the E-step sums
+    # saving delta does not change the E-step sums: bit-identical when both launches run the same chunk body (fp32 delta:
+    # the fast chunk), equal up to fp32 summation order when the fp16-delta launch takes the general body
+    if ddt == torch.float32:
+        assert torch.equal(pe, pe0) and torch.equal(psq, psq0)
+    else:
+        assert _relmax(pe, pe0) < 2e-6 and _relmax(psq, psq0) < 2e-6
     zq = zp[0].double() + zp[1].double() / 2048
     wq = wp[0].double() + wp[1].double() / 2048
     pred, d, e = _estep_ref(zq, wq, b3, x.float(), K, Mv, sigma)
