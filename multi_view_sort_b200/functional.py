@@ -325,7 +325,8 @@ def run_em(module, x: torch.Tensor, iters: int, gamma0: Optional[torch.Tensor] =
     B = x.shape[0]
     dev = x.device
     if gamma0 is None or (gamma_prior is None and module.if_gamma_prior != 0):
-        _, _, g0, gp = module.init_state(x.shape, x)
+        assert x.shape[1] == module.m, "number of view dose not match"
+        g0, gp = module.init_gamma(B, dev)               # init_state's gamma / gamma_prior without its h and pred buffers
         gamma0 = g0 if gamma0 is None else gamma0
         gamma_prior = gp if gamma_prior is None else gamma_prior
     gamma0 = gamma0.to(dev, torch.float32).reshape(B, module.k, module.m).contiguous()

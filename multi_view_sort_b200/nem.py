@@ -95,6 +95,27 @@ class NEM(Model):
         gamma_prior = p.view(1, k, m, 1).repeat(B, 1, 1, 1).to(dev)
         return h, pred, gamma, gamma_prior
 
+    def init_gamma(self, B, dev):
+        """The (gamma, gamma_prior) of init_state as (B, K, M) float32 tensors on `dev`, without the h and pred buffers
+        the fused loop never reads (pred alone is B*K*M*D floats: 2.4 GB at configs[1]).  For the deterministic init
+        types the (K, M) tables live on the device and are expanded there: no host->device copy per call."""
+        k, m = self.k, self.m
+        if k > 1 and self.init_type == 'rand':                       # one host draw per call, like the reference
+            gamma = torch.rand([B, k, m, 1])
+            gamma = (gamma / gamma.sum(1).unsqueeze(1)).to(dev).view(B, k, m)
+            return gamma, gamma
+        if k == 1 or self.init_type == 'bin_uniform':
+            key = (k, m, self.init_type, str(dev))
+            cached = self.__dict__.get("_vmm_view_tables")
+            if cached is None or cached[0] != key:
+                g, p = self.view_tables()
+                cached = (key, g.to(dev), p.to(dev))
+                self.__dict__["_vmm_view_tables"] = cached
+            g, p = cached[1], cached[2]
+        else:                                                        # 'bin_rand': python's RNG, drawn per call
+            g, p = (t.to(dev) for t in self.view_tables())
+        return g.view(1, k, m).expand(B, k, m).contiguous(), p.view(1, k, m).expand(B, k, m).contiguous()
+
     # -- compute ---------------------------------------------------------------------------
     def invalidate_weights(self):
         """Drop the cached operand planes of the weights.  Needed only after changing parameter VALUES in a way

@@ -61,11 +61,11 @@ def test_grad_arena_single_rank():
     for p, g in zip(params, plain):
         if g is None:
             assert p.grad is None
-        else:
-            assert torch.allclose(p.grad, g, rtol=1e-5, atol=1e-8)
+        else:                                                # two runs: equal up to the order of the reduce-adds
+            assert ((p.grad - g).abs().max() / g.abs().max().clamp_min(1e-30)).item() < 1e-5
     inside = [p for p in nem.parameters() if p.grad is not None and arena.data_ptr() <= p.grad.data_ptr() < arena.data_ptr() + arena.numel() * 4]
     assert len(inside) == 22
     step()                                                   # .grad is set: plain accumulation, no aliasing
     for p, g in zip(params, plain):
         if g is not None:
-            assert torch.allclose(p.grad, 2 * g, rtol=1e-4, atol=1e-8)
+            assert ((p.grad - 2 * g).abs().max() / g.abs().max().clamp_min(1e-30)).item() < 1e-4

@@ -30,3 +30,15 @@ for ev in prof.events():
 print(f"B={B} {prec}: total device kernel time {tot:.1f} ms")
 for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
     print(f"{ms:9.2f} ms {100*ms/tot:5.1f}%  x{c:4d}  {k[:100]}")
+# idle time between kernels of the profiled step (CUPTI timestamps): what a dependent-launch scheme could hide at most
+evs = sorted([(ev.time_range.start, ev.time_range.end, ev.name) for ev in prof.events()
+              if ev.device_type == torch.autograd.DeviceType.CUDA and ev.time_range.end > ev.time_range.start], key=lambda t: t[0])
+if evs:
+    span = (evs[-1][1] - evs[0][0]) / 1e3
+    gaps = [(evs[i + 1][0] - max(e[1] for e in evs[max(0, i - 3):i + 1])) / 1e3 for i in range(len(evs) - 1)]
+    pos = [g for g in gaps if g > 0]
+    print(f"span first kernel start .. last kernel end {span:.1f} ms; idle between kernels {sum(pos):.2f} ms over {len(pos)} gaps "
+          f"(median {sorted(pos)[len(pos) // 2] * 1e3:.1f} us, max {max(pos) * 1e3:.0f} us)")
+    big = sorted(((g, evs[i][2], evs[i + 1][2]) for i, g in enumerate(gaps) if g > 0.02), reverse=True)[:8]
+    for g, a, b in big:
+        print(f"   {g * 1e3:7.0f} us between {a[:50]} -> {b[:50]}")
