@@ -69,3 +69,31 @@ def test_grad_arena_single_rank():
     for p, g in zip(params, plain):
         if g is not None:
             assert ((p.grad - 2 * g).abs().max() / g.abs().max().clamp_min(1e-30)).item() < 1e-4
+
+
+def test_cli_trains_under_torchrun(tmp_path):
+    """The reference's command line under torchrun on 2 GPUs: DistributedSampler shards, gradient arenas attached by the
+    trainer, NCCL exchange, rank-0 logging / checkpoints, all-reduced validation counters.  Needs 2 GPUs (NCCL)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import glob
+    import json
+    sys.path.insert(0, HERE)
+    from test_features import make_store
+    train_root = make_store(str(tmp_path / "train"), "MNet10", per_class=6, M=12, D=4096, seed=1)
+    val_root = make_store(str(tmp_path / "val"), "MNet10", per_class=3, M=12, D=4096, seed=2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), "-m", "multi_view_sort_b200.train_nem", "-name", "run2", "-dataset", "MNet10",
+           "-cluster_n", "3", "-iter", "2", "-bs", "4", "-train_path", train_root, "-val_path", val_root, "-precision", "bf16",
+           "-epoch", "2"]
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(HERE) + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stdout[-3000:]
+    run = tmp_path / "run2"
+    assert json.load(open(run / "config.json"))["cluster_n"] == 3
+    assert glob.glob(str(run / "NEM" / "model-*.pth")) and glob.glob(str(run / "MV_C_Net" / "model-*.pth"))
+    scal = [json.loads(l) for l in open(run / "scalars.jsonl")]
+    losses = [s["value"] for s in scal if s["tag"] == "train/train_loss"]
+    assert len(losses) == 2 * 3 and all(v == v and abs(v) < 1e4 for v in losses)      # 24 objects / (2 ranks x 4) = 3 steps per epoch
+    val = [s["value"] for s in scal if s["tag"] == "val/val_overall_acc"]
+    assert len(val) == 2 and all(0.0 <= v <= 1.0 for v in val)
