@@ -127,6 +127,12 @@ VMM_API int vmm_gemm_rowscaled(int M, int N, int nseg, const vmm_gemm_seg* segs,
  * Process-wide; for tests and A/B timing. */
 VMM_API int vmm_gemm_force_ncta(int ncta);
 
+/* Tail split of the contraction kernels: the output tiles of a partial last wave are split along K so that every CTA
+ * shares them (their parts add into C; a store zeroes that part of C first).  mode -1 = only inside the backward entry
+ * points (default: forward results stay bit-identical under batch permutation and from run to run), 0 = never,
+ * 1 = every launch.  Process-wide; for tests and A/B timing. */
+VMM_API int vmm_gemm_tail_split(int mode);
+
 /* Same contract computed by a plain one-thread-per-output CUDA kernel (no tensor cores):
  * the on-device cross-check used by the GPU tests.  Not used by the product path. */
 VMM_API int vmm_gemm_check(int M, int N, int nseg, const vmm_gemm_seg* segs, int a_mn_major, int b_mn_major,

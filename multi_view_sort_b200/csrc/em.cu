@@ -784,6 +784,7 @@ int vmm_em_forward(const vmm_em_config* cfg, const vmm_em_params* params, const 
 int vmm_em_backward(const vmm_em_config* cfg, const vmm_em_params* params, const void* weights, const void* x,
                     const float* gamma0, const float* prior, const void* workspace, void* scratch, const float* d_h,
                     const float* d_gamma, const float* d_loss, const vmm_em_grads* grads, void* stream) {
+  vmm::BackwardScope backward;
   return vmm::em_backward(cfg, params, weights, x, gamma0, prior, workspace, scratch, d_h, d_gamma, d_loss, grads,
                           static_cast<cudaStream_t>(stream));
 }
@@ -802,6 +803,7 @@ int vmm_em_step_backward(const vmm_em_config* cfg, const vmm_em_params* params, 
                          const void* step_scratch, void* scratch, const float* d_h_out, const float* d_pred_out,
                          const float* d_gamma_out, const vmm_em_grads* grads, float* d_h_in, float* d_pred_in, float* d_gamma_in,
                          void* stream) {
+  vmm::BackwardScope backward;
   return vmm::em_step_backward(cfg, params, weights, x, h_in, pred_in, gamma_in, workspace, step_scratch, scratch, d_h_out,
                                d_pred_out, d_gamma_out, grads, d_h_in, d_pred_in, d_gamma_in, static_cast<cudaStream_t>(stream));
 }

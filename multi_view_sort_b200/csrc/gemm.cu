@@ -139,8 +139,7 @@ static int launch_one(const GemmParams& p, cudaStream_t stream) {
     }
     opted_in.fetch_or(bit, std::memory_order_release);
   }
-  const int units = ceil_div(p.num_m_blk, NCTA);
-  const int total_work = units * p.num_n_blk * p.splits;
+  const int total_work = p.total_work;
   const int workers = device_sm_count() / NCTA;
   const int grid = (total_work < workers ? total_work : workers) * NCTA;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -262,7 +261,75 @@ static int fill_common(GemmParams& p, int M, int N, int nseg, const vmm_gemm_seg
   p.chain_kb = chain;
   p.total_chains = ceil_div(nkb_max, chain);
   p.splits = want < p.total_chains ? want : p.total_chains;
+  p.total_work = ceil_div(p.num_m_blk, ncta) * p.num_n_blk * p.splits;
   return 0;
+}
+
+// (m unit, n block) of output tile `tile` in the kernel's rasterisation (decode_work): groups of GROUP_M / ncta m units,
+// m fastest inside a group.
+static void tile_coords(const GemmParams& p, int tile, int ncta, int* m_unit, int* n_blk, int* group_first, int* group_size) {
+  const int units = ceil_div(p.num_m_blk, ncta);
+  const int group_m = GROUP_M / ncta;
+  const int per_group = group_m * p.num_n_blk;
+  const int group = tile / per_group;
+  const int first_m = group * group_m;
+  const int gsize = units - first_m < group_m ? units - first_m : group_m;
+  const int in_group = tile - group * per_group;
+  *m_unit = first_m + in_group % gsize;
+  *n_blk = in_group / gsize;
+  *group_first = first_m;
+  *group_size = gsize;
+}
+
+// Tail split (GemmParams::tail_*): when the tile count leaves a partial last wave that at most half of the workers would
+// work on, split those tiles along K so that the whole machine shares them (backward passes only, see BackwardScope:
+// measured -1 % of the step; the forward contractions gain nothing - they sit at the power cap - and would lose their
+// bit-reproducibility).  EPI_STORE: the parts add into C, so the
+// rectangle of C that holds the tail tiles is zeroed first (it may also cover earlier tiles of the same rows, which
+// plain-store over the zeros) - returned through `zero_*` for the caller to memset.  Off for launches that already
+// split K, for the non-TMA store path, and when fewer than 8 k-blocks per part would be left.
+// -1: inside backward passes only (default); 0: never; 1: every launch (tests, A/B timing; VMM_TAIL_SPLIT overrides)
+static std::atomic<int> g_tail_mode{getenv("VMM_TAIL_SPLIT") ? (getenv("VMM_TAIL_SPLIT")[0] == '0' ? 0 : 1) : -1};
+static thread_local int g_backward_depth = 0;
+BackwardScope::BackwardScope() { ++g_backward_depth; }
+BackwardScope::~BackwardScope() { --g_backward_depth; }
+static void plan_tail_split(GemmParams& p, int nkb_max, bool store, int* zero_row0, int* zero_rows, int* zero_col0) {
+  *zero_rows = 0;
+  const int mode = g_tail_mode.load(std::memory_order_relaxed);
+  if (mode == 0 || (mode < 0 && g_backward_depth == 0) || p.splits != 1 || (store && !p.tma_c)) return;
+  const int ncta = pick_ncta(p);
+  const int workers = device_sm_count() / ncta;
+  const int tiles = ceil_div(p.num_m_blk, ncta) * p.num_n_blk;
+  const int tail = tiles % workers;
+  if (tiles <= workers || tail == 0 || tail * 2 > workers) return;
+  int s = workers / tail;
+  if (s > 8) s = 8;
+  if (s > nkb_max / 8) s = nkb_max / 8;
+  if (s < 2) return;
+  const int first = tiles - tail;
+  if (store) {
+    // all tail tiles must lie in ONE rasterisation group: then they are the tiles (m in group, n >= n0) plus part of
+    // column n0, and the rectangle rows(group) x columns [n0 * BN, N) covers them
+    int m0, n0, gf0, gs0, m1, n1, gf1, gs1;
+    tile_coords(p, first, ncta, &m0, &n0, &gf0, &gs0);
+    tile_coords(p, tiles - 1, ncta, &m1, &n1, &gf1, &gs1);
+    if (gf0 != gf1) return;
+    *zero_row0 = gf0 * ncta * BM;
+    const int row_end = (gf0 + gs0) * ncta * BM < p.M ? (gf0 + gs0) * ncta * BM : p.M;
+    *zero_rows = row_end - *zero_row0;
+    *zero_col0 = n0 * 256;
+  }
+  p.tail_first = first;
+  p.tail_splits = s;
+  if (p.total_chains >= s) {
+    p.tail_chain_kb = p.chain_kb;
+    p.tail_total_chains = p.total_chains;
+  } else {
+    p.tail_chain_kb = ceil_div(nkb_max, s);
+    p.tail_total_chains = ceil_div(nkb_max, p.tail_chain_kb);
+    if (p.tail_total_chains < s) p.tail_splits = p.tail_total_chains;
+  }
+  p.total_work = first + tail * p.tail_splits;
 }
 
 int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool b_mn, float* C, long long ldc,
@@ -281,7 +348,14 @@ int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool 
   static const bool tma_epilogue = !(getenv("VMM_TMA_EPILOGUE") && getenv("VMM_TMA_EPILOGUE")[0] == '0');   // A/B switch
   p.tma_c = (tma_epilogue && p.vec_ok && N % 4 == 0) ? 1 : 0;
   if (p.tma_c) VMM_TRY(make_tmap_f32_store(&p.tma_out, C, N, M, ldc));
+  int nkb_max = 0;
+  for (int s = 0; s < nseg; ++s) nkb_max = p.seg_kb[s] > nkb_max ? p.seg_kb[s] : nkb_max;
+  int zr0 = 0, zrows = 0, zc0 = 0;
+  plan_tail_split(p, nkb_max, !accumulate, &zr0, &zrows, &zc0);
   if (accumulate) return launch_major<EPI_RED, float, 1>(p, a_mn, b_mn, stream);
+  if (zrows > 0)
+    VMM_CHECK_CUDA(cudaMemset2DAsync(C + static_cast<long long>(zr0) * ldc + zc0, static_cast<size_t>(ldc) * 4, 0,
+                                     static_cast<size_t>(N - zc0) * 4, static_cast<size_t>(zrows), stream));
   return launch_major<EPI_STORE, float, 1>(p, a_mn, b_mn, stream);
 }
 
@@ -489,6 +563,11 @@ long long vmm_launch_count(void) { return vmm::g_launches.load(); }
 
 int vmm_gemm_force_ncta(int ncta) {
   vmm::g_force_ncta.store(ncta == 1 || ncta == 2 ? ncta : 0);
+  return 0;
+}
+
+int vmm_gemm_tail_split(int mode) {
+  vmm::g_tail_mode.store(mode > 0 ? 1 : (mode == 0 ? 0 : -1));
   return 0;
 }
 

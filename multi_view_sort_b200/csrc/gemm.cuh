@@ -65,6 +65,12 @@ struct alignas(64) GemmParams {
   int M, N;
   int num_m_blk, num_n_blk;
   int splits;
+  // Tail split: the last (tiles mod workers) output tiles - the partial wave that would otherwise leave most CTAs idle
+  // for a whole tile time - are split `tail_splits` ways along K (work items >= tail_first), each part covering a range
+  // of accumulation chains of `tail_chain_kb` k-blocks and adding into C (EPI_STORE: into a zeroed tile; the part that
+  // holds chain 0 adds the bias).  0 / 1 = off.
+  int tail_first, tail_splits, tail_chain_kb, tail_total_chains;
+  int total_work;            // work items of the launch (tiles * splits, or full tiles + tail parts)
   int vec_ok;                // C rows are 16-byte aligned -> float4 path
   int tma_c;                 // C is written through tma_out (TMA store / reduce-add of the staging tiles)
   float* C;
@@ -121,13 +127,30 @@ struct GemmCfg {
 // (first chain stores, later chains add: same CTA, same thread, same address - no atomics).
 struct WorkItem {
   int m_blk, n_blk, c0, c1;
+  int chain_kb;              // k-blocks per accumulation chain of this item
+  int part;                  // 1: one of several K parts of a tile (every chain adds into C)
 };
 
 // `ncta` consecutive m-blocks form one scheduling unit (the two CTAs of a pair take one each).
 __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work, int ncta, int rank) {
   WorkItem w;
-  const int tile = work / p.splits;
-  const int split = work - tile * p.splits;
+  int tile, split, nsplit, total_chains;
+  if (p.tail_splits > 1 && work >= p.tail_first) {
+    const int t = work - p.tail_first;
+    tile = p.tail_first + t / p.tail_splits;      // (splits == 1 whenever a tail split is planned)
+    split = t - (t / p.tail_splits) * p.tail_splits;
+    nsplit = p.tail_splits;
+    total_chains = p.tail_total_chains;
+    w.chain_kb = p.tail_chain_kb;
+    w.part = 1;
+  } else {
+    tile = work / p.splits;
+    split = work - tile * p.splits;
+    nsplit = p.splits;
+    total_chains = p.total_chains;
+    w.chain_kb = p.chain_kb;
+    w.part = p.splits > 1 ? 1 : 0;
+  }
   const int units = (p.num_m_blk + ncta - 1) / ncta;
   const int group_m = GROUP_M / ncta;
   const int per_group = group_m * p.num_n_blk;
@@ -137,8 +160,8 @@ __device__ __forceinline__ WorkItem decode_work(const GemmParams& p, int work, i
   const int in_group = tile - group * per_group;
   w.m_blk = (first_m + in_group % gsize) * ncta + rank;
   w.n_blk = in_group / gsize;
-  w.c0 = static_cast<int>((static_cast<long long>(p.total_chains) * split) / p.splits);
-  w.c1 = static_cast<int>((static_cast<long long>(p.total_chains) * (split + 1)) / p.splits);
+  w.c0 = static_cast<int>((static_cast<long long>(total_chains) * split) / nsplit);
+  w.c1 = static_cast<int>((static_cast<long long>(total_chains) * (split + 1)) / nsplit);
   return w;
 }
 
@@ -312,7 +335,8 @@ __device__ __forceinline__ void estep_fast_chunk(const GemmParams& p, const uint
 // STORE / RED: accumulator chunk -> staging (row per lane) -> coalesced 4-rows-per-instruction.
 template <int EPI>
 __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint32_t (&v)[32], float4* st, int row0,
-                                                int col0, int lane, bool add_to_c, bool& st_busy, int groups_per_chain) {
+                                                int col0, int lane, bool add_to_c, bool first_chain, bool& st_busy,
+                                                int groups_per_chain) {
   if (p.tma_c) {
     // TMA path: scale / bias in the row-per-lane layout, stage the 32x32 tile (its XOR swizzle IS the SWIZZLE_128B box
     // layout) and let ONE bulk tensor store - or reduce-add, for accumulation chains, split-K and gradient
@@ -330,7 +354,7 @@ __device__ __forceinline__ void epi_store_chunk(const GemmParams& p, const uint3
     }
     float rs = 1.f;
     if (p.row_scale && row0 + lane < p.M) rs = __ldg(p.row_scale + row0 + lane);
-    const bool add_bias = (EPI == EPI_STORE) && !add_to_c && p.bias != nullptr;
+    const bool add_bias = (EPI == EPI_STORE) && first_chain && p.bias != nullptr;   // once per output element
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4 val = make_float4(__uint_as_float(v[4 * j]) * rs, __uint_as_float(v[4 * j + 1]) * rs,
@@ -429,7 +453,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   const int rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;          // 0 = leader of the pair
   const int worker = NCTA == 2 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
   const int nworkers = NCTA == 2 ? static_cast<int>(cluster_count_x()) : static_cast<int>(gridDim.x);
-  const int total_work = ((p.num_m_blk + NCTA - 1) / NCTA) * p.num_n_blk * p.splits;
+  const int total_work = p.total_work;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -477,7 +501,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const int n0 = w.n_blk * BN + rank * Cfg::B_ROWS;       // first N row of this CTA's part of the B tile
         for (int ch = w.c0; ch < w.c1; ++ch)
         for (int seg = 0; seg < p.nseg; ++seg) {
-        const int k_lo = ch * p.chain_kb, k_hi = min(k_lo + p.chain_kb, p.seg_kb[seg]);
+        const int k_lo = ch * w.chain_kb, k_hi = min(k_lo + w.chain_kb, p.seg_kb[seg]);
         for (int kb = k_lo; kb < k_hi; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * NCTA);
@@ -515,7 +539,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
       bool first = true;
       for (int seg = 0; seg < p.nseg; ++seg) {
-      const int k_lo = ch * p.chain_kb, k_hi = min(k_lo + p.chain_kb, p.seg_kb[seg]);
+      const int k_lo = ch * w.chain_kb, k_hi = min(k_lo + w.chain_kb, p.seg_kb[seg]);
       const unsigned fl = p.seg_flags[seg];
       const uint32_t idesc = umma_idesc_16b(BM * NCTA, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, fl & 1u, (fl >> 1) & 1u);
       bool rescale = (fl & 4u) != 0;                     // fold the scaled low-order terms accumulated so far
@@ -629,7 +653,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr0 + static_cast<uint32_t>((c + 1) * 32), vn);
         if (col0 < p.N) {                                            // warp-uniform
           if constexpr (!kFused) {
-            epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0, st_busy, groups_per_chain);
+            epi_store_chunk<EPI>(p, v, st, row0, col0, lane, ch > 0 || w.part != 0, ch == 0, st_busy, groups_per_chain);
           } else {
             XRegs<XT>& xc = (XPF == 2 && (c & 1)) ? xb : xa;
             const int csto = kEpiBufs >= 3 ? (c & 1) : 0;          // delta tile of this chunk

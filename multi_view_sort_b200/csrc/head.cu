@@ -432,6 +432,7 @@ int vmm_head_forward(const vmm_head_config* cfg, const vmm_head_params* params, 
 int vmm_head_backward(const vmm_head_config* cfg, const vmm_head_params* params, const void* weights, const float* h,
                       const void* workspace, void* scratch, const float* d_logits, const float* d_descriptor,
                       const vmm_head_grads* grads, float* d_h, void* stream) {
+  vmm::BackwardScope backward;
   return vmm::head_backward(cfg, params, weights, h, workspace, scratch, d_logits, d_descriptor, grads, d_h,
                             static_cast<cudaStream_t>(stream));
 }

@@ -71,6 +71,15 @@ struct Bump {
 // Cross terms A_i B_j with i + j < max(na, nb), least significant first.  Returns the count.
 int make_segs(vmm_gemm_seg* s, const Planes& a, long long lda, const Planes& b, long long ldb, long long k);
 
+// Backward passes run inside a BackwardScope: contraction launches of the calling thread may then split the tiles of a
+// partial last wave along K (gemm.cu: plan_tail_split).  Forward launches never do: their results stay bit-identical
+// under a permutation of the batch and from run to run (the backward pass accumulates with atomics anyway).
+struct BackwardScope {
+  BackwardScope();
+  ~BackwardScope();
+  BackwardScope(const BackwardScope&) = delete;
+  BackwardScope& operator=(const BackwardScope&) = delete;
+};
 int gemm_bf16(int M, int N, int nseg, const vmm_gemm_seg* segs, bool a_mn, bool b_mn, float* C, long long ldc,
               const float* bias, bool accumulate, int splits, int chain_kb, cudaStream_t stream,
               const float* row_scale = nullptr);   // row_scale[m] multiplies output row m (un-scales a row-scaled A)

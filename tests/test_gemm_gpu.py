@@ -293,3 +293,51 @@ def test_gemm_row_scaled_fp16_operand(accumulate):
     err = ((out.double() - ref).abs() / ref.abs().amax(1, keepdim=True).clamp_min(1e-300)).max().item()
     assert err < 2e-5, err                                                             # per ROW: every row keeps its precision
     assert _relmax(out.double() - (C0.double() if accumulate else 0), A.double() @ W.double()) < 2e-3   # vs the fp32 operands
+
+
+@pytest.mark.parametrize("M,N,K", [(2560, 2304, 2048), (12288, 4096, 1024), (2560, 2304 + 40, 2048 + 72)])
+@pytest.mark.parametrize("mode", ["store_bias", "store_chain4", "accumulate", "mn_store", "planes2", "rowscale"])
+def test_gemm_tail_split(M, N, K, mode):
+    """Shapes whose tile count leaves a partial last wave (90 tiles / 768 tiles on 74 CTA pairs): the tail tiles are
+    split along K (GemmParams::tail_*), by chain ranges when the launch has enough accumulation chains and by shorter
+    chains otherwise; stores add into a zeroed rectangle of C, the bias is added once.  Against fp32 matmul of the
+    same bf16 operands."""
+    from multi_view_sort_b200 import ops
+    from multi_view_sort_b200._lib import lib
+    lib().vmm_gemm_tail_split(1)              # every launch (the default confines it to the backward entry points)
+    try:
+        _tail_split_case(ops, M, N, K, mode)
+    finally:
+        lib().vmm_gemm_tail_split(-1)
+
+
+def _tail_split_case(ops, M, N, K, mode):
+    A, B = _rand((M, K), 70).bfloat16(), _rand((N, K), 71, 0.05).bfloat16()
+    ref = A.double() @ B.double().t()
+    if mode == "store_bias":
+        bias = _rand((N,), 72)
+        out = torch.full((M, N), 7.0, device="cuda")          # stale contents must not leak into the zeroed rectangle
+        ops.gemm([(A, B)], bias=bias, out=out)
+        ref = ref + bias.double()
+    elif mode == "store_chain4":
+        out = ops.gemm([(A, B)], chain=4)
+    elif mode == "accumulate":
+        out = _rand((M, N), 73)
+        ref = ref + out.double()
+        ops.gemm([(A, B)], out=out, accumulate=True)
+    elif mode == "mn_store":
+        out = ops.gemm([(A.t().contiguous(), B.t().contiguous())], True, True)
+    elif mode == "planes2":
+        A32, B32 = _rand((M, K), 70), _rand((N, K), 71, 0.05)
+        ap, bp = ops.split_planes(A32, 2), ops.split_planes(B32, 2)
+        out = ops.gemm(ops.plane_pairs(ap, bp), chain=16)
+        ref = A32.double() @ B32.double().t()
+        torch.cuda.synchronize()
+        assert _relmax(out, ref) < 3e-5
+        return
+    else:
+        rs = torch.rand(M, device="cuda") + 0.5
+        out = ops.gemm([(A, B)], row_scale=rs)
+        ref = ref * rs.double().view(-1, 1)
+    torch.cuda.synchronize()
+    assert _relmax(out, ref) < 2e-5, mode

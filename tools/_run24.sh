@@ -1,0 +1,5 @@
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -2
+for i in 1 2; do
+timeout 600 python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('default(bwd tail)', round(d['value']), round(d['ms_per_step'],2), d['clocks']['sm_mhz'])"
+VMM_TAIL_SPLIT=0 timeout 600 python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('notail           ', round(d['value']), round(d['ms_per_step'],2), d['clocks']['sm_mhz'])"
+done
